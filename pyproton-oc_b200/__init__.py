@@ -1,0 +1,11 @@
+"""protonoc-b200: the B200-native crime / recruitment hot path of PyPROTON-OC.
+
+Host side in Python (as the reference is), hand-written sm_100a CUDA kernels behind the C ABI declared
+in include/protonoc_b200.h.  There is no CPU fallback."""
+from . import tables  # noqa: F401
+from ._cabi import PocError, build  # noqa: F401
+from .params import HOT_PATH_DEFAULTS, make_params  # noqa: F401
+from .engine import CrimeEngine, LAYER_NAMES, REPORTER_NAMES  # noqa: F401
+
+__all__ = ["CrimeEngine", "make_params", "HOT_PATH_DEFAULTS", "PocError", "build", "tables", "LAYER_NAMES",
+           "REPORTER_NAMES"]

@@ -1,0 +1,787 @@
+// poc_api.cu -- C ABI (include/protonoc_b200.h) over the kernels in poc_kernels.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -shared -Xcompiler -fPIC
+//        (--fmad=false: candidate keys, tendencies and CDFs must equal CPython's left-to-right float64
+//         arithmetic bit for bit, so no multiply-add contraction anywhere.)
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "poc_kernels.cuh"
+
+#define N_TIMERS 8
+enum { TM_CELLS = 0, TM_TENDENCY, TM_DRAW, TM_SEARCH, TM_EMB, TM_COMMIT, TM_ARREST, TM_OTHER };
+#define EV_POOL 32768
+
+struct poc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevCtx d{};
+    std::vector<void *> allocs;
+    std::vector<poc_params> h_params;
+    std::vector<int> h_nagents;
+    std::string err;
+    int sticky = 0;
+    int epoch = 0;
+    int gx = 4;            // blocks per replica for the search / embeddedness grids
+    size_t smem_search = 0, smem_emb = 0;
+    // staging
+    StageCols stage{};
+    int32_t *st_rowptr[POC_NUM_LAYERS] = {};
+    int32_t *st_col = nullptr;      // all staged layers back to back
+    int32_t *st_co = nullptr;
+    long long st_off[POC_NUM_LAYERS + 1] = {};
+    int st_idx[POC_NUM_LAYERS] = {};  // layer -> position in the staging area
+    int st_have = 0;                // bitmask of layers staged for st_replica
+    int st_replica = -1;
+    int *d_err = nullptr;
+    int *d_prev_counters = nullptr;
+    int32_t *d_hook_a = nullptr, *d_hook_b = nullptr; double *d_hook_out = nullptr; long long hook_cap = 0;
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_class;
+    int ev_used = 0;
+    double tm_ms[N_TIMERS] = {};
+    long long tm_n[N_TIMERS] = {};
+    long long launches = 0;
+};
+
+static thread_local std::string g_err;
+
+static int fail(poc_ctx *c, int code, const std::string &msg) {
+    if (c) { c->err = msg; if (code == POC_ERR_CUDA) c->sticky = code; }
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+#define CHECK_CTX()                                                   \
+    do {                                                              \
+        if (!ctx) return POC_ERR_ARG;                                 \
+        if (ctx->sticky) return ctx->sticky;                          \
+        cudaSetDevice(ctx->device);                                   \
+    } while (0)
+
+template <typename T>
+static int dalloc(poc_ctx *ctx, T **p, size_t count) {
+    void *q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CU(cudaMalloc(&q, bytes));
+    CU(cudaMemsetAsync(q, 0, bytes, ctx->stream));
+    ctx->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+#define DA(ptr, count)                                 \
+    do {                                               \
+        int _r = dalloc(ctx, &(ptr), (size_t)(count)); \
+        if (_r) return _r;                             \
+    } while (0)
+
+struct Timed {
+    poc_ctx *c; int cls; int idx;
+    Timed(poc_ctx *c_, int cls_) : c(c_), cls(cls_), idx(-1) {
+        c->launches++;
+        if (c->timing && c->ev_used + 2 <= (int)c->ev.size()) {
+            idx = c->ev_used; c->ev_used += 2;
+            c->ev_class[idx] = cls;
+            cudaEventRecord(c->ev[idx], c->stream);
+        }
+    }
+    ~Timed() { if (idx >= 0) cudaEventRecord(c->ev[idx + 1], c->stream); }
+};
+
+extern "C" {
+
+int poc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *poc_last_error(poc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+int poc_sizeof_params(void) { return (int)sizeof(poc_params); }
+int poc_sizeof_tick_out(void) { return (int)sizeof(poc_tick_out); }
+
+int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_static_entries,
+                   int64_t max_criminal_entries, poc_ctx **out) {
+    if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 24) || max_static_entries < 0 || max_criminal_entries < 0)
+        return fail(nullptr, POC_ERR_ARG, "poc_ctx_create: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, POC_ERR_NOGPU, "poc_ctx_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, POC_ERR_ARG, "poc_ctx_create: bad device index");
+    poc_ctx *ctx = new poc_ctx();
+    ctx->device = device;
+    cudaSetDevice(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, cudaGetErrorString(e)); }
+    DevCtx &d = ctx->d;
+    int R = n_replicas, N = max_agents;
+    d.R = R; d.Ncap = N;
+    d.Ccap = N / 16 + 64;
+    d.Mcap = d.Ccap * 4 + 256;
+    int pc = 16384;
+    while (pc < d.Ccap * 8) pc <<= 1;
+    d.Pcap = pc;
+    d.ucap = std::max<long long>(max_static_entries, 1);
+    d.ccap = std::max<long long>(max_criminal_entries, 1);
+    d.Tcap = 1;
+    ctx->gx = std::max(4, std::min(64, 1184 / R));
+    d.scr_slots = R * ctx->gx;
+    size_t wcap = (size_t)(N + 31) / 32;
+    ctx->smem_search = 2 * wcap * sizeof(unsigned);
+    ctx->smem_emb = 2 * wcap * sizeof(unsigned);
+    if (ctx->smem_search + 40 * 1024 > 220 * 1024) { delete ctx; return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps"); }
+    size_t RN = (size_t)R * N;
+    DA(d.n_agents, R);
+    DA(d.attr, RN); DA(d.birth, RN); DA(d.ncrimes, RN); DA(d.ncrimes_tick, RN); DA(d.father, RN); DA(d.new_recruit, RN);
+    DA(d.propensity, RN); DA(d.tendency, RN); DA(d.sentence, RN); DA(d.arrest_w, RN);
+    DA(d.u_rowptr, (size_t)R * (N + 1)); DA(d.u_ent, (size_t)R * d.ucap);
+    DA(d.c_rowptr, (size_t)R * (N + 1)); DA(d.c_ent, (size_t)R * d.ccap);
+    DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
+    DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R);
+    DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
+    DA(d.cdf, RN);
+    size_t RC = (size_t)R * d.Ccap, RM = (size_t)R * d.Mcap;
+    DA(d.n_crimes, R); DA(d.crime_init, RC); DA(d.crime_k, RC); DA(d.crime_flags, RC);
+    DA(d.cr_target, RC); DA(d.cr_nacc, RC); DA(d.cr_d, RC); DA(d.cr_state, RC); DA(d.cr_fails, RC);
+    DA(d.cr_acc, RC * POC_MAX_GROUP); DA(d.search_list, RC); DA(d.n_search, R);
+    DA(d.emb_list, 2 * RN); DA(d.n_emb, 2 * R); DA(d.emb_stamp, RN); DA(d.emb_val, RN);
+    DA(d.group_off, (size_t)R * (d.Ccap + 1)); DA(d.group_mem, RM);
+    DA(d.pairs, (size_t)R * d.Pcap); DA(d.pair_cnt, (size_t)R * d.Pcap); DA(d.n_pairs, R);
+    DA(d.arrested, RM); DA(d.n_arrested, R); DA(d.aw, RM); DA(d.ap, RM); DA(d.acdf, RM);
+    DA(d.rp_u_init, RC); DA(d.rp_u_size, RC); DA(d.rp_fac_pick, RC);
+    DA(d.rp_u_arrest, RM); DA(d.rp_u_sentence, RM); DA(d.rp_arrest_idx, RM);
+    DA(d.rp_hdr, (size_t)R * 8); DA(d.rp_u_arrest_count, R); DA(d.philox_key, R);
+    DA(d.scr_list, (size_t)d.scr_slots * (N + 1)); DA(d.scr_key, (size_t)d.scr_slots * (N + 1));
+    DA(d.scr_dist, (size_t)d.scr_slots * (N + 1));
+    DA(d.reporters, (size_t)R * d.Tcap * POC_N_REPORTERS);
+    // staging
+    StageCols &s = ctx->stage;
+    DA(s.alive, N); DA(s.male, N); DA(s.oc_member, N); DA(s.facilitator, N); DA(s.prisoner, N); DA(s.has_job, N);
+    DA(s.has_school, N); DA(s.target, N); DA(s.job_level, N); DA(s.education_level, N); DA(s.wealth_level, N);
+    DA(s.age, N); DA(s.birth_tick, N); DA(s.num_crimes, N); DA(s.num_crimes_tick, N); DA(s.father, N); DA(s.new_recruit, N);
+    DA(s.propensity, N); DA(s.tendency, N); DA(s.sentence, N); DA(s.arrest_weight, N);
+    for (int l = 0; l < POC_NUM_LAYERS; l++) DA(ctx->st_rowptr[l], N + 1);
+    DA(ctx->st_col, d.ucap + d.ccap); DA(ctx->st_co, d.ccap);
+    DA(ctx->d_err, 1); DA(ctx->d_prev_counters, (size_t)R * CN_COUNT);
+    ctx->h_params.resize(R);
+    ctx->h_nagents.assign(R, 0);
+    ctx->ev.resize(EV_POOL); ctx->ev_class.assign(EV_POOL, 0);
+    for (auto &evx : ctx->ev) cudaEventCreate(&evx);
+    cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_embeddedness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb);
+    cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaDeviceSetLimit(cudaLimitStackSize, 2048);  // pw_sum recursion
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return POC_OK;
+}
+
+int poc_ctx_destroy(poc_ctx *ctx) {
+    if (!ctx) return POC_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    for (auto &evx : ctx->ev) cudaEventDestroy(evx);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return POC_OK;
+}
+
+int poc_sync(poc_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_set_timing(poc_ctx *ctx, int on) { CHECK_CTX(); ctx->timing = on != 0; return POC_OK; }
+int poc_timers_reset(poc_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ev_used = 0; ctx->launches = 0;
+    for (int i = 0; i < N_TIMERS; i++) { ctx->tm_ms[i] = 0; ctx->tm_n[i] = 0; }
+    return POC_OK;
+}
+int poc_timers_read(poc_ctx *ctx, double *ms_out, int64_t *launches_out) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) { ctx->tm_ms[ctx->ev_class[i]] += ms; ctx->tm_n[ctx->ev_class[i]]++; }
+    }
+    ctx->ev_used = 0;
+    for (int i = 0; i < N_TIMERS; i++) { if (ms_out) ms_out[i] = ctx->tm_ms[i]; if (launches_out) launches_out[i] = ctx->tm_n[i]; }
+    return POC_OK;
+}
+long long poc_launch_count(poc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int poc_set_params(poc_ctx *ctx, int replica, const poc_params *p) {
+    CHECK_CTX();
+    if (!p || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_set_params: bad argument");
+    if (p->n_cells < 1 || p->n_cells > POC_MAX_CELLS || p->n_sizes < 1 || p->n_sizes > POC_MAX_TAB || p->n_sent < 1 ||
+        p->n_sent > POC_MAX_TAB || p->max_accomplice_radius < 1 || p->max_accomplice_radius > MAX_RADIUS ||
+        p->oc_embeddedness_radius < 1 || p->oc_embeddedness_radius > MAX_RADIUS || p->ticks_per_year < 1 ||
+        p->ticks_between_intervention < 1)
+        return fail(ctx, POC_ERR_ARG, "poc_set_params: table sizes / radii out of range");
+    for (int a = 0; a < p->n_cells; a++)
+        for (int b = a + 1; b < p->n_cells; b++)
+            if (p->cell_male[a] == p->cell_male[b] && p->cell_age_from[a] <= p->cell_age_to[b] && p->cell_age_from[b] <= p->cell_age_to[a])
+                return fail(ctx, POC_ERR_ARG, "poc_set_params: age/sex cells overlap");
+    int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? ctx->d.R : replica + 1;
+    for (int r = r0; r < r1; r++) {
+        ctx->h_params[r] = *p;
+        CU(cudaMemcpyAsync(ctx->d.params + r, p, sizeof(poc_params), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // *p may be a temporary
+    return POC_OK;
+}
+
+static int read_err(poc_ctx *ctx, const char *what) {
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (h) {
+        CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        return fail(ctx, POC_ERR_ARG, std::string(what) + ": invalid input (code " + std::to_string(h) +
+                                          ": 1 attribute out of range, 2/3 row not ascending / bad slot / self loop)");
+    }
+    return POC_OK;
+}
+
+int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *c) {
+    CHECK_CTX();
+    if (!c || replica < 0 || replica >= ctx->d.R || n < 0 || n > ctx->d.Ncap) return fail(ctx, POC_ERR_ARG, "poc_upload_agents: bad argument");
+    StageCols &s = ctx->stage;
+    cudaStream_t st = ctx->stream;
+#define UP(f, T) CU(cudaMemcpyAsync(s.f, c->f, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st))
+    UP(alive, uint8_t); UP(male, uint8_t); UP(oc_member, uint8_t); UP(facilitator, uint8_t); UP(prisoner, uint8_t);
+    UP(has_job, uint8_t); UP(has_school, uint8_t); UP(target, uint8_t);
+    UP(job_level, int8_t); UP(education_level, int8_t); UP(wealth_level, int8_t);
+    UP(age, int32_t); UP(birth_tick, int32_t); UP(num_crimes, int32_t); UP(num_crimes_tick, int32_t); UP(father, int32_t);
+    UP(new_recruit, int32_t);
+    UP(propensity, double); UP(tendency, double); UP(sentence, double); UP(arrest_weight, double);
+#undef UP
+    CU(cudaMemcpyAsync(ctx->d.n_agents + replica, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    ctx->h_nagents[replica] = n;
+    if (n) k_pack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s, ctx->d_err);
+    CU(cudaGetLastError());
+    return read_err(ctx, "poc_upload_agents");
+}
+
+int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr, const int32_t *col, const int32_t *co) {
+    CHECK_CTX();
+    if (!rowptr || replica < 0 || replica >= ctx->d.R || layer < 0 || layer >= POC_NUM_LAYERS) return fail(ctx, POC_ERR_ARG, "poc_upload_layer: bad argument");
+    int n = ctx->h_nagents[replica];
+    if (ctx->st_replica != replica) { ctx->st_replica = replica; ctx->st_have = 0; ctx->st_off[0] = 0; }
+    long long ne = rowptr[n];
+    if (ne < 0 || (ne > 0 && !col)) return fail(ctx, POC_ERR_ARG, "poc_upload_layer: bad rowptr/col");
+    cudaStream_t st = ctx->stream;
+    if (layer == POC_CRIMINAL) {
+        if (ne > ctx->d.ccap) return fail(ctx, POC_ERR_CAPACITY, "poc_upload_layer: criminal layer exceeds max_criminal_entries");
+        int32_t *dcol = ctx->st_col + ctx->d.ucap;
+        CU(cudaMemcpyAsync(ctx->st_rowptr[layer], rowptr, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+        if (ne) CU(cudaMemcpyAsync(dcol, col, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+        if (ne && co) CU(cudaMemcpyAsync(ctx->st_co, co, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+        k_pack_criminal<<<(n + 256) / 256, 256, 0, st>>>(ctx->d, replica, n, ctx->st_rowptr[layer], dcol, co ? ctx->st_co : nullptr, ctx->d_err);
+        CU(cudaGetLastError());
+        ctx->st_have |= 1 << layer;
+        return read_err(ctx, "poc_upload_layer(criminal)");
+    }
+    // static layers are staged back to back in upload order; poc_build_graph merges them
+    int idx = 0;
+    for (int l = 0; l < POC_NUM_LAYERS; l++) if (l != POC_CRIMINAL && (ctx->st_have & (1 << l))) idx++;
+    if (ctx->st_have & (1 << layer)) return fail(ctx, POC_ERR_STATE, "poc_upload_layer: layer uploaded twice before poc_build_graph");
+    long long off = ctx->st_off[idx];
+    if (off + ne > ctx->d.ucap) return fail(ctx, POC_ERR_CAPACITY, "poc_upload_layer: static layers exceed max_static_entries");
+    CU(cudaMemcpyAsync(ctx->st_rowptr[layer], rowptr, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (ne) CU(cudaMemcpyAsync(ctx->st_col + off, col, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+    ctx->st_off[idx + 1] = off + ne;
+    ctx->st_have |= 1 << layer;
+    ctx->st_idx[layer] = idx;
+    CU(cudaStreamSynchronize(st));  // host buffers may be reused by the caller
+    return POC_OK;
+}
+
+int poc_build_graph(poc_ctx *ctx, int replica) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R || ctx->st_replica != replica) return fail(ctx, POC_ERR_STATE, "poc_build_graph: upload the layers of this replica first");
+    int all = (1 << POC_NUM_LAYERS) - 1;
+    if ((ctx->st_have & all) != all) return fail(ctx, POC_ERR_STATE, "poc_build_graph: all nine layers must be uploaded");
+    int n = ctx->h_nagents[replica];
+    cudaStream_t st = ctx->stream;
+    StageLayers L;
+    for (int l = 0, b = 0; l < POC_NUM_LAYERS; l++) {
+        if (l == POC_CRIMINAL) continue;
+        int idx = ctx->st_idx[l];
+        L.rowptr[b] = ctx->st_rowptr[l];
+        L.col[b] = ctx->st_col + ctx->st_off[idx];
+        b++;
+    }
+    int *lens = ctx->d.c_addlen + (size_t)replica * ctx->d.Ncap;  // scratch
+    int32_t *urp = ctx->d.u_rowptr + (size_t)replica * (ctx->d.Ncap + 1);
+    if (n) {
+        k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 0, ctx->d_err);
+        k_exscan_i32<<<1, 1024, 0, st>>>(lens, urp, n);
+        k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 1, ctx->d_err);
+    } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
+    CU(cudaGetLastError());
+    ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;
+    return read_err(ctx, "poc_build_graph");
+}
+
+int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *c) {
+    CHECK_CTX();
+    if (!c || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_download_agents: bad argument");
+    int n = ctx->h_nagents[replica];
+    StageCols &s = ctx->stage;
+    cudaStream_t st = ctx->stream;
+    if (n) k_unpack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s);
+    CU(cudaGetLastError());
+#define DN(f, T) if (c->f) CU(cudaMemcpyAsync(c->f, s.f, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, st))
+    DN(alive, uint8_t); DN(male, uint8_t); DN(oc_member, uint8_t); DN(facilitator, uint8_t); DN(prisoner, uint8_t);
+    DN(has_job, uint8_t); DN(has_school, uint8_t); DN(target, uint8_t);
+    DN(job_level, int8_t); DN(education_level, int8_t); DN(wealth_level, int8_t);
+    DN(age, int32_t); DN(birth_tick, int32_t); DN(num_crimes, int32_t); DN(num_crimes_tick, int32_t); DN(father, int32_t);
+    DN(new_recruit, int32_t);
+    DN(propensity, double); DN(tendency, double); DN(sentence, double); DN(arrest_weight, double);
+#undef DN
+    CU(cudaStreamSynchronize(st));
+    return POC_OK;
+}
+
+// layers come back through the host: state I/O, not the hot path
+static int fetch_graph(poc_ctx *ctx, int replica, std::vector<int32_t> &urp, std::vector<uint32_t> &uent,
+                       std::vector<int32_t> &crp, std::vector<int2> &cent) {
+    int n = ctx->h_nagents[replica];
+    DevCtx &d = ctx->d;
+    urp.resize(n + 1); crp.resize(n + 1);
+    CU(cudaMemcpyAsync(urp.data(), d.u_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(crp.data(), d.c_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uent.resize(urp[n]); cent.resize(crp[n]);
+    if (urp[n]) CU(cudaMemcpyAsync(uent.data(), d.u_ent + (size_t)replica * d.ucap, sizeof(uint32_t) * urp[n], cudaMemcpyDeviceToHost, ctx->stream));
+    if (crp[n]) CU(cudaMemcpyAsync(cent.data(), d.c_ent + (size_t)replica * d.ccap, sizeof(int2) * crp[n], cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_layer_entries(poc_ctx *ctx, int replica, int layer, int64_t *out) {
+    CHECK_CTX();
+    if (!out || replica < 0 || replica >= ctx->d.R || layer < 0 || layer >= POC_NUM_LAYERS) return fail(ctx, POC_ERR_ARG, "poc_layer_entries: bad argument");
+    std::vector<int32_t> urp, crp; std::vector<uint32_t> uent; std::vector<int2> cent;
+    int rc = fetch_graph(ctx, replica, urp, uent, crp, cent);
+    if (rc) return rc;
+    if (layer == POC_CRIMINAL) { *out = (int64_t)cent.size(); return POC_OK; }
+    uint32_t bit = 1u << layer_bit(layer);
+    int64_t k = 0;
+    for (uint32_t e : uent) if (ENT_MASK(e) & bit) k++;
+    *out = k;
+    return POC_OK;
+}
+
+int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, int32_t *col, int32_t *co) {
+    CHECK_CTX();
+    if (!rowptr || replica < 0 || replica >= ctx->d.R || layer < 0 || layer >= POC_NUM_LAYERS) return fail(ctx, POC_ERR_ARG, "poc_download_layer: bad argument");
+    std::vector<int32_t> urp, crp; std::vector<uint32_t> uent; std::vector<int2> cent;
+    int rc = fetch_graph(ctx, replica, urp, uent, crp, cent);
+    if (rc) return rc;
+    int n = ctx->h_nagents[replica];
+    int32_t p = 0;
+    for (int a = 0; a < n; a++) {
+        rowptr[a] = p;
+        if (layer == POC_CRIMINAL) {
+            for (int e = crp[a]; e < crp[a + 1]; e++) { if (col) col[p] = cent[e].x; if (co) co[p] = cent[e].y; p++; }
+        } else {
+            uint32_t bit = 1u << layer_bit(layer);
+            for (int e = urp[a]; e < urp[a + 1]; e++) if (ENT_MASK(uent[e]) & bit) { if (col) col[p] = ENT_COL(uent[e]); p++; }
+        }
+    }
+    rowptr[n] = p;
+    return POC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hot path
+static int max_n(poc_ctx *ctx) { int m = 0; for (int v : ctx->h_nagents) m = std::max(m, v); return m; }
+static int max_radius(poc_ctx *ctx) { int m = 1; for (auto &p : ctx->h_params) m = std::max(m, (int)p.max_accomplice_radius); return m; }
+
+int poc_begin_tick(poc_ctx *ctx, int tick) {
+    CHECK_CTX();
+    int n = max_n(ctx);
+    if (!n) return POC_OK;
+    { Timed t(ctx, TM_OTHER); k_begin_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d, tick); }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+int poc_end_tick(poc_ctx *ctx) {
+    CHECK_CTX();
+    int n = max_n(ctx);
+    if (!n) return POC_OK;
+    { Timed t(ctx, TM_OTHER); k_end_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d); }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+static int launch_cells(poc_ctx *ctx, int yearly) {
+    { Timed t(ctx, TM_CELLS); k_cells<<<ctx->d.R, 1024, 0, ctx->stream>>>(ctx->d, yearly); }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+static int launch_tendency(poc_ctx *ctx) {
+    int n = max_n(ctx);
+    if (!n) return POC_OK;
+    { Timed t(ctx, TM_TENDENCY); k_tendency_pre<<<dim3((n + 127) / 128, ctx->d.R), 128, 0, ctx->stream>>>(ctx->d); }
+    { Timed t(ctx, TM_TENDENCY); k_tendency_eps<<<ctx->d.R, 1024, 0, ctx->stream>>>(ctx->d); }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+int poc_tendency(poc_ctx *ctx) {
+    CHECK_CTX();
+    int rc = launch_cells(ctx, 0);
+    if (rc) return rc;
+    return launch_tendency(ctx);
+}
+
+int poc_crime_multiplier(poc_ctx *ctx, double *out) {
+    CHECK_CTX();
+    int rc = launch_cells(ctx, 1);
+    if (rc) return rc;
+    if (out) {
+        CU(cudaMemcpyAsync(out, ctx->d.crime_mult, sizeof(double) * ctx->d.R, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return POC_OK;
+}
+
+int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_set_crime_multiplier: bad replica");
+    CU(cudaMemcpyAsync(ctx->d.crime_mult + replica, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+// search / embeddedness rounds shared by commit_crimes and the find_accomplices hook
+static int launch_search_rounds(poc_ctx *ctx, int tick) {
+    DevCtx &d = ctx->d;
+    int rounds = max_radius(ctx);
+    dim3 grid(ctx->gx, d.R);
+    for (int rd = 0; rd <= rounds; rd++) {
+        { Timed t(ctx, TM_SEARCH); k_search<<<grid, 256, ctx->smem_search, ctx->stream>>>(d, tick, ctx->epoch, rd & 1); }
+        if (rd < rounds) { Timed t(ctx, TM_EMB); k_embeddedness<<<grid, 256, ctx->smem_emb, ctx->stream>>>(d, rd & 1); }
+    }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+static int launch_commit(poc_ctx *ctx, int tick, bool cells_done, int report_t) {
+    DevCtx &d = ctx->d;
+    ctx->epoch++;
+    if (!cells_done) { int rc = launch_cells(ctx, 0); if (rc) return rc; }
+    { Timed t(ctx, TM_OTHER); k_snapshot_counters<<<(d.R * CN_COUNT + 255) / 256, 256, 0, ctx->stream>>>(d, ctx->d_prev_counters); }
+    { Timed t(ctx, TM_DRAW); k_draw<<<d.R, 512, 0, ctx->stream>>>(d, tick); }
+    int rc = launch_search_rounds(ctx, tick);
+    if (rc) return rc;
+    { Timed t(ctx, TM_COMMIT); k_commit<<<d.R, 1024, 0, ctx->stream>>>(d); }
+    { Timed t(ctx, TM_ARREST); k_recruit_arrest<<<(d.R + 31) / 32, 32, 0, ctx->stream>>>(d, tick); }
+    if (report_t >= 0) { Timed t(ctx, TM_OTHER); k_report<<<d.R, 512, 0, ctx->stream>>>(d, report_t); }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+static int upload_replay(poc_ctx *ctx, const poc_replay *const *replay, const uint64_t *keys) {
+    DevCtx &d = ctx->d;
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> hdr((size_t)d.R * 8, 0);
+    std::vector<double> uac(d.R, 0.0);
+    for (int r = 0; r < d.R; r++) {
+        const poc_replay *rp = replay ? replay[r] : nullptr;
+        if (!rp) continue;
+        if (rp->n_crimes > d.Ccap || rp->n_u_arrest > d.Mcap || rp->n_u_sentence > d.Mcap || rp->n_arrest_idx > d.Mcap)
+            return fail(ctx, POC_ERR_CAPACITY, "replay arrays exceed capacity");
+        int32_t *h = &hdr[(size_t)r * 8];
+        h[0] = 1; h[1] = rp->n_crimes; h[2] = rp->n_u_arrest; h[3] = rp->n_u_sentence;
+        h[4] = (rp->arrest_idx && rp->n_arrest_idx >= 0) ? rp->n_arrest_idx : -1;
+        uac[r] = rp->u_arrest_count;
+        if (rp->n_crimes) {
+            CU(cudaMemcpyAsync(d.rp_u_init + (size_t)r * d.Ccap, rp->u_init, sizeof(double) * rp->n_crimes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d.rp_u_size + (size_t)r * d.Ccap, rp->u_size, sizeof(double) * rp->n_crimes, cudaMemcpyHostToDevice, st));
+            if (rp->fac_pick) CU(cudaMemcpyAsync(d.rp_fac_pick + (size_t)r * d.Ccap, rp->fac_pick, sizeof(int32_t) * rp->n_crimes, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemsetAsync(d.rp_fac_pick + (size_t)r * d.Ccap, 0xff, sizeof(int32_t) * rp->n_crimes, st));
+        }
+        if (rp->n_u_arrest) CU(cudaMemcpyAsync(d.rp_u_arrest + (size_t)r * d.Mcap, rp->u_arrest, sizeof(double) * rp->n_u_arrest, cudaMemcpyHostToDevice, st));
+        if (rp->n_u_sentence) CU(cudaMemcpyAsync(d.rp_u_sentence + (size_t)r * d.Mcap, rp->u_sentence, sizeof(double) * rp->n_u_sentence, cudaMemcpyHostToDevice, st));
+        if (h[4] > 0) CU(cudaMemcpyAsync(d.rp_arrest_idx + (size_t)r * d.Mcap, rp->arrest_idx, sizeof(int32_t) * h[4], cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(d.rp_hdr, hdr.data(), sizeof(int32_t) * hdr.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d.rp_u_arrest_count, uac.data(), sizeof(double) * d.R, cudaMemcpyHostToDevice, st));
+    if (keys) CU(cudaMemcpyAsync(d.philox_key, keys, sizeof(uint64_t) * d.R, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // hdr / uac are locals
+    return POC_OK;
+}
+
+static int read_tick_out(poc_ctx *ctx, poc_tick_out *out, poc_tick_records *rec) {
+    DevCtx &d = ctx->d;
+    std::vector<int> cn((size_t)d.R * CN_COUNT), prev((size_t)d.R * CN_COUNT);
+    std::vector<unsigned long long> edges(d.R);
+    CU(cudaMemcpyAsync(cn.data(), d.counters, sizeof(int) * cn.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(prev.data(), ctx->d_prev_counters, sizeof(int) * prev.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(edges.data(), d.edges, sizeof(unsigned long long) * d.R, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemsetAsync(d.edges, 0, sizeof(unsigned long long) * d.R, ctx->stream));
+    for (int r = 0; r < d.R && out; r++) {
+        const int *c = &cn[(size_t)r * CN_COUNT], *p = &prev[(size_t)r * CN_COUNT];
+        poc_tick_out &o = out[r];
+        o.n_crimes = c[CN_TICK_CRIMES]; o.n_members = c[CN_TICK_MEMBERS]; o.n_arrests = c[CN_TICK_ARRESTS];
+        o.n_emb_evals = c[CN_TICK_EMB];
+        o.d_number_crimes = c[CN_NUMBER_CRIMES] - p[CN_NUMBER_CRIMES];
+        o.d_crime_size_fails = c[CN_SIZE_FAILS] - p[CN_SIZE_FAILS];
+        o.d_facilitator_crimes = c[CN_FAC_CRIMES] - p[CN_FAC_CRIMES];
+        o.d_facilitator_fails = c[CN_FAC_FAILS] - p[CN_FAC_FAILS];
+        o.d_big_crime_from_small_fish = c[CN_BIG_CRIME] - p[CN_BIG_CRIME];
+        o.d_offspring_recruited = c[CN_OFFSPRING_RECRUITED] - p[CN_OFFSPRING_RECRUITED];
+        o.d_protected_recruited = c[CN_PROTECTED_RECRUITED] - p[CN_PROTECTED_RECRUITED];
+        o.d_people_jailed = c[CN_PEOPLE_JAILED] - p[CN_PEOPLE_JAILED];
+        o.n_recruited = c[CN_TICK_RECRUITED]; o.error = c[CN_ERROR];
+        o.traversed_edges = (int64_t)edges[r];
+    }
+    if (rec) {
+        int ncr = cn[CN_TICK_CRIMES], nm = cn[CN_TICK_MEMBERS], na = cn[CN_TICK_ARRESTS];
+        if (ncr > rec->cap_crimes || nm > rec->cap_members || na > rec->cap_arrests) return fail(ctx, POC_ERR_CAPACITY, "poc_tick_records buffers too small");
+        cudaStream_t st = ctx->stream;
+        if (ncr && rec->initiator) CU(cudaMemcpyAsync(rec->initiator, d.crime_init, sizeof(int32_t) * ncr, cudaMemcpyDeviceToHost, st));
+        if (ncr && rec->k) CU(cudaMemcpyAsync(rec->k, d.crime_k, sizeof(int32_t) * ncr, cudaMemcpyDeviceToHost, st));
+        if (rec->group_off) CU(cudaMemcpyAsync(rec->group_off, d.group_off, sizeof(int32_t) * (ncr + 1), cudaMemcpyDeviceToHost, st));
+        if (nm && rec->group_mem) CU(cudaMemcpyAsync(rec->group_mem, d.group_mem, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost, st));
+        if (na && rec->arrested) CU(cudaMemcpyAsync(rec->arrested, d.arrested, sizeof(int32_t) * na, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return POC_OK;
+}
+
+int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay, const uint64_t *keys, poc_tick_out *out,
+                      poc_tick_records *rec) {
+    CHECK_CTX();
+    int rc = upload_replay(ctx, replay, keys);
+    if (rc) return rc;
+    rc = launch_commit(ctx, tick, false, -1);
+    if (rc) return rc;
+    if (out || rec) return read_tick_out(ctx, out, rec);
+    return POC_OK;
+}
+
+int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, double *reporters_out) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (n_ticks < 0) return fail(ctx, POC_ERR_ARG, "poc_run_ticks: n_ticks < 0");
+    int rc = upload_replay(ctx, nullptr, keys);
+    if (rc) return rc;
+    if (reporters_out && n_ticks > d.Tcap) {
+        double *p = nullptr;
+        DA(p, (size_t)d.R * n_ticks * POC_N_REPORTERS);
+        d.reporters = p; d.Tcap = n_ticks;
+    }
+    int n = max_n(ctx);
+    for (int i = 0; i < n_ticks; i++) {
+        int tick = tick0 + i;
+        if (n) { Timed t(ctx, TM_OTHER); k_begin_tick<<<dim3((n + 255) / 256, d.R), 256, 0, ctx->stream>>>(d, tick); }
+        bool yearly = false;  // model.py:248 -- evaluated per replica below only through ticks_per_year of replica 0
+        int tpy = ctx->h_params[0].ticks_per_year;
+        yearly = (tick % tpy == 0) || tick == 1;
+        rc = launch_cells(ctx, yearly ? 1 : 0);
+        if (rc) return rc;
+        if (yearly) { rc = launch_tendency(ctx); if (rc) return rc; }
+        rc = launch_commit(ctx, tick, true, reporters_out ? i : -1);
+        if (rc) return rc;
+        if (n) { Timed t(ctx, TM_OTHER); k_end_tick<<<dim3((n + 255) / 256, d.R), 256, 0, ctx->stream>>>(d); }
+    }
+    CU(cudaGetLastError());
+    if (reporters_out && n_ticks) {
+        // device layout [R][Tcap][K] -> host [R][n_ticks][K]
+        for (int r = 0; r < d.R; r++)
+            CU(cudaMemcpyAsync(reporters_out + (size_t)r * n_ticks * POC_N_REPORTERS, d.reporters + (size_t)r * d.Tcap * POC_N_REPORTERS,
+                               sizeof(double) * (size_t)n_ticks * POC_N_REPORTERS, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return POC_OK;
+}
+
+int poc_read_counters(poc_ctx *ctx, int32_t *counters_out /* [R][24] */, uint64_t *edges_out /* [R] */) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (counters_out) CU(cudaMemcpyAsync(counters_out, d.counters, sizeof(int) * (size_t)d.R * CN_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    if (edges_out) CU(cudaMemcpyAsync(edges_out, d.edges, sizeof(unsigned long long) * d.R, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage hooks
+static int hook_bufs(poc_ctx *ctx, long long n) {
+    if (n <= ctx->hook_cap) return POC_OK;
+    long long cap = std::max<long long>(n, 1024);
+    DA(ctx->d_hook_a, cap); DA(ctx->d_hook_b, cap); DA(ctx->d_hook_out, cap);
+    ctx->hook_cap = cap;
+    return POC_OK;
+}
+
+int poc_rings(poc_ctx *ctx, int replica, int n_src, const int32_t *src, int dd, int exact, int32_t *out_off, int32_t *out_mem,
+              int64_t cap_mem) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R || n_src < 0 || !src || !out_off || dd < 1 || dd > MAX_RADIUS) return fail(ctx, POC_ERR_ARG, "poc_rings: bad argument");
+    int n = ctx->h_nagents[replica];
+    for (int i = 0; i < n_src; i++) if (src[i] < 0 || src[i] >= n) return fail(ctx, POC_ERR_ARG, "poc_rings: bad source slot");
+    int rc = hook_bufs(ctx, std::max<long long>(n_src, 1));
+    if (rc) return rc;
+    int32_t *d_mem = nullptr;
+    long long per = n;  // a ring cannot exceed n members
+    CU(cudaMalloc((void **)&d_mem, sizeof(int32_t) * std::max<size_t>((size_t)n_src * per, 1)));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->d_hook_a, src, sizeof(int32_t) * n_src, cudaMemcpyHostToDevice, st));
+    int grid = std::min(std::max(n_src, 1), ctx->d.scr_slots);
+    k_rings_hook<<<grid, 256, ctx->smem_search, st>>>(ctx->d, replica, n_src, ctx->d_hook_a, dd, exact, ctx->d_hook_b, d_mem, per);
+    std::vector<int32_t> cnt(n_src), mem((size_t)n_src * per);
+    cudaError_t e1 = cudaMemcpyAsync(cnt.data(), ctx->d_hook_b, sizeof(int32_t) * n_src, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(mem.data(), d_mem, sizeof(int32_t) * mem.size(), cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    cudaFree(d_mem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail(ctx, POC_ERR_CUDA, "poc_rings: CUDA failure");
+    int64_t p = 0;
+    for (int s = 0; s < n_src; s++) {
+        out_off[s] = (int32_t)p;
+        if (p + cnt[s] > cap_mem) return fail(ctx, POC_ERR_CAPACITY, "poc_rings: out_mem too small");
+        std::sort(mem.begin() + (size_t)s * per, mem.begin() + (size_t)s * per + cnt[s]);
+        if (out_mem) std::copy(mem.begin() + (size_t)s * per, mem.begin() + (size_t)s * per + cnt[s], out_mem + p);
+        p += cnt[s];
+    }
+    out_off[n_src] = (int32_t)p;
+    return POC_OK;
+}
+
+static int pairs_hook(poc_ctx *ctx, int replica, int n_pairs, const int32_t *a, const int32_t *b, double *out, int mode) {
+    int n = ctx->h_nagents[replica];
+    for (int i = 0; i < n_pairs; i++) if (a[i] < 0 || a[i] >= n || b[i] < 0 || b[i] >= n) return fail(ctx, POC_ERR_ARG, "bad slot in pair list");
+    int rc = hook_bufs(ctx, std::max(n_pairs, 1));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->d_hook_a, a, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_hook_b, b, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    if (n_pairs) k_pairs_hook<<<(n_pairs * 32 + 255) / 256, 256, 0, st>>>(ctx->d, replica, n_pairs, ctx->d_hook_a, ctx->d_hook_b, ctx->d_hook_out, mode);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->d_hook_out, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return POC_OK;
+}
+
+int poc_social_proximity(poc_ctx *ctx, int replica, int n_pairs, const int32_t *a, const int32_t *b, double *out) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R || n_pairs < 0 || !a || !b || !out) return fail(ctx, POC_ERR_ARG, "poc_social_proximity: bad argument");
+    return pairs_hook(ctx, replica, n_pairs, a, b, out, 0);
+}
+
+static int run_emb(poc_ctx *ctx, int replica, int n, const int32_t *agents) {
+    DevCtx &d = ctx->d;
+    if (n > d.Ncap) return fail(ctx, POC_ERR_CAPACITY, "too many embeddedness requests");
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> zero(2 * d.R, 0);
+    zero[replica] = n;
+    CU(cudaMemcpyAsync(d.n_emb, zero.data(), sizeof(int32_t) * zero.size(), cudaMemcpyHostToDevice, st));
+    if (n) CU(cudaMemcpyAsync(d.emb_list + (size_t)replica * d.Ncap, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    { Timed t(ctx, TM_EMB); k_embeddedness<<<dim3(ctx->gx, d.R), 256, ctx->smem_emb, st>>>(d, 0); }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return POC_OK;
+}
+
+int poc_embeddedness(poc_ctx *ctx, int replica, int n, const int32_t *agents, double *out) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R || n < 0 || !agents || !out) return fail(ctx, POC_ERR_ARG, "poc_embeddedness: bad argument");
+    int na = ctx->h_nagents[replica];
+    for (int i = 0; i < n; i++) if (agents[i] < 0 || agents[i] >= na) return fail(ctx, POC_ERR_ARG, "poc_embeddedness: bad slot");
+    int rc = run_emb(ctx, replica, n, agents);
+    if (rc) return rc;
+    std::vector<double> all(na);
+    CU(cudaMemcpyAsync(all.data(), ctx->d.emb_val + (size_t)replica * ctx->d.Ncap, sizeof(double) * na, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) out[i] = all[agents[i]];
+    return POC_OK;
+}
+
+int poc_candidate_weights(poc_ctx *ctx, int replica, int n_pairs, const int32_t *self, const int32_t *cand, double *out) {
+    CHECK_CTX();
+    if (replica < 0 || replica >= ctx->d.R || n_pairs < 0 || !self || !cand || !out) return fail(ctx, POC_ERR_ARG, "poc_candidate_weights: bad argument");
+    int na = ctx->h_nagents[replica];
+    for (int i = 0; i < n_pairs; i++) if (cand[i] < 0 || cand[i] >= na) return fail(ctx, POC_ERR_ARG, "poc_candidate_weights: bad slot");
+    std::vector<int32_t> uniq(cand, cand + n_pairs);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    int rc = run_emb(ctx, replica, (int)uniq.size(), uniq.data());
+    if (rc) return rc;
+    return pairs_hook(ctx, replica, n_pairs, self, cand, out, 1);
+}
+
+int poc_find_accomplices(poc_ctx *ctx, int replica, int n, const int32_t *initiator, const int32_t *k, const int32_t *fac_pick,
+                         const double *u_fac, int32_t *groups, int32_t *group_len, int32_t *d_fails) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (replica < 0 || replica >= d.R || n < 0 || n > d.Ccap || !initiator || !k || !groups || !group_len) return fail(ctx, POC_ERR_ARG, "poc_find_accomplices: bad argument");
+    int na = ctx->h_nagents[replica];
+    for (int i = 0; i < n; i++) if (initiator[i] < 0 || initiator[i] >= na || k[i] < 0) return fail(ctx, POC_ERR_ARG, "poc_find_accomplices: bad initiator / k");
+    int rc = hook_bufs(ctx, std::max(n, 1));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> hdr((size_t)d.R * 8, 0);
+    hdr[(size_t)replica * 8] = 2;  // hook mode: rp_u_init carries u_fac, rp_fac_pick the recorded pick
+    std::vector<double> uf(n, 0.0);
+    std::vector<int32_t> fp(n, -1);
+    if (u_fac) std::copy(u_fac, u_fac + n, uf.begin());
+    if (fac_pick) std::copy(fac_pick, fac_pick + n, fp.begin());
+    CU(cudaMemcpyAsync(d.rp_hdr, hdr.data(), sizeof(int32_t) * hdr.size(), cudaMemcpyHostToDevice, st));
+    if (n) {
+        CU(cudaMemcpyAsync(d.rp_u_init + (size_t)replica * d.Ccap, uf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d.rp_fac_pick + (size_t)replica * d.Ccap, fp.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_hook_a, initiator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_hook_b, k, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    // other replicas must stay idle during the hook
+    std::vector<int32_t> zeros(d.R, 0);
+    CU(cudaMemcpyAsync(d.n_search, zeros.data(), sizeof(int32_t) * d.R, cudaMemcpyHostToDevice, st));
+    std::vector<int> cn_before((size_t)d.R * CN_COUNT);
+    CU(cudaMemcpyAsync(cn_before.data(), d.counters, sizeof(int) * cn_before.size(), cudaMemcpyDeviceToHost, st));
+    ctx->epoch++;
+    k_hook_init_crimes<<<(std::max(n, 1) + 255) / 256, 256, 0, st>>>(d, replica, n, ctx->d_hook_a, ctx->d_hook_b);
+    k_hook_fill_search<<<1, 32, 0, st>>>(d, replica, n);
+    CU(cudaGetLastError());
+    rc = launch_search_rounds(ctx, 0);
+    if (rc) return rc;
+    std::vector<int32_t> acc((size_t)n * POC_MAX_GROUP), nacc(n), fails(n);
+    if (n) {
+        CU(cudaMemcpyAsync(acc.data(), d.cr_acc + (size_t)replica * d.Ccap * POC_MAX_GROUP, sizeof(int32_t) * acc.size(), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(nacc.data(), d.cr_nacc + (size_t)replica * d.Ccap, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(fails.data(), d.cr_fails + (size_t)replica * d.Ccap, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    // the hook must not disturb the model counters
+    CU(cudaMemcpyAsync(d.counters, cn_before.data(), sizeof(int) * cn_before.size(), cudaMemcpyHostToDevice, st));
+    std::fill(hdr.begin(), hdr.end(), 0);
+    CU(cudaMemcpyAsync(d.rp_hdr, hdr.data(), sizeof(int32_t) * hdr.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) {
+        int g = k[i] > 0 ? nacc[i] : 0;
+        for (int j = 0; j < g; j++) groups[(size_t)i * POC_MAX_GROUP + j] = acc[(size_t)i * POC_MAX_GROUP + j];
+        groups[(size_t)i * POC_MAX_GROUP + g] = initiator[i];
+        group_len[i] = g + 1;
+        if (d_fails) { d_fails[3 * i] = fails[i] & 1; d_fails[3 * i + 1] = (fails[i] >> 1) & 1; d_fails[3 * i + 2] = (fails[i] >> 2) & 1; }
+    }
+    return POC_OK;
+}
+
+}  // extern "C"

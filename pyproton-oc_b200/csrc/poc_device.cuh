@@ -1,0 +1,264 @@
+// poc_device.cuh -- device-side data model and block-cooperative primitives (sm_100a).
+//
+// Data layout in HBM (per ctx = batch of R replicas, every array is [R][capacity], replica-major):
+//   attr      u32   age | flags<<8 | job<<16 | edu<<20 | wealth<<24   (one 4-byte gather scores a candidate)
+//   tendency  f64, propensity f64, sentence f64, arrest_w f64
+//   birth, ncrimes, ncrimes_tick, father, new_recruit   i32
+//   u_rowptr  i32 [Ncap+1], u_ent u32 [ucap]: the eight non-criminal layers merged into one directed CSR,
+//             entry = neighbour slot (24 bit) | layer mask (8 bit) << 24 ; rows ascending by slot
+//   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses}, rows ascending
+// Reference mapping: Person attributes entities.py:49-83, the nine neighbour sets entities.py:38-47.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/protonoc_b200.h"
+
+#define FULL_MASK 0xffffffffu
+
+// ---- packed attribute word ------------------------------------------------------------------------
+enum : uint32_t {
+    F_ALIVE = 1u << 8, F_MALE = 1u << 9, F_OC = 1u << 10, F_FAC = 1u << 11, F_PRISONER = 1u << 12,
+    F_HASJOB = 1u << 13, F_HASSCHOOL = 1u << 14, F_TARGET = 1u << 15
+};
+__host__ __device__ __forceinline__ int attr_age(uint32_t a) { return (int)(a & 0xffu); }
+__host__ __device__ __forceinline__ int attr_job(uint32_t a) { return (int)((a >> 16) & 0xfu); }
+__host__ __device__ __forceinline__ int attr_edu(uint32_t a) { return (int)((a >> 20) & 0xfu); }
+__host__ __device__ __forceinline__ int attr_wealth(uint32_t a) { return (int)((a >> 24) & 0xfu); }
+
+// layer -> bit of the 8-bit mask in the multiplex entry (criminal is stored separately)
+__host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < POC_CRIMINAL ? layer : layer - 1; }
+#define MB_SIB 0x01u
+#define MB_OFF 0x02u
+#define MB_PAR 0x04u
+#define MB_PARTNER 0x08u
+#define MB_HH 0x10u
+#define MB_FRIEND 0x20u
+#define MB_PROF 0x40u
+#define MB_SCHOOL 0x80u
+#define ENT_COL(e) ((int)((e) & 0x00ffffffu))
+#define ENT_MASK(e) ((e) >> 24)
+
+// counters per replica (ints), cumulative unless noted
+enum {
+    CN_NUMBER_CRIMES = 0, CN_SIZE_FAILS, CN_FAC_CRIMES, CN_FAC_FAILS, CN_BIG_CRIME, CN_OFFSPRING_RECRUITED,
+    CN_PROTECTED_RECRUITED, CN_PEOPLE_JAILED, CN_RECRUITED, CN_ERROR, CN_TICK_CRIMES, CN_TICK_MEMBERS,
+    CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_COUNT = 24
+};
+
+struct DevCtx {
+    int R, Ncap, Ccap, Mcap, Pcap;  // replicas, agent / crime / member / pair capacities per replica
+    long long ucap, ccap;           // static / criminal entry capacity per replica
+    int *n_agents;                  // [R]
+    // agents
+    uint32_t *attr;
+    int32_t *birth, *ncrimes, *ncrimes_tick, *father, *new_recruit;
+    double *propensity, *tendency, *sentence, *arrest_w;
+    // graph
+    int32_t *u_rowptr; uint32_t *u_ent;
+    int32_t *c_rowptr; int2 *c_ent;
+    int32_t *c_rowptr_tmp; int2 *c_ent_tmp; int32_t *c_addlen;
+    // parameters / scalars
+    poc_params *params;             // [R]
+    double *crime_mult;             // [R]
+    int *counters;                  // [R][CN_COUNT]
+    unsigned long long *edges;      // [R] traversed multiplex entries (bench metric)
+    // cells
+    int32_t *cell_members;          // [R][Ncap] ascending slot inside each cell
+    int32_t *cell_off;              // [R][POC_MAX_CELLS+1]
+    int32_t *cell_strict;           // [R][POC_MAX_CELLS] counts with age_from < age (Q8)
+    double *cdf;                    // [R][Ncap]
+    // crimes of the tick
+    int32_t *n_crimes;              // [R]
+    int32_t *crime_init, *crime_k, *crime_flags;  // [R][Ccap]; flags bit0 = started by OC member
+    int32_t *cr_target, *cr_nacc, *cr_d, *cr_state, *cr_fails;  // [R][Ccap]
+    int32_t *cr_acc;                // [R][Ccap][POC_MAX_GROUP]
+    int32_t *search_list, *n_search;  // [R][Ccap], [R]
+    // embeddedness requests
+    int32_t *emb_list;              // [2][R][Ncap]
+    int32_t *n_emb;                 // [2][R]
+    int32_t *emb_stamp;             // [R][Ncap]
+    double *emb_val;                // [R][Ncap]
+    // groups of the tick, canonical
+    int32_t *group_off, *group_mem; // [R][Ccap+1], [R][Mcap]
+    unsigned long long *pairs;      // [R][Pcap]
+    int32_t *pair_cnt;              // [R][Pcap]
+    int32_t *n_pairs;               // [R]
+    int32_t *arrested, *n_arrested; // [R][Mcap], [R]
+    double *aw, *ap, *acdf;         // [R][Mcap] arrest sampler scratch
+    // replay (device copies), NULL pointers => Philox
+    double *rp_u_init, *rp_u_size; int32_t *rp_fac_pick;   // [R][Ccap]
+    double *rp_u_arrest, *rp_u_sentence; int32_t *rp_arrest_idx;  // [R][Mcap]
+    int32_t *rp_hdr;                // [R][8]: use_replay, n_crimes, n_u_arrest, n_u_sentence, n_arrest_idx
+    double *rp_u_arrest_count;      // [R]
+    unsigned long long *philox_key; // [R]
+    // per-block scratch (block slot = blockIdx.y * gridDim.x + blockIdx.x)
+    int32_t *scr_list;              // [slots][Ncap+1]
+    double *scr_key;                // [slots][Ncap+1]
+    unsigned long long *scr_dist;   // [slots][Ncap+1]
+    int scr_slots;
+    double *reporters;              // [R][Tcap][POC_N_REPORTERS]
+    int Tcap;
+};
+
+// ---- Philox4x32-10 (Salmon et al. SC'11) -----------------------------------------------------------
+enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4 };
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two doubles in [0,1) with 53 random bits each (numpy's random() mapping)
+__device__ __forceinline__ void philox_u2(unsigned long long key, int tick, int stage, int idx, double &u0, double &u1) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)tick, (uint32_t)stage, (uint32_t)idx, 0u, (uint32_t)key, (uint32_t)(key >> 32), o);
+    unsigned long long a = ((unsigned long long)o[1] << 32) | o[0], b = ((unsigned long long)o[3] << 32) | o[2];
+    u0 = __dmul_rn((double)(a >> 11), 1.0 / 9007199254740992.0);
+    u1 = __dmul_rn((double)(b >> 11), 1.0 / 9007199254740992.0);
+}
+
+// searchsorted(cdf, u, side='right')
+__device__ __forceinline__ int ss_right(const double *cdf, int n, double u) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (cdf[m] <= u) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// ---- block primitives ------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// exclusive scan of one int per thread across the block; returns the exclusive prefix, *total = block sum.
+// smem `ws` needs 33 ints.  All threads must call.
+__device__ __forceinline__ int block_exscan(int v, int *ws, int *total) {
+    int lane = lane_id(), w = warp_id(), nw = (blockDim.x + 31) >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = (lane < nw) ? ws[lane] : 0, t = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, t, o); if (lane >= o) t += y; }
+        ws[lane] = t - s;
+        if (lane == 31) ws[32] = t;
+    }
+    __syncthreads();
+    int res = ws[w] + x - v;
+    if (total) *total = ws[32];
+    __syncthreads();
+    return res;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// ---- multiplex traversal ---------------------------------------------------------------------------
+struct Graph {
+    const int32_t *u_rowptr; const uint32_t *u_ent;
+    const int32_t *c_rowptr; const int2 *c_ent;
+};
+__device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
+    Graph g;
+    g.u_rowptr = C.u_rowptr + (size_t)r * (C.Ncap + 1); g.u_ent = C.u_ent + (size_t)r * C.ucap;
+    g.c_rowptr = C.c_rowptr + (size_t)r * (C.Ncap + 1); g.c_ent = C.c_ent + (size_t)r * C.ccap;
+    return g;
+}
+
+// Block-cooperative frontier BFS over the union of the nine OUT-neighbour sets
+// (Person._agents_in_radius, entities.py:469-480; ring peeling entities.py:482-524).
+// list[0..nsrc) holds the sources (already written by the caller); level L members are appended at
+// lvl_off[L]..lvl_off[L+1] (lvl_off[0] = 0, lvl_off[1] = nsrc).  One warp expands one frontier node;
+// newly discovered neighbours are compacted with ballot/popc and a single atomicAdd per warp.
+// bitmap: ceil(N/32) words of shared memory, cleared here.  Returns the total list length.
+__device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *list, int nsrc, int depth, int *lvl_off,
+                          int *s_count, unsigned long long &edges) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsrc; i += blockDim.x) { int v = list[i]; atomicOr(&bitmap[v >> 5], 1u << (v & 31)); }
+    if (threadIdx.x == 0) { *s_count = nsrc; lvl_off[0] = 0; lvl_off[1] = nsrc; }
+    __syncthreads();
+    int lane = lane_id(), nw = blockDim.x >> 5;
+    for (int lvl = 1; lvl <= depth; lvl++) {
+        int fb = lvl_off[lvl - 1], fe = lvl_off[lvl];
+        for (int fi = fb + warp_id(); fi < fe; fi += nw) {
+            int u = list[fi];
+            int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1];
+            int b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
+            int len0 = e0 - b0, len = len0 + (e1 - b1);
+            for (int base = 0; base < len; base += 32) {
+                int i = base + lane;
+                int v = -1;
+                if (i < len0) { uint32_t ent = g.u_ent[b0 + i]; if (ENT_MASK(ent)) v = ENT_COL(ent); }
+                else if (i < len) v = g.c_ent[b1 + (i - len0)].x;
+                bool isnew = false;
+                if (v >= 0) {
+                    unsigned bit = 1u << (v & 31);
+                    unsigned old = atomicOr(&bitmap[v >> 5], bit);
+                    isnew = !(old & bit);
+                }
+                unsigned m = __ballot_sync(FULL_MASK, isnew);
+                if (m) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(s_count, __popc(m));
+                    pos = __shfl_sync(FULL_MASK, pos, 0);
+                    if (isnew) list[pos + __popc(m & ((1u << lane) - 1))] = v;
+                }
+            }
+            if (lane == 0) edges += (unsigned long long)len;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) lvl_off[lvl + 1] = *s_count;
+        __syncthreads();
+    }
+    return lvl_off[depth + 1];
+}
+
+// number of friendship entries shared test helper: does row `c` contain a friendship neighbour whose bit is
+// set in `fbits` (bitmap of the initiator's friends)?  Warp-cooperative; all lanes return the result.
+__device__ __forceinline__ bool warp_friend_intersect(const Graph &g, int c, const unsigned *fbits) {
+    int b = g.u_rowptr[c], e = g.u_rowptr[c + 1];
+    bool hit = false;
+    for (int i = b + lane_id(); i < e; i += 32) {
+        uint32_t ent = g.u_ent[i];
+        if (ENT_MASK(ent) & MB_FRIEND) { int v = ENT_COL(ent); if (fbits[v >> 5] & (1u << (v & 31))) hit = true; }
+    }
+    return __any_sync(FULL_MASK, hit);
+}
+
+// Person.social_proximity (entities.py:674-689) given both packed attribute words and the friendship test.
+// fp64, no contraction: ((((0 + ageTerm) + sex) + wealth) + edu) + friends, then / 5.
+__device__ __forceinline__ double social_proximity(uint32_t self_attr, uint32_t tgt_attr, bool friends_shared) {
+    double da = fabs((double)attr_age(tgt_attr) - (double)attr_age(self_attr));
+    double total = 0.0;
+    total = __dadd_rn(total, (da > 18.0) ? 0.0 : __dsub_rn(1.0, __ddiv_rn(da, 18.0)));
+    total = __dadd_rn(total, (((self_attr ^ tgt_attr) & F_MALE) == 0) ? 1.0 : 0.0);
+    total = __dadd_rn(total, (attr_wealth(self_attr) == attr_wealth(tgt_attr)) ? 1.0 : 0.0);
+    total = __dadd_rn(total, (attr_edu(self_attr) == attr_edu(tgt_attr)) ? 1.0 : 0.0);
+    total = __dadd_rn(total, friends_shared ? 1.0 : 0.0);
+    return __ddiv_rn(total, 5.0);
+}
+
+// binary search helpers on sorted rows
+__device__ __forceinline__ int crim_find(const Graph &g, int u, int v) {  // returns count or -1
+    int lo = g.c_rowptr[u], hi = g.c_rowptr[u + 1], end = hi;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (g.c_ent[m].x < v) lo = m + 1; else hi = m; }
+    if (lo < end) { int2 e = g.c_ent[lo]; if (e.x == v) return e.y; }
+    return -1;
+}
+__device__ __forceinline__ uint32_t static_find_mask(const Graph &g, int u, int v) {  // layer mask of v in u's row or 0
+    int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (ENT_COL(g.u_ent[m]) < v) lo = m + 1; else hi = m; }
+    if (lo < end) { uint32_t e = g.u_ent[lo]; if (ENT_COL(e) == v) return ENT_MASK(e); }
+    return 0u;
+}

@@ -1,0 +1,1160 @@
+// poc_kernels.cuh -- the hot-path kernels (sm_100a).  Included once by poc_api.cu.
+// Every kernel is batched: blockIdx.y (or blockIdx.x for the one-block-per-replica kernels) selects the
+// replica, so one launch serves the whole ensemble batch.
+#pragma once
+#include "poc_device.cuh"
+
+#define RP(ptr, r, stride) ((ptr) + (size_t)(r) * (size_t)(stride))
+#define MAX_RADIUS 16
+#define EMB_SCALE 17179869184.0 /* 2^34 */
+#define DIST_INF 0x7ff0000000000000ull
+#define DCAP 4096 /* ball size up to which the SSSP distance array lives in shared memory */
+
+// ============================================================================ state I/O
+struct StageCols {
+    uint8_t *alive, *male, *oc_member, *facilitator, *prisoner, *has_job, *has_school, *target;
+    int8_t *job_level, *education_level, *wealth_level;
+    int32_t *age, *birth_tick, *num_crimes, *num_crimes_tick, *father, *new_recruit;
+    double *propensity, *tendency, *sentence, *arrest_weight;
+};
+
+__global__ void k_pack_agents(DevCtx C, int r, int n, StageCols S, int *err) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    int age = S.age[a], job = S.job_level[a], edu = S.education_level[a], w = S.wealth_level[a];
+    if (age < 0 || job < 0 || job > 15 || edu < 0 || edu > 15 || w < 0 || w > 15) atomicExch(err, 1);
+    if (age > 255) age = 255;
+    uint32_t x = (uint32_t)age | ((uint32_t)(job & 15) << 16) | ((uint32_t)(edu & 15) << 20) | ((uint32_t)(w & 15) << 24);
+    if (S.alive[a]) x |= F_ALIVE;
+    if (S.male[a]) x |= F_MALE;
+    if (S.oc_member[a]) x |= F_OC;
+    if (S.facilitator[a]) x |= F_FAC;
+    if (S.prisoner[a]) x |= F_PRISONER;
+    if (S.has_job[a]) x |= F_HASJOB;
+    if (S.has_school[a]) x |= F_HASSCHOOL;
+    if (S.target[a]) x |= F_TARGET;
+    size_t o = (size_t)r * C.Ncap + a;
+    C.attr[o] = x;
+    C.birth[o] = S.birth_tick[a]; C.ncrimes[o] = S.num_crimes[a]; C.ncrimes_tick[o] = S.num_crimes_tick[a];
+    C.father[o] = S.father[a]; C.new_recruit[o] = S.new_recruit[a];
+    C.propensity[o] = S.propensity[a]; C.tendency[o] = S.tendency[a]; C.sentence[o] = S.sentence[a];
+    C.arrest_w[o] = S.arrest_weight[a];
+    C.emb_stamp[o] = 0;
+}
+
+__global__ void k_unpack_agents(DevCtx C, int r, int n, StageCols S) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    size_t o = (size_t)r * C.Ncap + a;
+    uint32_t x = C.attr[o];
+    S.age[a] = attr_age(x); S.job_level[a] = (int8_t)attr_job(x); S.education_level[a] = (int8_t)attr_edu(x);
+    S.wealth_level[a] = (int8_t)attr_wealth(x);
+    S.alive[a] = (x & F_ALIVE) != 0; S.male[a] = (x & F_MALE) != 0; S.oc_member[a] = (x & F_OC) != 0;
+    S.facilitator[a] = (x & F_FAC) != 0; S.prisoner[a] = (x & F_PRISONER) != 0; S.has_job[a] = (x & F_HASJOB) != 0;
+    S.has_school[a] = (x & F_HASSCHOOL) != 0; S.target[a] = (x & F_TARGET) != 0;
+    S.birth_tick[a] = C.birth[o]; S.num_crimes[a] = C.ncrimes[o]; S.num_crimes_tick[a] = C.ncrimes_tick[o];
+    S.father[a] = C.father[o]; S.new_recruit[a] = C.new_recruit[o];
+    S.propensity[a] = C.propensity[o]; S.tendency[a] = C.tendency[o]; S.sentence[a] = C.sentence[o];
+    S.arrest_weight[a] = C.arrest_w[o];
+}
+
+// The eight non-criminal layers arrive as separate CSRs (rows ascending); one thread k-way-merges the
+// rows of one agent into packed {slot, layer mask} entries.  fill = 0: count only.
+struct StageLayers { const int32_t *rowptr[8]; const int32_t *col[8]; };
+__global__ void k_union_rows(DevCtx C, int r, int n, StageLayers L, int *lens, int fill, int *err) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    int cur[8], end[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) { cur[l] = L.rowptr[l][a]; end[l] = L.rowptr[l][a + 1]; }
+    int out = fill ? RP(C.u_rowptr, r, C.Ncap + 1)[a] : 0, cnt = 0, prev = -1;
+    uint32_t *ent = RP(C.u_ent, r, C.ucap);
+    for (;;) {
+        int mn = 0x7fffffff;
+#pragma unroll
+        for (int l = 0; l < 8; l++) if (cur[l] < end[l]) { int v = L.col[l][cur[l]]; if (v < mn) mn = v; }
+        if (mn == 0x7fffffff) break;
+        if (mn <= prev || mn < 0 || mn >= n || mn == a) atomicExch(err, 2);  // unsorted row / bad slot / self loop
+        prev = mn;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) if (cur[l] < end[l] && L.col[l][cur[l]] == mn) { mask |= 1u << l; cur[l]++; }
+        if (fill) ent[out + cnt] = (uint32_t)mn | (mask << 24);
+        cnt++;
+    }
+    if (!fill) lens[a] = cnt;
+}
+
+// single-block exclusive scan: out[0..n] (out[n] = total)
+__global__ void __launch_bounds__(1024) k_exscan_i32(const int *in, int *out, int n) {
+    __shared__ int ws[33];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x, v = (i < n) ? in[i] : 0, tot;
+        int ex = block_exscan(v, ws, &tot);
+        if (i < n) out[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void k_pack_criminal(DevCtx C, int r, int n, const int32_t *rowptr, const int32_t *col, const int32_t *co, int *err) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > n) return;
+    RP(C.c_rowptr, r, C.Ncap + 1)[a] = rowptr[a];
+    if (a == n) return;
+    int2 *ent = RP(C.c_ent, r, C.ccap);
+    int prev = -1;
+    for (int e = rowptr[a]; e < rowptr[a + 1]; e++) {
+        int v = col[e];
+        if (v <= prev || v < 0 || v >= n || v == a) atomicExch(err, 3);
+        prev = v;
+        ent[e] = make_int2(v, co ? co[e] : 0);
+    }
+}
+
+// ============================================================================ tick bookkeeping
+// model.py:236-238 (+ extra.py:359-361): per scheduled agent zero the this-tick counter and recompute age.
+__global__ void k_begin_tick(DevCtx C, int tick) {
+    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    size_t o = (size_t)r * C.Ncap + a;
+    uint32_t x = C.attr[o];
+    if (!(x & F_ALIVE)) return;
+    int tpy = C.params[r].ticks_per_year;
+    int dt = tick - C.birth[o];
+    int age = (dt >= 0) ? dt / tpy : -((-dt + tpy - 1) / tpy);
+    age = age < 0 ? 0 : (age > 255 ? 255 : age);
+    C.attr[o] = (x & ~0xffu) | (uint32_t)age;
+    C.ncrimes_tick[o] = 0;
+}
+
+// model.py:279-283
+__global__ void k_end_tick(DevCtx C) {
+    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    size_t o = (size_t)r * C.Ncap + a;
+    uint32_t x = C.attr[o];
+    if ((x & (F_ALIVE | F_PRISONER)) != (F_ALIVE | F_PRISONER)) return;
+    double s = C.sentence[o] - 1.0;
+    C.sentence[o] = s;
+    if (s == 0.0) C.attr[o] = x & ~F_PRISONER;
+}
+
+// Age/sex cell partition (model.py:1172-1173, 1430-1432): stable (ascending slot) member lists per cell,
+// the strict counts calculate_crime_multiplier uses (model.py:1152, Q8) and, when `yearly`, the multiplier.
+// One block per replica.
+__global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
+    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const poc_params &P = C.params[r];
+    int nc = P.n_cells;
+    __shared__ unsigned char lut[512], luts[512];
+    __shared__ int cnt[POC_MAX_CELLS], cnts[POC_MAX_CELLS], base[POC_MAX_CELLS + 1], running[POC_MAX_CELLS];
+    __shared__ int wc[32][POC_MAX_CELLS + 1];
+    __shared__ int nalive;
+    for (int i = tid; i < 512; i += blockDim.x) {
+        int male = i >> 8, age = i & 255, c = 255, cs = 255;
+        for (int k = nc - 1; k >= 0; k--)
+            if (P.cell_male[k] == male) {
+                if (P.cell_age_from[k] <= age && age <= P.cell_age_to[k]) c = k;
+                if (P.cell_age_from[k] < age && age <= P.cell_age_to[k]) cs = k;
+            }
+        lut[i] = (unsigned char)c; luts[i] = (unsigned char)cs;
+    }
+    if (tid < POC_MAX_CELLS) { cnt[tid] = 0; cnts[tid] = 0; running[tid] = 0; }
+    if (tid == 0) nalive = 0;
+    __syncthreads();
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    int nround = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
+    for (int a = tid; a < nround; a += blockDim.x) {
+        int c = 255, cs = 255;
+        bool alive = false;
+        if (a < n) { uint32_t x = attr[a]; alive = x & F_ALIVE; if (alive) { int i = ((x & F_MALE) ? 256 : 0) | attr_age(x); c = lut[i]; cs = luts[i]; } }
+        unsigned ma = __ballot_sync(FULL_MASK, alive);
+        if (lane == 0 && ma) atomicAdd(&nalive, __popc(ma));
+        for (int k = 0; k < nc; k++) {
+            unsigned m = __ballot_sync(FULL_MASK, c == k), ms = __ballot_sync(FULL_MASK, cs == k);
+            if (lane == 0) { if (m) atomicAdd(&cnt[k], __popc(m)); if (ms) atomicAdd(&cnts[k], __popc(ms)); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int k = 0; k < nc; k++) { base[k] = s; s += cnt[k]; }
+        base[nc] = s;
+        int32_t *co = RP(C.cell_off, r, POC_MAX_CELLS + 1);
+        for (int k = 0; k <= nc; k++) co[k] = base[k];
+        for (int k = 0; k < nc; k++) RP(C.cell_strict, r, POC_MAX_CELLS)[k] = cnts[k];
+        RP(C.counters, r, CN_COUNT)[CN_N_ALIVE] = nalive;
+        if (yearly) {  // model.py:1150-1157, left-to-right float64
+            double total = 0.0;
+            for (int k = 0; k < nc; k++) total += P.cell_c[k] * (double)cnts[k];
+            C.crime_mult[r] = P.crimes_yearly_per10k / 10000.0 * (double)nalive / total;
+        }
+    }
+    __syncthreads();
+    int32_t *members = RP(C.cell_members, r, C.Ncap);
+    int nw = blockDim.x >> 5;
+    for (int a0 = 0; a0 < nround; a0 += blockDim.x) {
+        int a = a0 + tid, c = 255;
+        if (a < n) { uint32_t x = attr[a]; if (x & F_ALIVE) c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)]; }
+        int myrank = 0;
+        for (int k = 0; k < nc; k++) {
+            unsigned m = __ballot_sync(FULL_MASK, c == k);
+            if (c == k) myrank = __popc(m & ((1u << lane) - 1));
+            if (lane == 0) wc[w][k] = __popc(m);
+        }
+        __syncthreads();
+        if (tid < nc) {  // exclusive prefix over warps for cell `tid`
+            int s = 0;
+            for (int ww = 0; ww < nw; ww++) { int t = wc[ww][tid]; wc[ww][tid] = s; s += t; }
+            cnt[tid] = s;  // tile total
+        }
+        __syncthreads();
+        if (c != 255) members[base[c] + running[c] + wc[w][c] + myrank] = a;
+        __syncthreads();
+        if (tid < nc) running[tid] += cnt[tid];
+        __syncthreads();
+    }
+}
+
+// ============================================================================ A1 criminal tendency
+// Person.update_criminal_tendency, entities.py:337-367 (quirks Q2, Q3 kept).  One thread per agent.
+__global__ void k_tendency_pre(DevCtx C) {
+    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    size_t o = (size_t)r * C.Ncap + a;
+    uint32_t x = C.attr[o];
+    if (!(x & F_ALIVE)) return;
+    const poc_params &P = C.params[r];
+    int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, cell = -1;
+    for (int k = 0; k < P.n_cells; k++)
+        if (P.cell_male[k] == male && P.cell_age_from[k] <= age && age <= P.cell_age_to[k]) { cell = k; break; }
+    if (cell < 0) return;
+    Graph g = graph_of(C, r);
+    const int32_t *ncr = RP(C.ncrimes, r, C.Ncap);
+    double t = P.cell_c[cell];
+    t *= (attr_job(x) == 1) ? 1.30 : 1.0;
+    t *= (attr_edu(x) >= 2) ? 0.94 : 1.0;
+    t *= (C.propensity[o] > P.propensity_threshold) ? 1.97 : 1.0;
+    t *= 1.62;
+    int fam = 0, famc = 0, nf = 0, np = 0, pc = 0;
+    for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
+        uint32_t ent = g.u_ent[e];
+        uint32_t m = ENT_MASK(ent);
+        int f = __popc(m & (MB_SIB | MB_OFF | MB_PARTNER));
+        bool crim = false;
+        if (f || (m & MB_PROF)) crim = ncr[ENT_COL(ent)] > 0;
+        fam += f; if (crim) famc += f;
+        if (m & MB_FRIEND) nf++;
+        if (m & MB_PROF) { np++; if (crim) pc++; }
+    }
+    t *= (fam > 0 && ((double)famc / (double)fam) > 0.5) ? 1.45 : 1.0;
+    bool neigh = nf > 0;
+    if (!neigh && np > 0) neigh = ((double)pc / (double)(nf + np)) > 0.5;
+    t *= neigh ? 1.81 : 1.0;
+    t *= (x & F_OC) ? 4.50 : 1.0;
+    C.tendency[o] = t;
+}
+
+// numpy's pairwise add.reduce over tend[idx[0..n)] (what np.mean uses at model.py:1182)
+__device__ double pw_sum(const double *t, const int *idx, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r += t[idx[i]];
+        return r;
+    } else if (n <= 128) {
+        double q[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) q[j] = t[idx[j]];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j] += t[idx[i + j]];
+        }
+        double res = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        for (; i < n; i++) res += t[idx[i]];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return pw_sum(t, idx, n2) + pw_sum(t, idx + n2, n - n2);
+}
+
+// epsilon re-centring per cell, model.py:1180-1184.  One block per replica, one thread per cell for the
+// (order-defined) mean, then all threads add epsilon.
+__global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C) {
+    int r = blockIdx.x, tid = threadIdx.x;
+    const poc_params &P = C.params[r];
+    __shared__ double eps[POC_MAX_CELLS];
+    __shared__ int off[POC_MAX_CELLS + 1];
+    const int32_t *members = RP(C.cell_members, r, C.Ncap);
+    double *tend = RP(C.tendency, r, C.Ncap);
+    if (tid <= P.n_cells) off[tid] = RP(C.cell_off, r, POC_MAX_CELLS + 1)[tid];
+    __syncthreads();
+    // spread the per-cell chains over different warps
+    if ((tid & 31) == 0 && (tid >> 5) < P.n_cells) {
+        int k = tid >> 5, m = off[k + 1] - off[k];
+        eps[k] = (m > 0) ? P.cell_c[k] - pw_sum(tend, members + off[k], m) / (double)m : 0.0;
+    }
+    __syncthreads();
+    int total = off[P.n_cells];
+    for (int i = tid; i < total; i += blockDim.x) {
+        int k = 0;
+        while (i >= off[k + 1]) k++;
+        tend[members[i]] += eps[k];
+    }
+}
+
+// ============================================================================ A3 crime draw
+// model.py:1427-1440 + extra.py:102-149.  One block per replica.  The CDF is built exactly as
+// weighted_n_of + Generator.choice build it: optional min-shift, left-to-right sum, p/sum, sequential
+// cumsum, divide by the last element; one lane per cell runs the two order-defined chains.
+__global__ void __launch_bounds__(512) k_draw(DevCtx C, int tick) {
+    int r = blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    const poc_params &P = C.params[r];
+    int nc = P.n_cells;
+    __shared__ int off[POC_MAX_CELLS + 1], ncr[POC_MAX_CELLS], coff[POC_MAX_CELLS + 1], nz[POC_MAX_CELLS];
+    __shared__ double mn[POC_MAX_CELLS], last[POC_MAX_CELLS];
+    __shared__ int neg[POC_MAX_CELLS];
+    const int32_t *members = RP(C.cell_members, r, C.Ncap);
+    const double *tend = RP(C.tendency, r, C.Ncap);
+    double *cdf = RP(C.cdf, r, C.Ncap);
+    int *cn = RP(C.counters, r, CN_COUNT);
+    if (tid <= nc) off[tid] = RP(C.cell_off, r, POC_MAX_CELLS + 1)[tid];
+    __syncthreads();
+    if (tid < nc) {
+        int m = off[tid + 1] - off[tid];
+        double target = P.cell_c[tid] * (double)m / (double)P.ticks_per_year * C.crime_mult[r];
+        int k = (int)rint(target);  // np.round: half to even (Q1)
+        ncr[tid] = k > 0 ? k : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int k = 0; k < nc; k++) { coff[k] = s; s += ncr[k]; }
+        coff[nc] = s;
+        if (s > C.Ccap) { atomicExch(&cn[CN_ERROR], 10); s = C.Ccap; for (int k = 0; k <= nc; k++) if (coff[k] > s) coff[k] = s; }
+        C.n_crimes[r] = s;
+        C.n_search[r] = 0;
+        C.n_pairs[r] = 0;
+        cn[CN_TICK_CRIMES] = s; cn[CN_TICK_MEMBERS] = 0; cn[CN_TICK_ARRESTS] = 0; cn[CN_TICK_EMB] = 0; cn[CN_TICK_RECRUITED] = 0;
+        cn[CN_NUMBER_CRIMES] += s;
+        C.n_emb[r] = 0; C.n_emb[C.R + r] = 0;
+        C.n_arrested[r] = 0;
+    }
+    // stage weights cell-ordered, and per-cell min / any-negative (one warp per cell, round robin)
+    int total = off[nc];
+    for (int i = tid; i < total; i += blockDim.x) cdf[i] = tend[members[i]];
+    __syncthreads();
+    for (int k = w; k < nc; k += nw) {
+        double m = INFINITY;
+        bool ng = false;
+        for (int i = off[k] + lane; i < off[k + 1]; i += 32) { double v = cdf[i]; m = fmin(m, v); ng |= (v < 0.0); }
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL_MASK, m, o));
+        ng = __any_sync(FULL_MASK, ng);
+        if (lane == 0) { mn[k] = m; neg[k] = ng; }
+    }
+    __syncthreads();
+    // the two sequential chains, one thread per cell, spread over warps
+    if (lane == 0 && w < nc) {
+        for (int k = w; k < nc; k += nw) {
+            if (ncr[k] == 0) { nz[k] = 1; last[k] = 1.0; continue; }
+            int b = off[k], e = off[k + 1];
+            double sump = 0.0, shift = neg[k] ? mn[k] : 0.0;
+            int nzz = 0;
+            if (neg[k]) { for (int i = b; i < e; i++) { double p = cdf[i] - shift; cdf[i] = p; sump += p; nzz += (p != 0.0); } }
+            else { for (int i = b; i < e; i++) { double p = cdf[i]; sump += p; nzz += (p != 0.0); } }
+            double acc = 0.0;
+            if (sump != 0.0) for (int i = b; i < e; i++) { acc += cdf[i] / sump; cdf[i] = acc; }
+            nz[k] = (sump == 0.0) ? 0 : nzz;
+            last[k] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += blockDim.x) {
+        int k = 0;
+        while (i >= off[k + 1]) k++;
+        if (ncr[k] > 0 && nz[k] > 0) cdf[i] = cdf[i] / last[k];
+    }
+    __syncthreads();
+    // the draws
+    int ncrimes = coff[nc];
+    const int32_t *hdr = RP(C.rp_hdr, r, 8);
+    bool replay = hdr[0] != 0;
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    for (int j = tid; j < ncrimes; j += blockDim.x) {
+        int k = 0;
+        while (j >= coff[k + 1]) k++;
+        double u1, u2;
+        if (replay) {
+            if (j < hdr[1]) { u1 = RP(C.rp_u_init, r, C.Ccap)[j]; u2 = RP(C.rp_u_size, r, C.Ccap)[j]; }
+            else { u1 = 0.0; u2 = 0.0; atomicExch(&cn[CN_ERROR], 3); }
+        } else philox_u2(C.philox_key[r], tick, ST_CRIME, j, u1, u2);
+        size_t o = (size_t)r * C.Ccap + j;
+        if (nz[k] < 1) {  // the reference raises IndexError here (weighted_one_of on all-zero weights)
+            atomicExch(&cn[CN_ERROR], 1);
+            C.crime_init[o] = -1; C.crime_k[o] = 0; C.crime_flags[o] = 0; C.cr_nacc[o] = 0; C.cr_state[o] = 4;
+            continue;
+        }
+        int m = off[k + 1] - off[k];
+        int ii = ss_right(cdf + off[k], m, u1);
+        if (ii >= m) ii = m - 1;
+        int init = members[off[k] + ii];
+        int si = ss_right(P.size_cdf, P.n_sizes, u2);
+        if (si >= P.n_sizes) si = P.n_sizes - 1;
+        int kk = P.size_n[si] - 1;
+        uint32_t ia = attr[init];
+        C.crime_init[o] = init; C.crime_k[o] = kk; C.crime_flags[o] = (ia & F_OC) ? 1 : 0;
+        // find_accomplices prologue, entities.py:419-426
+        int target = kk, fn = 0;
+        if (kk > 0) { fn = ((double)kk >= P.threshold_use_facilitators) && !(ia & F_FAC); if (fn) target -= 1; }
+        C.cr_target[o] = target; C.cr_nacc[o] = 0; C.cr_d[o] = 1; C.cr_fails[o] = 0;
+        C.cr_state[o] = (kk > 0) ? (fn ? 2 : 0) : 4;
+        if (kk > 0) { int pos = atomicAdd(&C.n_search[r], 1); RP(C.search_list, r, C.Ccap)[pos] = j; }
+    }
+}
+
+// ============================================================================ A4-A6 accomplice search
+// Person.find_accomplices, entities.py:413-455.  One block per crime with k >= 1.
+// cr_state bits: 1 = ring cr_d built and its embeddedness requested (OC initiators), 2 = facilitator still
+// needed, 4 = done.  Non-OC initiators run to completion in one call; an OC initiator needs
+// oc_embeddedness of every ring member (candidates_weight, entities.py:465-466), so its block requests the
+// evaluations, returns, and resumes in the next round after k_embeddedness has run.
+struct ArgBest { double key; int slot; int idx; };
+__device__ __forceinline__ bool better(double k1, int s1, double k2, int s2) { return (k1 < k2) || (k1 == k2 && s1 < s2); }
+
+__device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch, int parity, unsigned *bitmap,
+                             unsigned *fbits, int *list, double *keys, unsigned long long &edges) {
+    __shared__ int s_count, lvl_off[MAX_RADIUS + 3];
+    __shared__ int s_st[6];  // nacc, target, mrem, facneeded, pickidx, stop
+    __shared__ double wkey[8];
+    __shared__ int wslot[8], widx[8];
+    int n = C.n_agents[r], nwords = (n + 31) >> 5, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    const poc_params &P = C.params[r];
+    Graph g = graph_of(C, r);
+    size_t o = (size_t)r * C.Ccap + c;
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const double *tend = RP(C.tendency, r, C.Ncap);
+    const double *embv = RP(C.emb_val, r, C.Ncap);
+    int *cn = RP(C.counters, r, CN_COUNT);
+    int *acc = C.cr_acc + o * POC_MAX_GROUP;
+    int init = C.crime_init[o];
+    uint32_t self_attr = attr[init];
+    bool is_oc = (C.crime_flags[o] & 1) != 0;
+    int state = C.cr_state[o], d = C.cr_d[o];
+    int maxrad = P.max_accomplice_radius;
+    if (tid == 0) { s_st[0] = C.cr_nacc[o]; s_st[1] = C.cr_target[o]; s_st[3] = (state >> 1) & 1; s_st[5] = 0; }
+    // bitmap of the initiator's friends (entities.py:687-688)
+    for (int i = tid; i < nwords; i += blockDim.x) fbits[i] = 0u;
+    __syncthreads();
+    for (int e = g.u_rowptr[init] + tid; e < g.u_rowptr[init + 1]; e += blockDim.x) {
+        uint32_t ent = g.u_ent[e];
+        if (ENT_MASK(ent) & MB_FRIEND) { int v = ENT_COL(ent); atomicOr(&fbits[v >> 5], 1u << (v & 31)); }
+    }
+    __syncthreads();
+    bool awaiting = state & 1;
+    while (s_st[0] < s_st[1] && d <= maxrad && !s_st[5]) {
+        if (tid == 0) list[0] = init;
+        __syncthreads();
+        bfs_levels(g, nwords, bitmap, list, 1, d, lvl_off, &s_count, edges);
+        int rb = lvl_off[d], m = lvl_off[d + 1] - rb;
+        if (is_oc && !awaiting) {
+            // request oc_embeddedness for every ring member not yet evaluated this tick (cache: entities.py:531)
+            int32_t *stamp = RP(C.emb_stamp, r, C.Ncap);
+            int32_t *elist = C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
+            int *ecount = &C.n_emb[parity * C.R + r];
+            for (int i = tid; i < m; i += blockDim.x) {
+                int v = list[rb + i];
+                if (atomicExch(&stamp[v], epoch) != epoch) elist[atomicAdd(ecount, 1)] = v;
+            }
+            if (tid == 0) { C.cr_nacc[o] = s_st[0]; C.cr_target[o] = s_st[1]; C.cr_d[o] = d; C.cr_state[o] = 1 | (s_st[3] << 1); }
+            return;
+        }
+        awaiting = false;
+        // candidate keys: warp per candidate
+        for (int i = w; i < m; i += nw) {
+            int cand = list[rb + i];
+            uint32_t ca = attr[cand];
+            bool shared = warp_friend_intersect(g, cand, fbits);
+            if (lane == 0) {
+                double prox = social_proximity(self_attr, ca, shared);
+                double key = is_oc ? -1.0 * ((prox * embv[cand]) * tend[cand]) : prox * tend[cand];
+                keys[i] = key;
+            }
+        }
+        if (tid == 0) s_st[2] = m;
+        __syncthreads();
+        // take the smallest keys first (ascending stable sort, entities.py:429-437; ties: ascending slot)
+        while (s_st[0] < s_st[1] && s_st[2] > 0 && !s_st[5]) {
+            int mrem = s_st[2];
+            double bk = INFINITY; int bs = 0x7fffffff, bi = -1;
+            for (int i = tid; i < mrem; i += blockDim.x) {
+                double k = keys[i]; int s = list[rb + i];
+                if (bi < 0 || better(k, s, bk, bs)) { bk = k; bs = s; bi = i; }
+            }
+            for (int of = 16; of > 0; of >>= 1) {
+                double k2 = __shfl_xor_sync(FULL_MASK, bk, of); int s2 = __shfl_xor_sync(FULL_MASK, bs, of), i2 = __shfl_xor_sync(FULL_MASK, bi, of);
+                if (i2 >= 0 && (bi < 0 || better(k2, s2, bk, bs))) { bk = k2; bs = s2; bi = i2; }
+            }
+            if (lane == 0) { wkey[w] = bk; wslot[w] = bs; widx[w] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int ww = 1; ww < nw; ww++)
+                    if (widx[ww] >= 0 && (bi < 0 || better(wkey[ww], wslot[ww], bk, bs))) { bk = wkey[ww]; bs = wslot[ww]; bi = widx[ww]; }
+                int na = s_st[0];
+                if (na >= POC_MAX_GROUP - 1) { atomicExch(&cn[CN_ERROR], 2); s_st[5] = 1; }
+                else {
+                    acc[na] = bs; s_st[0] = na + 1;
+                    if (attr[bs] & F_FAC) { s_st[1] += 1; s_st[3] = 0; }  // Q6
+                    list[rb + bi] = list[rb + mrem - 1]; keys[bi] = keys[mrem - 1]; s_st[2] = mrem - 1;
+                }
+            }
+            __syncthreads();
+        }
+        d++;
+    }
+    // ---- epilogue, entities.py:439-455
+    int nacc = s_st[0];
+    if (s_st[3] && nacc > 0) {
+        for (int i = tid; i < nacc; i += blockDim.x) list[i] = acc[i];
+        __syncthreads();
+        int total = bfs_levels(g, nwords, bitmap, list, nacc, maxrad, lvl_off, &s_count, edges);
+        // facilitators within max_accomplice_radius of any accomplice
+        int *avail = (int *)keys;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (int i = nacc + tid; i < total; i += blockDim.x) { int v = list[i]; if (attr[v] & F_FAC) avail[atomicAdd(&s_count, 1)] = v; }
+        __syncthreads();
+        int na = s_count;
+        if (na > 0) {
+            const int32_t *hdr = RP(C.rp_hdr, r, 8);
+            int pick = -1;
+            if (hdr[0] && RP(C.rp_fac_pick, r, C.Ccap)[c] >= 0) pick = RP(C.rp_fac_pick, r, C.Ccap)[c];
+            if (pick < 0) {
+                double u = 0.0, u1;
+                if (hdr[0] == 2) u = RP(C.rp_u_init, r, C.Ccap)[c];  // stage-hook mode: u_fac supplied here
+                else if (!hdr[0]) philox_u2(C.philox_key[r], tick, ST_FAC, c, u, u1);
+                int ix = (int)floor(u * (double)na);
+                if (ix >= na) ix = na - 1;
+                if (tid == 0) s_st[4] = -1;
+                __syncthreads();
+                for (int i = tid; i < na; i += blockDim.x) {  // ix-th smallest slot (CANON: ascending slot list)
+                    int v = avail[i], rank = 0;
+                    for (int j = 0; j < na; j++) rank += (avail[j] < v);
+                    if (rank == ix) s_st[4] = v;
+                }
+                __syncthreads();
+                pick = s_st[4];
+            }
+            if (tid == 0 && pick >= 0) {
+                bool dup = false;
+                for (int i = 0; i < nacc; i++) dup |= (acc[i] == pick);
+                if (!dup && nacc < POC_MAX_GROUP - 1) { acc[nacc] = pick; s_st[0] = nacc + 1; }
+            }
+            __syncthreads();
+            nacc = s_st[0];
+        }
+    }
+    if (tid == 0) {
+        int target = s_st[1], fails = 0;
+        if (nacc < target) { atomicAdd(&cn[CN_SIZE_FAILS], 1); fails |= 1; }
+        if ((double)target >= P.threshold_use_facilitators) {
+            bool anyf = (self_attr & F_FAC) != 0;
+            for (int i = 0; i < nacc; i++) anyf |= (attr[acc[i]] & F_FAC) != 0;
+            if (anyf) { atomicAdd(&cn[CN_FAC_CRIMES], 1); fails |= 2; } else { atomicAdd(&cn[CN_FAC_FAILS], 1); fails |= 4; }
+        }
+        C.cr_nacc[o] = nacc; C.cr_target[o] = target; C.cr_d[o] = d; C.cr_state[o] = 4; C.cr_fails[o] = fails;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, int parity) {
+    extern __shared__ unsigned smem_u[];
+    int r = blockIdx.y;
+    int wcap = (C.Ncap + 31) >> 5;
+    unsigned *bitmap = smem_u, *fbits = smem_u + wcap;
+    int slot = blockIdx.y * gridDim.x + blockIdx.x;
+    int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
+    double *keys = C.scr_key + (size_t)slot * (C.Ncap + 1);
+    unsigned long long edges = 0;
+    // the next round's request list must start empty; nobody appends to it during this launch
+    if (blockIdx.x == 0 && threadIdx.x == 0) C.n_emb[(parity ^ 1) * C.R + r] = 0;
+    int ns = C.n_search[r];
+    for (int item = blockIdx.x; item < ns; item += gridDim.x) {
+        int c = RP(C.search_list, r, C.Ccap)[item];
+        if (C.cr_state[(size_t)r * C.Ccap + c] & 4) continue;
+        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, edges);
+        __syncthreads();
+    }
+    edges = warp_sum_u64(edges);
+    if (lane_id() == 0 && edges) atomicAdd(&C.edges[r], edges);
+}
+
+// ============================================================================ A7 OC embeddedness
+// Person.oc_embeddedness, entities.py:526-558 + ProtonOC.update_meta_links, model.py:1515-1536, on the
+// caller's own ball.  One block per evaluation:
+//   1. radius-R ball by frontier BFS (shared-memory bitmap);
+//   2. dense local index = rank of the slot in the bitmap (per-word popcount prefix);
+//   3. SSSP from the caller over the induced meta graph, edge weight 1/(#shared layers + co-offences),
+//      by iterated relaxation with 64-bit atomicMin on the distance bit patterns (non-negative doubles
+//      order like integers) until a fixed point: the same least fixed point Dijkstra reaches;
+//   4. sum(1/dist) over OC members / over the ball, accumulated in 2^-34 fixed point (order independent).
+__global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
+    extern __shared__ unsigned smem_u[];
+    __shared__ int s_count, lvl_off[MAX_RADIUS + 3], s_flag[2], ws[33];
+    __shared__ unsigned long long s_num, s_den;
+    __shared__ unsigned long long s_dist[DCAP];
+    int r = blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
+    int tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    unsigned *bitmap = smem_u;
+    int *wprefix = (int *)(smem_u + wcap);
+    int slot = blockIdx.y * gridDim.x + blockIdx.x;
+    int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
+    unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
+    const poc_params &P = C.params[r];
+    Graph g = graph_of(C, r);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    double *embv = RP(C.emb_val, r, C.Ncap);
+    const int32_t *elist = C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
+    int ne = C.n_emb[parity * C.R + r];
+    int R = P.oc_embeddedness_radius;
+    unsigned long long edges = 0;
+    int nevals = 0;
+    for (int item = blockIdx.x; item < ne; item += gridDim.x) {
+        int self = elist[item];
+        if (tid == 0) { list[0] = self; s_flag[0] = 0; }
+        __syncthreads();
+        int total = bfs_levels(g, nwords, bitmap, list, 1, R, lvl_off, &s_count, edges);
+        int nb = total - 1;
+        bool anyoc = false;
+        for (int i = 1 + tid; i < total; i += blockDim.x) anyoc |= (attr[list[i]] & F_OC) != 0;
+        if (anyoc) s_flag[0] = 1;
+        __syncthreads();
+        if (!s_flag[0]) { if (tid == 0) embv[self] = 0.0; __syncthreads(); continue; }
+        nevals++;
+        // per-word exclusive popcount prefix -> rank(v)
+        {
+            __shared__ int carry;
+            if (tid == 0) carry = 0;
+            __syncthreads();
+            for (int base = 0; base < nwords; base += blockDim.x) {
+                int i = base + tid, v = (i < nwords) ? __popc(bitmap[i]) : 0, tot;
+                int ex = block_exscan(v, ws, &tot);
+                if (i < nwords) wprefix[i] = carry + ex;
+                __syncthreads();
+                if (tid == 0) carry += tot;
+                __syncthreads();
+            }
+        }
+        unsigned long long *dist = (total <= DCAP) ? s_dist : gdist;
+#define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
+        for (int i = tid; i < total; i += blockDim.x) dist[i] = DIST_INF;
+        __syncthreads();
+        if (tid == 0) { dist[RANK(self)] = 0ull; s_flag[1] = 1; }
+        __syncthreads();
+        int rounds = 0;
+        while (s_flag[1]) {
+            __syncthreads();
+            if (tid == 0) s_flag[1] = 0;
+            __syncthreads();
+            bool changed = false;
+            for (int i = w; i < total; i += nw) {
+                int u = list[i], ru = RANK(u);
+                int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1], b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
+                int len0 = e0 - b0, len = len0 + (e1 - b1);
+                for (int j = lane; j < len; j += 32) {
+                    int v, wgt;
+                    if (j < len0) {
+                        uint32_t ent = g.u_ent[b0 + j];
+                        v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
+                        if (wgt == 0) continue;  // cleared by an arrest (Q11)
+                        if (!(bitmap[v >> 5] & (1u << (v & 31)))) continue;
+                        if (e1 > b1) { int cc = crim_find(g, u, v); if (cc > 0) wgt += cc; }
+                    } else {
+                        int2 ce = g.c_ent[b1 + (j - len0)];
+                        v = ce.x; wgt = ce.y;
+                        if (!(bitmap[v >> 5] & (1u << (v & 31)))) continue;
+                        if (static_find_mask(g, u, v)) continue;  // counted with the static entry
+                        if (wgt <= 0) continue;                    // the reference divides by zero here
+                    }
+                    int rv = RANK(v);
+                    double wt = 1.0 / (double)wgt;
+                    double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
+                    // undirected meta edge (CANON: each direction relaxes with its own weight = max multiplicity)
+                    double nv = du + wt, nu = dv + wt;
+                    if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
+                    if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
+                }
+                if (lane == 0) edges += (unsigned long long)len;
+            }
+            if (changed) s_flag[1] = 1;
+            __syncthreads();
+            if (++rounds > total + 2) break;  // cannot happen with positive weights
+        }
+        if (tid == 0) { s_num = 0ull; s_den = 0ull; }
+        __syncthreads();
+        unsigned long long num = 0, den = 0;
+        for (int i = 1 + tid; i < total; i += blockDim.x) {
+            int v = list[i];
+            double dv = __longlong_as_double((long long)dist[RANK(v)]);
+            long long q = __double2ll_rn((1.0 / dv) * EMB_SCALE);
+            den += (unsigned long long)q;
+            if (attr[v] & F_OC) num += (unsigned long long)q;
+        }
+        num = warp_sum_u64(num); den = warp_sum_u64(den);
+        if (lane == 0) { atomicAdd(&s_num, num); atomicAdd(&s_den, den); }
+        __syncthreads();
+        if (tid == 0) embv[self] = (double)(long long)s_num / (double)(long long)s_den;
+        __syncthreads();
+#undef RANK
+        (void)nb;
+    }
+    edges = warp_sum_u64(edges);
+    if (lane == 0 && edges) atomicAdd(&C.edges[r], edges);
+    if (tid == 0 && nevals) atomicAdd(&RP(C.counters, r, CN_COUNT)[CN_TICK_EMB], nevals);
+}
+
+// ============================================================================ A8 commit: groups, counters, link merge
+// ProtonOC.commit_crime, model.py:1487-1504 + Person.add_criminal_link, entities.py:215-224, for all groups
+// of the tick at once: canonical groups, per-agent crime counters, ordered co-offender pairs -> bitonic sort
+// -> dedup with multiplicity -> merge into the criminal CSR (new links enter with 0 and every co-offence
+// adds 1).  One block per replica.
+__global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
+    int r = blockIdx.x, tid = threadIdx.x, n = C.n_agents[r];
+    __shared__ int ws[33];
+    __shared__ int carry, s_np;
+    const poc_params &P = C.params[r];
+    int *cn = RP(C.counters, r, CN_COUNT);
+    int ncr = C.n_crimes[r];
+    int32_t *goff = RP(C.group_off, r, C.Ccap + 1), *gmem = RP(C.group_mem, r, C.Mcap);
+    unsigned long long *pairs = RP(C.pairs, r, C.Pcap);
+    int32_t *pcnt = RP(C.pair_cnt, r, C.Pcap);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const double *tend = RP(C.tendency, r, C.Ncap);
+    int32_t *ncrimes = RP(C.ncrimes, r, C.Ncap), *ncrimes_tick = RP(C.ncrimes_tick, r, C.Ncap);
+    Graph g = graph_of(C, r);
+    // ---- group offsets (flattened criminals list, model.py:1461)
+    if (tid == 0) { carry = 0; s_np = 0; }
+    __syncthreads();
+    for (int base = 0; base < ncr; base += blockDim.x) {
+        int c = base + tid, gs = 0, tot;
+        if (c < ncr) { size_t o = (size_t)r * C.Ccap + c; gs = (C.crime_init[o] >= 0) ? C.cr_nacc[o] + 1 : 0; }
+        int ex = block_exscan(gs, ws, &tot);
+        if (c < ncr) goff[c] = carry + ex;
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { goff[ncr] = carry; cn[CN_TICK_MEMBERS] = carry; if (carry > C.Mcap) atomicExch(&cn[CN_ERROR], 11); }
+    __syncthreads();
+    if (carry > C.Mcap) return;
+    // ---- canonical groups (accomplices ascending slot, initiator last), counters, ordered pairs
+    for (int c = tid; c < ncr; c += blockDim.x) {
+        size_t o = (size_t)r * C.Ccap + c;
+        int init = C.crime_init[o];
+        if (init < 0) continue;
+        int na = C.cr_nacc[o];
+        int grp[POC_MAX_GROUP];
+        const int *acc = C.cr_acc + o * POC_MAX_GROUP;
+        for (int i = 0; i < na; i++) {  // insertion sort
+            int v = acc[i], j = i;
+            while (j > 0 && grp[j - 1] > v) { grp[j] = grp[j - 1]; j--; }
+            grp[j] = v;
+        }
+        grp[na] = init;
+        int gs = na + 1, b = goff[c];
+        for (int i = 0; i < gs; i++) { gmem[b + i] = grp[i]; atomicAdd(&ncrimes[grp[i]], 1); atomicAdd(&ncrimes_tick[grp[i]], 1); }
+        if (gs > P.this_is_a_big_crime && tend[init] < P.good_guy_threshold) atomicAdd(&cn[CN_BIG_CRIME], 1);
+        if (gs > 1) {
+            int pos = atomicAdd(&s_np, gs * (gs - 1));
+            if (pos + gs * (gs - 1) <= C.Pcap) {
+                for (int i = 0; i < gs; i++)
+                    for (int j = 0; j < gs; j++)
+                        if (i != j) pairs[pos++] = ((unsigned long long)(unsigned)grp[i] << 32) | (unsigned)grp[j];
+            }
+        }
+    }
+    __syncthreads();
+    int np = s_np;
+    if (np > C.Pcap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 12); return; }
+    int32_t *rp_new = RP(C.c_rowptr_tmp, r, C.Ncap + 1);
+    int2 *ent_new = RP(C.c_ent_tmp, r, C.ccap);
+    int32_t *addlen = RP(C.c_addlen, r, C.Ncap);
+    if (np == 0) { if (tid == 0) C.n_pairs[r] = 0; return; }  // no multi-member group: criminal layer unchanged
+    // ---- bitonic sort of the ordered pairs
+    int np2 = 1;
+    while (np2 < np) np2 <<= 1;
+    for (int i = np + tid; i < np2; i += blockDim.x) pairs[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = pairs[i], b = pairs[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { pairs[i] = b; pairs[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // ---- dedup with multiplicity (in place; unique pair u gets pcnt[u] = occurrences)
+    for (int i = tid; i < np; i += blockDim.x) pcnt[i] = 0;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < np; base += blockDim.x) {
+        int i = base + tid;
+        bool valid = i < np;
+        unsigned long long me = valid ? pairs[i] : 0ull;
+        bool head = valid && (i == 0 || pairs[i - 1] != me);
+        int tot, ex = block_exscan(head ? 1 : 0, ws, &tot);
+        int run = carry + ex + (head ? 0 : -1);
+        __syncthreads();
+        if (valid) { atomicAdd(&pcnt[run], 1); if (head) pairs[run] = me; }
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    int nu = carry;
+    if (tid == 0) C.n_pairs[r] = nu;
+    // ---- resolve each unique pair against the old rows
+    for (int a = tid; a < n; a += blockDim.x) addlen[a] = 0;
+    __syncthreads();
+    for (int i = tid; i < nu; i += blockDim.x) {
+        int a = (int)(pairs[i] >> 32), b = (int)(pairs[i] & 0xffffffffu);
+        int cab = crim_find(g, a, b), cba = crim_find(g, b, a);
+        int old = (cab >= 0 && cba >= 0) ? cab : 0;  // CANON: a half-present link is re-created with 0
+        pcnt[i] = old + pcnt[i];
+        if (cab < 0) atomicAdd(&addlen[a], 1);
+    }
+    __syncthreads();
+    // ---- new row pointers
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int a = base + tid, v = 0, tot;
+        if (a < n) v = (g.c_rowptr[a + 1] - g.c_rowptr[a]) + addlen[a];
+        int ex = block_exscan(v, ws, &tot);
+        if (a < n) rp_new[a] = carry + ex;
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { rp_new[n] = carry; if (carry > C.ccap) atomicExch(&cn[CN_ERROR], 13); }
+    __syncthreads();
+    if (carry > C.ccap) return;
+    // ---- merge old rows with the new pairs
+    for (int a = tid; a < n; a += blockDim.x) {
+        int ob = g.c_rowptr[a], oe = g.c_rowptr[a + 1], out = rp_new[a];
+        int pb = 0, pe = nu;  // lower_bound of (a,*) in the unique pair list
+        { int lo = 0, hi = nu; unsigned long long key = (unsigned long long)(unsigned)a << 32;
+          while (lo < hi) { int m = (lo + hi) >> 1; if (pairs[m] < key) lo = m + 1; else hi = m; } pb = lo; }
+        pe = pb;
+        while (pe < nu && (int)(pairs[pe] >> 32) == a) pe++;
+        int i = ob, j = pb;
+        while (i < oe || j < pe) {
+            if (j >= pe) { ent_new[out++] = g.c_ent[i++]; continue; }
+            int b = (int)(pairs[j] & 0xffffffffu);
+            if (i < oe && g.c_ent[i].x < b) { ent_new[out++] = g.c_ent[i++]; continue; }
+            if (i < oe && g.c_ent[i].x == b) i++;
+            ent_new[out++] = make_int2(b, pcnt[j]); j++;
+        }
+    }
+    __syncthreads();
+    // ---- publish
+    int32_t *rp_cur = RP(C.c_rowptr, r, C.Ncap + 1);
+    int2 *ent_cur = RP(C.c_ent, r, C.ccap);
+    int tot_new = rp_new[n];
+    for (int a = tid; a <= n; a += blockDim.x) rp_cur[a] = rp_new[a];
+    for (int e = tid; e < tot_new; e += blockDim.x) ent_cur[e] = ent_new[e];
+}
+
+// ============================================================================ A9-A11 recruitment and arrests
+// model.py:1452-1485, extra.py:102-132, 223-237, entities.py:573-603.  Order-defined and tiny (a few hundred
+// list entries): one thread per replica follows the reference's sequence exactly.
+__device__ int weighted_cdf(const double *w, int n, double *p, double *cdf) {
+    bool neg = false;
+    for (int i = 0; i < n; i++) if (w[i] < 0.0) { neg = true; break; }
+    double mn = 0.0;
+    if (neg) { mn = w[0]; for (int i = 1; i < n; i++) if (w[i] < mn) mn = w[i]; }
+    double sump = 0.0;
+    int nz = 0;
+    for (int i = 0; i < n; i++) { double v = neg ? (w[i] - mn) : w[i]; p[i] = v; sump += v; if (v != 0.0) nz++; }
+    if (sump == 0.0) return 0;
+    double acc = 0.0;
+    for (int i = 0; i < n; i++) { double q = p[i] / sump; p[i] = q; acc += q; cdf[i] = acc; }
+    double last = cdf[n - 1];
+    for (int i = 0; i < n; i++) cdf[i] /= last;
+    return nz;
+}
+
+__device__ double pw_sum_plain(const double *a, int n) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
+    if (n <= 128) {
+        double q[8];
+        for (int j = 0; j < 8; j++) q[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) q[j] += a[i + j];
+        double res = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return pw_sum_plain(a, n2) + pw_sum_plain(a + n2, n - n2);
+}
+
+__global__ void k_recruit_arrest(DevCtx C, int tick) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C.R) return;
+    const poc_params &P = C.params[r];
+    int *cn = RP(C.counters, r, CN_COUNT);
+    int ncr = C.n_crimes[r];
+    const int32_t *goff = RP(C.group_off, r, C.Ccap + 1), *gmem = RP(C.group_mem, r, C.Mcap);
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const int32_t *father = RP(C.father, r, C.Ncap);
+    int32_t *new_recruit = RP(C.new_recruit, r, C.Ncap);
+    double *arrest_w = RP(C.arrest_w, r, C.Ncap);
+    if (cn[CN_ERROR] >= 11 && cn[CN_ERROR] <= 13) return;
+    int nm = goff[ncr];
+    // A9 recruitment, sequential (a father recruited earlier in the loop counts, model.py:1456-1458)
+    int nrec = 0;
+    for (int gidx = 0; gidx < ncr; gidx++) {
+        if (!(C.crime_flags[(size_t)r * C.Ccap + gidx] & 1)) continue;
+        for (int i = goff[gidx]; i < goff[gidx + 1]; i++) {
+            int a = gmem[i];
+            if (attr[a] & F_OC) continue;
+            new_recruit[a] = tick;
+            attr[a] |= F_OC;
+            nrec++;
+            if (father[a] >= 0 && (attr[father[a]] & F_OC)) cn[CN_OFFSPRING_RECRUITED] += 1;
+            if (attr[a] & F_TARGET) cn[CN_PROTECTED_RECRUITED] += 1;
+        }
+    }
+    cn[CN_RECRUITED] += nrec; cn[CN_TICK_RECRUITED] = nrec;
+    if (nm <= 0) return;
+    // A10 arrest weights
+    Graph g = graph_of(C, r);
+    double *aw = RP(C.aw, r, C.Mcap), *ap = RP(C.ap, r, C.Mcap), *acdf = RP(C.acdf, r, C.Mcap);
+    bool ion = (tick % P.ticks_between_intervention == 0) && P.intervention_start <= tick && tick < P.intervention_end;
+    if (ion && P.facilitator_repression) {
+        for (int i = 0; i < nm; i++) arrest_w[gmem[i]] = (attr[gmem[i]] & F_FAC) ? P.facilitator_repression_multiplier : 1.0;
+    } else {
+        bool anyoc = false;
+        for (int i = 0; i < nm; i++) anyoc |= (attr[gmem[i]] & F_OC) != 0;
+        if (ion && P.oc_boss_repression && anyoc) {
+            // extra.calculate_oc_status over the OC members of the list, duplicates included
+            int noc = 0;
+            double mn = 0.0;
+            for (int i = 0; i < nm; i++) {
+                int a = gmem[i];
+                if (!(attr[a] & F_OC)) { arrest_w[a] = 1.0; continue; }
+                int nn = 0, sumco = 0, cntoc = 0;
+                for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
+                    uint32_t ent = g.u_ent[e];
+                    if (ENT_MASK(ent) && (attr[ENT_COL(ent)] & F_OC)) nn++;
+                }
+                for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
+                    int2 ce = g.c_ent[e];
+                    if (attr[ce.x] & F_OC) { sumco += ce.y; cntoc++; if (!static_find_mask(g, a, ce.x)) nn++; }
+                }
+                double pos = (double)(nn + sumco - cntoc);
+                arrest_w[a] = pos;
+                ap[noc] = pos;
+                if (noc == 0 || pos < mn) mn = pos;
+                noc++;
+            }
+            for (int i = 0; i < noc; i++) ap[i] = ap[i] - mn;
+            double div = pw_sum_plain(ap, noc) / (double)noc;
+            for (int i = 0; i < nm; i++) {
+                int a = gmem[i];
+                if (!(attr[a] & F_OC)) continue;
+                arrest_w[a] = (div > 0.0) ? (arrest_w[a] - mn) / div : 1.0;
+            }
+        } else {
+            for (int i = 0; i < nm; i++) arrest_w[gmem[i]] = 1.0;
+        }
+    }
+    for (int i = 0; i < nm; i++) aw[i] = arrest_w[gmem[i]];
+    double arrest_mod = P.arrests_per_year / (double)P.ticks_per_year / 10000.0 * (double)cn[CN_N_ALIVE];
+    const int32_t *hdr = RP(C.rp_hdr, r, 8);
+    bool replay = hdr[0] == 1;
+    double ua, ub;
+    if (replay) ua = C.rp_u_arrest_count[r]; else philox_u2(C.philox_key[r], tick, ST_ARREST_N, 0, ua, ub);
+    int target = (ua < (arrest_mod - floor(arrest_mod))) ? (int)floor(arrest_mod + 1.0) : 0;  // Q7
+    int nz = weighted_cdf(aw, nm, ap, acdf);
+    if (nz < target) target = nz;
+    int32_t *found = RP(C.arrested, r, C.Mcap);
+    int nfound = 0;
+    if (replay && hdr[4] >= 0) {
+        const int32_t *ai = RP(C.rp_arrest_idx, r, C.Mcap);
+        for (int i = 0; i < hdr[4] && i < target; i++) found[nfound++] = ai[i];
+    } else {
+        int ucur = 0;
+        while (nfound < target) {  // numpy Generator.choice(replace=False, p) (R3)
+            int need = target - nfound;
+            if (nfound > 0) {
+                for (int i = 0; i < nfound; i++) ap[found[i]] = 0.0;
+                double acc = 0.0;
+                for (int i = 0; i < nm; i++) { acc += ap[i]; acdf[i] = acc; }
+                double last = acdf[nm - 1];
+                for (int i = 0; i < nm; i++) acdf[i] /= last;
+            }
+            int base = nfound;
+            for (int j = 0; j < need; j++) {
+                double u, u2;
+                if (replay) { if (ucur >= hdr[2]) { cn[CN_ERROR] = 4; u = 0.0; } else u = RP(C.rp_u_arrest, r, C.Mcap)[ucur]; }
+                else philox_u2(C.philox_key[r], tick, ST_ARREST, ucur, u, u2);
+                ucur++;
+                int ix = ss_right(acdf, nm, u);
+                if (ix >= nm) ix = nm - 1;
+                bool dup = false;
+                for (int q = base; q < nfound; q++) dup |= (found[q] == ix);
+                if (!dup) found[nfound++] = ix;
+            }
+        }
+    }
+    // A11 get_caught
+    double *sentence = RP(C.sentence, r, C.Ncap);
+    uint32_t *uent = RP(C.u_ent, r, C.ucap);
+    for (int i = 0; i < nfound; i++) {
+        int a = gmem[found[i]];
+        found[i] = a;  // report slots
+        cn[CN_PEOPLE_JAILED] += 1;
+        uint32_t x = attr[a] | F_PRISONER;
+        double us, us2;
+        if (replay) { if (i >= hdr[3]) { cn[CN_ERROR] = 5; us = 0.0; } else us = RP(C.rp_u_sentence, r, C.Mcap)[i]; }
+        else philox_u2(C.philox_key[r], tick, ST_SENT, i, us, us2);
+        int si = ss_right((x & F_MALE) ? P.sent_cdf_m : P.sent_cdf_f, P.n_sent, us);
+        if (si >= P.n_sent) si = P.n_sent - 1;
+        sentence[a] = P.sent_months[si] * P.punishment_length;
+        if (x & F_HASJOB) x = (x & ~(F_HASJOB | (0xfu << 16))) | (1u << 16);
+        x &= ~F_HASSCHOOL;
+        attr[a] = x;
+        for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) uent[e] &= ~((MB_PROF | MB_SCHOOL) << 24);  // Q11
+    }
+    C.n_arrested[r] = nfound;
+    cn[CN_TICK_ARRESTS] = nfound;
+}
+
+// ============================================================================ reporters (calculate_fast_reporters subset)
+// model.py:1687-1735, the columns the hot path feeds.  One block per replica.
+__global__ void __launch_bounds__(512) k_report(DevCtx C, int t) {
+    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x;
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const int32_t *ncr = RP(C.ncrimes, r, C.Ncap), *nct = RP(C.ncrimes_tick, r, C.Ncap);
+    const int32_t *crp = RP(C.c_rowptr, r, C.Ncap + 1);
+    const double *tend = RP(C.tendency, r, C.Ncap);
+    long long noc = 0, npris = 0, nlink = 0, sumcr = 0, ococ = 0;
+    double st = 0.0, st2 = 0.0;
+    long long nal = 0;
+    for (int a = tid; a < n; a += blockDim.x) {
+        uint32_t x = attr[a];
+        if (!(x & F_ALIVE)) continue;
+        nal++;
+        if (x & F_OC) { noc++; ococ += nct[a]; }
+        if (x & F_PRISONER) npris++;
+        nlink += crp[a + 1] - crp[a];
+        sumcr += ncr[a];
+        double tv = tend[a];
+        st += tv; st2 += tv * tv;
+    }
+    long long vi[6] = { noc, npris, nlink, sumcr, ococ, nal };
+    double vd[2] = { st, st2 };
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int k = 0; k < 6; k++) vi[k] += __shfl_xor_sync(FULL_MASK, vi[k], o);
+        for (int k = 0; k < 2; k++) vd[k] += __shfl_xor_sync(FULL_MASK, vd[k], o);
+    }
+    __shared__ long long wi[16][6];
+    __shared__ double wd[16][2];
+    if (lane_id() == 0) { for (int k = 0; k < 6; k++) wi[warp_id()][k] = vi[k]; for (int k = 0; k < 2; k++) wd[warp_id()][k] = vd[k]; }
+    __syncthreads();
+    if (tid == 0) {
+        int nw = blockDim.x >> 5;
+        for (int ww = 1; ww < nw; ww++) { for (int k = 0; k < 6; k++) vi[k] += wi[ww][k]; for (int k = 0; k < 2; k++) vd[k] += wd[ww][k]; }
+        const int *cn = RP(C.counters, r, CN_COUNT);
+        double *row = C.reporters + ((size_t)r * C.Tcap + t) * POC_N_REPORTERS;
+        double nn = (double)vi[5];
+        double mean = nn > 0 ? vd[0] / nn : 0.0, var = nn > 0 ? vd[1] / nn - mean * mean : 0.0;
+        row[0] = cn[CN_NUMBER_CRIMES]; row[1] = cn[CN_SIZE_FAILS]; row[2] = cn[CN_FAC_CRIMES]; row[3] = cn[CN_FAC_FAILS];
+        row[4] = cn[CN_BIG_CRIME]; row[5] = cn[CN_OFFSPRING_RECRUITED]; row[6] = cn[CN_PEOPLE_JAILED];
+        row[7] = (double)vi[0]; row[8] = (double)vi[1]; row[9] = (double)vi[2]; row[10] = (double)vi[3];
+        row[11] = (double)vi[4]; row[12] = mean; row[13] = var > 0 ? sqrt(var) : 0.0; row[14] = nn;
+        row[15] = C.crime_mult[r];
+    }
+}
+
+// ============================================================================ stage hooks
+__global__ void __launch_bounds__(256) k_rings_hook(DevCtx C, int r, int nsrc, const int32_t *src, int d, int exact,
+                                                    int32_t *out_cnt, int32_t *out_mem, long long cap_per_src) {
+    extern __shared__ unsigned smem_u[];
+    __shared__ int s_count, lvl_off[MAX_RADIUS + 3];
+    int n = C.n_agents[r], nwords = (n + 31) >> 5;
+    int *list = C.scr_list + (size_t)blockIdx.x * (C.Ncap + 1);
+    Graph g = graph_of(C, r);
+    unsigned long long edges = 0;
+    for (int s = blockIdx.x; s < nsrc; s += gridDim.x) {
+        if (threadIdx.x == 0) list[0] = src[s];
+        __syncthreads();
+        int total = bfs_levels(g, nwords, smem_u, list, 1, d, lvl_off, &s_count, edges);
+        int b = exact ? lvl_off[d] : 1, m = total - b;
+        if (threadIdx.x == 0) out_cnt[s] = m;
+        for (int i = threadIdx.x; i < m && i < cap_per_src; i += blockDim.x) out_mem[(size_t)s * cap_per_src + i] = list[b + i];
+        __syncthreads();
+    }
+}
+
+// warp per pair: social proximity, and candidate weight (needs emb_val for OC `self`)
+__global__ void k_pairs_hook(DevCtx C, int r, int npairs, const int32_t *sa, const int32_t *sb, double *out, int mode) {
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (gw >= npairs) return;
+    Graph g = graph_of(C, r);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    int a = sa[gw], b = sb[gw];
+    // friendship intersection by merging the two sorted rows: lane-strided over a's friends, binary search in b
+    bool hit = false;
+    for (int e = g.u_rowptr[a] + lane; e < g.u_rowptr[a + 1]; e += 32) {
+        uint32_t ent = g.u_ent[e];
+        if ((ENT_MASK(ent) & MB_FRIEND) && (static_find_mask(g, b, ENT_COL(ent)) & MB_FRIEND)) hit = true;
+    }
+    hit = __any_sync(FULL_MASK, hit);
+    if (lane == 0) {
+        double prox = social_proximity(attr[a], attr[b], hit);
+        if (mode == 0) out[gw] = prox;
+        else {
+            double t = RP(C.tendency, r, C.Ncap)[b];
+            out[gw] = (attr[a] & F_OC) ? -1.0 * ((prox * RP(C.emb_val, r, C.Ncap)[b]) * t) : prox * t;
+        }
+    }
+}
+
+// stage hook for Person.find_accomplices: n independent searches (crime slots 0..n-1 of replica r)
+__global__ void k_hook_init_crimes(DevCtx C, int r, int n, const int32_t *init, const int32_t *k) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) { C.n_crimes[r] = n; C.n_search[r] = 0; C.n_emb[r] = 0; C.n_emb[C.R + r] = 0; }
+    if (j >= n) return;
+    const poc_params &P = C.params[r];
+    size_t o = (size_t)r * C.Ccap + j;
+    uint32_t ia = RP(C.attr, r, C.Ncap)[init[j]];
+    int kk = k[j];
+    C.crime_init[o] = init[j]; C.crime_k[o] = kk; C.crime_flags[o] = (ia & F_OC) ? 1 : 0;
+    int target = kk, fn = 0;
+    if (kk > 0) { fn = ((double)kk >= P.threshold_use_facilitators) && !(ia & F_FAC); if (fn) target -= 1; }
+    C.cr_target[o] = target; C.cr_nacc[o] = 0; C.cr_d[o] = 1; C.cr_fails[o] = 0;
+    C.cr_state[o] = (kk > 0) ? (fn ? 2 : 0) : 4;
+}
+__global__ void k_hook_fill_search(DevCtx C, int r, int n) {  // deterministic search list 0..n-1 with k > 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int m = 0;
+        for (int j = 0; j < n; j++) if (C.crime_k[(size_t)r * C.Ccap + j] > 0) RP(C.search_list, r, C.Ccap)[m++] = j;
+        C.n_search[r] = m;
+    }
+}
+__global__ void k_snapshot_counters(DevCtx C, int *prev) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C.R * CN_COUNT) prev[i] = C.counters[i];
+}

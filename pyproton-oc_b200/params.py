@@ -1,0 +1,77 @@
+"""Host-side parameter block of the crime path: turns ProtonOC-style attributes and tables into poc_params.
+
+CDFs are built the way the reference's sampling primitive builds them (extra.weighted_n_of, extra.py:114-128,
+then numpy Generator.choice: cumsum(p); cdf /= cdf[-1]) so that searchsorted(cdf, U, 'right') on the device
+returns what the reference returns for the same uniform U."""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+
+from . import tables
+from ._cabi import MAX_CELLS, MAX_TAB, Params
+
+# the model attributes the hot path reads (model.py:108-134, 82-83) with the reference defaults
+HOT_PATH_DEFAULTS = dict(
+    nat_propensity_m=1.0, nat_propensity_sigma=0.25, nat_propensity_threshold=1.0,
+    number_crimes_yearly_per10k=2000, number_arrests_per_year=30, punishment_length=1,
+    threshold_use_facilitators=4, facilitator_repression_multiplier=2.0, good_guy_threshold=0.6,
+    max_accomplice_radius=2, oc_embeddedness_radius=2, facilitator_repression=False,
+    oc_boss_repression=False, ticks_between_intervention=12, intervention_start=13,
+    intervention_end=999, this_is_a_big_crime=3, ticks_per_year=12)
+
+
+def choice_cdf(weights: Iterable[float]) -> np.ndarray:
+    p = [float(x) for x in weights]
+    sump = sum(p)                       # Python left-to-right sum, extra.py:120
+    p = np.array([i / sump for i in p], dtype=np.float64)
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    return cdf
+
+
+def propensity_threshold(m: float, sigma: float, thr: float) -> float:
+    """The expression at entities.py:350-353, verbatim (Q4)."""
+    return float(np.exp(m - sigma ** 2 / 2) + thr * np.sqrt(np.exp(sigma) ** 2 - 1) * np.exp(m + sigma ** 2 / 2))
+
+
+def make_params(attrs: Optional[Dict] = None, c_range=None, co_offenders=None, conviction=None) -> Params:
+    """attrs: any mapping / object attributes named like the reference's model attributes."""
+    d = dict(HOT_PATH_DEFAULTS)
+    if attrs is not None:
+        get = attrs.get if isinstance(attrs, dict) else (lambda k, default=None: getattr(attrs, k, default))
+        for k in d:
+            v = get(k, None)
+            if v is not None:
+                d[k] = v
+    c_range = c_range if c_range is not None else tables.C_RANGE_BY_AGE_AND_SEX
+    co_offenders = co_offenders if co_offenders is not None else tables.NUM_CO_OFFENDERS_DIST
+    conviction = conviction if conviction is not None else tables.CONVICTION_LENGTH
+    if len(c_range) > MAX_CELLS or len(co_offenders) > MAX_TAB or len(conviction) > MAX_TAB:
+        raise ValueError("table too large for poc_params")
+    p = Params()
+    p.n_cells = len(c_range)
+    for i, (male, a0, a1, c) in enumerate(c_range):
+        p.cell_male[i], p.cell_age_from[i], p.cell_age_to[i], p.cell_c[i] = int(male), int(a0), int(a1), float(c)
+    p.n_sizes = len(co_offenders)
+    cdf = choice_cdf([r[-1] for r in co_offenders])
+    for i, r in enumerate(co_offenders):
+        p.size_n[i], p.size_cdf[i] = int(r[0]), float(cdf[i])
+    p.n_sent = len(conviction)
+    cf, cm = choice_cdf([r[1] for r in conviction]), choice_cdf([r[2] for r in conviction])
+    for i, r in enumerate(conviction):
+        p.sent_months[i], p.sent_cdf_f[i], p.sent_cdf_m[i] = float(r[0]), float(cf[i]), float(cm[i])
+    p.propensity_threshold = propensity_threshold(d["nat_propensity_m"], d["nat_propensity_sigma"],
+                                                  d["nat_propensity_threshold"])
+    p.crimes_yearly_per10k = float(d["number_crimes_yearly_per10k"])
+    p.arrests_per_year = float(d["number_arrests_per_year"])
+    p.punishment_length = float(d["punishment_length"])
+    p.threshold_use_facilitators = float(d["threshold_use_facilitators"])
+    p.facilitator_repression_multiplier = float(d["facilitator_repression_multiplier"])
+    p.good_guy_threshold = float(d["good_guy_threshold"])
+    for k in ["max_accomplice_radius", "oc_embeddedness_radius", "facilitator_repression", "oc_boss_repression",
+              "ticks_between_intervention", "intervention_start", "intervention_end", "this_is_a_big_crime",
+              "ticks_per_year"]:
+        setattr(p, k, int(d[k]))
+    return p

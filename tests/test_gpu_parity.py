@@ -1,0 +1,275 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference fixtures.
+Bit-exact for every integer / index stage and for the fp64 stages whose operation order is defined
+(tendency, CDF, candidate keys); embeddedness is compared bit-for-bit with the oracle and within 1e-6
+relative (the north-star tolerance) with the reference."""
+import numpy as np
+import pytest
+
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+COLS = ["alive", "male", "oc_member", "facilitator", "prisoner", "has_job", "has_school", "target_of_intervention",
+        "job_level", "education_level", "wealth_level", "age", "birth_tick", "num_crimes_committed",
+        "num_crimes_committed_this_tick", "father", "new_recruit", "propensity", "criminal_tendency",
+        "sentence_countdown"]
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pyproton_oc_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle_c
+    return oracle_c
+
+
+def engine_for(P, states, crim_headroom=20000):
+    n, stat, crim = P.CrimeEngine.capacity_for(states, crim_headroom)
+    return P.CrimeEngine(len(states), n, stat, crim)
+
+
+def assert_state_equal(gpu_state, orc, cols=COLS, layers=(6, 7, 8), what=""):
+    oc = orc.cols()
+    for k in cols:
+        assert np.array_equal(gpu_state[k], oc[k]), "%s column %s differs" % (what, k)
+    for l in layers:
+        rp, col, co = orc.layer(l)
+        assert np.array_equal(gpu_state["rowptr_%d" % l], rp), "%s layer %d rowptr" % (what, l)
+        assert np.array_equal(gpu_state["col_%d" % l], col), "%s layer %d col" % (what, l)
+        if l == 6:
+            assert np.array_equal(gpu_state["co_off"], co), "%s co_off" % what
+
+
+# ------------------------------------------------------------------ state round trip
+def test_state_roundtrip(P):
+    fx = U.load_fixture(U.golden_files("tick")[0])
+    st = U.pre_state(fx)
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params(U.fixture_params(fx)))
+        E.upload_state(0, st)
+        back = E.download_state(0)
+    for k in COLS + ["arrest_weight"]:
+        assert np.array_equal(back[k], st[k]), k
+    for l in range(9):
+        assert np.array_equal(back["rowptr_%d" % l], st["rowptr_%d" % l]), l
+        assert np.array_equal(back["col_%d" % l], st["col_%d" % l]), l
+    assert np.array_equal(back["co_off"], st["co_off"])
+
+
+# ------------------------------------------------------------------ A1 / A2
+@pytest.mark.parametrize("path", U.golden_files("tend"), ids=lambda p: p.split("/")[-1][:-4])
+def test_tendency_and_multiplier_bit_exact(P, O, path):
+    fx = U.load_fixture(path)
+    st = U.pre_state(fx)
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params(U.fixture_params(fx)))
+        E.upload_state(0, st)
+        E.tendency()
+        mult = E.crime_multiplier()[0]
+        got = E.download_agents(0)["criminal_tendency"]
+    alive = st["alive"].astype(bool)
+    assert np.array_equal(got[alive], fx["post_criminal_tendency"][alive])   # vs the reference, bit-exact
+    assert mult == float(fx["post_crime_multiplier"])
+    S = O.OracleState(st)
+    S.tendency(O.make_params(U.fixture_params(fx)))
+    assert np.array_equal(got, S.cols()["criminal_tendency"])               # vs the oracle, all slots
+
+
+# ------------------------------------------------------------------ whole tick with the reference's draws
+@pytest.mark.parametrize("path", U.golden_files("tick"), ids=lambda p: p.split("/")[-1][:-4])
+def test_tick_replay(P, O, path):
+    fx = U.load_fixture(path)
+    st = U.pre_state(fx)
+    prm, co = U.fixture_params(fx), U.fixture_co_offenders(fx)
+    tick, mult, rp = int(fx["tick"]), float(fx["crime_multiplier"]), U.fixture_replay(fx)
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params(prm, co_offenders=co))
+        E.upload_state(0, st)
+        E.set_crime_multiplier(mult)
+        outs, rec = E.commit_crimes(tick, [rp], records=True)
+        after = E.download_state(0)
+    out = outs[0]
+    assert out["error"] == 0
+    # --- against the oracle: everything identical
+    S = O.OracleState(st)
+    ores = S.commit_crimes(O.make_params(prm, co_offenders=co), tick, mult, rp)
+    assert np.array_equal(rec["initiator"], ores["initiator"])
+    assert np.array_equal(rec["k"], ores["k"])
+    assert len(rec["groups"]) == len(ores["groups"])
+    for c, (g, og) in enumerate(zip(rec["groups"], ores["groups"])):
+        assert g.tolist() == og.tolist(), "crime %d" % c
+    assert rec["arrested"].tolist() == ores["arrested"].tolist()
+    for k in ["n_crimes", "n_members", "n_arrests", "n_emb_evals", "d_number_crimes", "d_crime_size_fails",
+              "d_facilitator_crimes", "d_facilitator_fails", "d_big_crime_from_small_fish", "d_offspring_recruited",
+              "d_protected_recruited", "d_people_jailed", "n_recruited"]:
+        assert out[k] == ores["out"][k], k
+    assert_state_equal(after, S, what="after tick")
+    members = np.unique(np.concatenate(rec["groups"])) if rec["groups"] else np.zeros(0, np.int64)
+    assert np.array_equal(after["arrest_weight"][members], S.cols()["arrest_weight"][members])
+    # --- against the reference record: initiators / k bit-exact, groups modulo set-order ties
+    assert np.array_equal(rec["initiator"], fx["crime_initiator"])
+    assert np.array_equal(rec["k"], fx["crime_k"])
+    exact = True
+    for c, (g, r) in enumerate(zip(rec["groups"], U.ref_groups(fx))):
+        if g.tolist() != U.canonical_group(r):
+            exact = False
+            assert U.tie_explains(fx, c, g, rel=0.05 if fx["crime_oc"][c] else 0.0)
+    if exact:
+        assert np.array_equal(after["rowptr_6"], fx["post_rowptr_6"]) and np.array_equal(after["col_6"], fx["post_col_6"])
+        assert np.array_equal(after["co_off"], fx["post_co_off"])
+        for k in ["oc_member", "num_crimes_committed", "num_crimes_committed_this_tick", "new_recruit"]:
+            assert np.array_equal(after[k], fx["post_" + k]), k
+
+
+# ------------------------------------------------------------------ stage hooks on recorded crimes
+def test_rings_keys_embeddedness_hooks(P, O):
+    n_rings = n_keys = n_emb = 0
+    for path in U.golden_files("tick"):
+        fx = U.load_fixture(path)
+        st = U.pre_state(fx)
+        prm = U.fixture_params(fx)
+        S = O.OracleState(st)
+        R = int(prm["oc_embeddedness_radius"])
+        with engine_for(P, [st]) as E:
+            E.set_params(P.make_params(prm, co_offenders=U.fixture_co_offenders(fx)))
+            E.upload_state(0, st)
+            for c in range(len(fx["crime_k"])):
+                init = int(fx["crime_initiator"][c])
+                for d, members in U.ref_rings(fx, c):
+                    got = E.rings([init], d, True)[0]
+                    assert got.tolist() == sorted(members.tolist())           # A4 vs the reference
+                    ball = E.rings([init], d, False)[0]
+                    assert ball.tolist() == S.ring(init, d, False).tolist()   # ball vs the oracle
+                    n_rings += 1
+                keys = U.ref_keys(fx, c)
+                if keys and not fx["crime_oc"][c]:
+                    slots = list(keys)
+                    got = E.candidate_weights([init] * len(slots), slots)
+                    assert got.tolist() == [keys[s] for s in slots]          # A5/A6 vs the reference, bit-exact
+                    prox = E.social_proximity([init] * len(slots), slots)
+                    assert prox.tolist() == [S.social_proximity(init, s) for s in slots]
+                    n_keys += len(slots)
+            if len(fx["emb_slot"]):
+                slots = fx["emb_slot"].tolist()
+                got = E.embeddedness(slots)
+                for a, g, want in zip(slots, got, fx["emb_fresh"]):
+                    ov, _, _, nasym = S.embeddedness_ex(int(a), R)
+                    assert g == ov                                            # A7 vs the oracle, bit-exact
+                    if nasym == 0:
+                        assert abs(g - want) <= 1e-6 * abs(want)              # A7 vs the reference
+                    n_emb += 1
+    assert n_rings > 20 and n_keys > 100 and n_emb > 50
+
+
+def test_find_accomplices_hook(P, O):
+    for name in ["tick_n500_s3_radius6_t2", "tick_n1000_s11_oc200_t3", "tick_n3000_s42_t30"]:
+        fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+        st = U.pre_state(fx)
+        prm, co = U.fixture_params(fx), U.fixture_co_offenders(fx)
+        S = O.OracleState(st)
+        OP = O.make_params(prm, co_offenders=co)
+        init, k = fx["crime_initiator"], fx["crime_k"]
+        with engine_for(P, [st]) as E:
+            E.set_params(P.make_params(prm, co_offenders=co))
+            E.upload_state(0, st)
+            groups, fails = E.find_accomplices(init, k, u_fac=np.full(len(init), 0.37))
+        for c in range(len(init)):
+            S.reset_embeddedness()
+            og, of = S.find_accomplices(OP, int(init[c]), int(k[c]), -1, 0.37)
+            assert groups[c].tolist() == og.tolist(), (name, c)
+            assert fails[c].tolist() == of.tolist(), (name, c)
+
+
+# ------------------------------------------------------------------ the reference's known-answer tests
+def test_known_answers_micro_net(P):
+    st = U.micro_net_state()
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params({}))
+        E.upload_state(0, st)
+        assert E.rings([0], 2, True)[0].tolist() == [6]
+        assert E.rings([9], 3, True)[0].tolist() == [12, 15]
+        assert E.rings([0], 2, False)[0].tolist() == [1, 2, 3, 4, 5, 6]
+        assert E.rings([9], 3, False)[0].tolist() == [7, 8, 10, 11, 12, 13, 15]
+        groups, _ = E.find_accomplices([0], [5])
+        assert groups[0][-1] == 0 and len(set(groups[0].tolist())) == len(groups[0])
+
+
+def test_known_answers_embeddedness(P):
+    cases = [
+        (U.build_state(1, {}), 0.0),
+        (U.build_state(2, {"sibling": [(0, 1)]}, oc_member=[0, 1]), 1.0),
+        (U.build_state(11, {}, {"offspring": [(0, i) for i in range(1, 11)]}, oc_member=[0] + [1] * 5 + [0] * 5), 0.5),
+        (U.build_state(3, {"sibling": [(0, 1)], "partner": [(0, 2)], "friendship": [(0, 2)]}, oc_member=[0, 0, 1]), 2 / 3),
+        (U.build_state(3, {"partner": [(0, 1)], "friendship": [(0, 1), (0, 2)]}, oc_member=[0, 0, 1]), 1 / 3),
+        (U.build_state(3, {"sibling": [(0, 1)], "criminal": [(0, 2)]}, {"offspring": [(0, 2)]}, co_off={(0, 2): 4},
+                       oc_member=[0, 0, 1]), 5 / 6),
+        (U.build_state(6, {"partner": [(0, 1)], "friendship": [(0, 2)], "professional": [(0, 3)], "school": [(0, 4)],
+                           "criminal": [(0, 5)]}, {"offspring": [(0, 5)]}, co_off={(0, 5): 5},
+                       oc_member=[0, 0, 0, 0, 0, 1]), 0.6)]
+    for st, want in cases:
+        with engine_for(P, [st]) as E:
+            E.set_params(P.make_params({}))
+            E.upload_state(0, st)
+            got = E.embeddedness([0])[0]
+        assert abs(got - want) <= 1e-9, (got, want)
+
+
+# ------------------------------------------------------------------ production RNG: many ticks, GPU == oracle
+@pytest.mark.parametrize("name,ticks", [("tick_n1000_s42_t12", 40), ("tick_n1000_s11_oc200_t3", 30),
+                                        ("tick_n3000_s42_t24", 14), ("tick_n1000_s7_disruptive_strong_t14", 26)])
+def test_philox_run_matches_oracle(P, O, name, ticks):
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st = U.pre_state(fx)
+    prm, co = U.fixture_params(fx), U.fixture_co_offenders(fx)
+    tick0, key = int(fx["tick"]), 0x9E3779B97F4A7C15
+    S = O.OracleState(st)
+    mult, totals = S.run_ticks(O.make_params(prm, co_offenders=co), tick0, ticks, key, float(fx["crime_multiplier"]))
+    with engine_for(P, [st], crim_headroom=60000) as E:
+        E.set_params(P.make_params(prm, co_offenders=co))
+        E.upload_state(0, st)
+        E.set_crime_multiplier(float(fx["crime_multiplier"]))
+        rep = E.run_ticks(tick0, ticks, [key])
+        after = E.download_state(0)
+        cn, _ = E.counters()
+    assert cn[0, 9] == 0  # CN_ERROR
+    assert_state_equal(after, S, what="after %d ticks" % ticks)
+    assert rep[0, -1, 0] == totals[0]                     # crimes
+    assert rep[0, -1, 15] == mult                         # crime multiplier, bit-exact
+    oc = S.cols()
+    alive = oc["alive"].astype(bool)
+    assert rep[0, -1, 7] == int((oc["oc_member"][alive] > 0).sum())
+
+
+def test_batched_replicas_equal_single_runs(P):
+    names = ["tick_n1000_s42_t12", "tick_n1000_s11_oc200_t3", "tick_n100_s42_t12", "tick_n1000_s42_t120"]
+    fxs = [U.load_fixture(U.GOLDEN + "/%s.npz" % n) for n in names]
+    sts = [U.pre_state(f) for f in fxs]
+    keys = [11, 22, 33, 44]
+    ticks = 15
+    singles = []
+    for f, st, k in zip(fxs, sts, keys):
+        with engine_for(P, [st], crim_headroom=40000) as E:
+            E.set_params(P.make_params(U.fixture_params(f)))
+            E.upload_state(0, st)
+            E.set_crime_multiplier(float(f["crime_multiplier"]))
+            rep = E.run_ticks(5, ticks, [k])
+            singles.append((E.download_state(0), rep[0]))
+    with engine_for(P, sts, crim_headroom=40000) as E:
+        for r, (f, st) in enumerate(zip(fxs, sts)):
+            E.set_params(P.make_params(U.fixture_params(f)), replica=r)
+            E.upload_state(r, st)
+            E.set_crime_multiplier(float(f["crime_multiplier"]), replica=r)
+        rep = E.run_ticks(5, ticks, keys)
+        for r in range(len(sts)):
+            got = E.download_state(r)
+            want, wrep = singles[r]
+            for k in COLS:
+                assert np.array_equal(got[k], want[k]), (r, k)
+            for l in (6, 7, 8):
+                assert np.array_equal(got["col_%d" % l], want["col_%d" % l]), (r, l)
+            assert np.array_equal(got["co_off"], want["co_off"])
+            assert np.array_equal(rep[r], wrep)
