@@ -133,6 +133,9 @@ int poc_timers_reset(poc_ctx *ctx);
 int poc_timers_read(poc_ctx *ctx, double *ms_out /* [8] */, int64_t *launches_out /* [8] */);
 /* kernel classes of the timers: 0 cells, 1 tendency, 2 draw, 3 search, 4 embeddedness, 5 commit, 6 arrests, 7 other */
 long long poc_launch_count(poc_ctx *ctx); /* kernels launched since the last poc_timers_reset */
+/* CUDA events on the ctx stream for callers that time a region on the device (16 slots) */
+int poc_marker(poc_ctx *ctx, int slot);
+int poc_marker_elapsed_ms(poc_ctx *ctx, int from_slot, int to_slot, double *ms_out);
 /* raw per-replica counters [n_replicas][24] and traversed multiplex entries [n_replicas] */
 int poc_read_counters(poc_ctx *ctx, int32_t *counters_out, uint64_t *edges_out);
 

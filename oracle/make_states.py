@@ -1,0 +1,59 @@
+"""Export full-size reference setup states (the output of the reference's own ProtonOC.setup, model.py:1003-1049)
+as the workload inputs for bench.py and the full-size tests.  TEST INFRASTRUCTURE, build container only.
+
+    python -m oracle.make_states            # baseline 3k + 10k, and the three samples/sample_json.json variants
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import ref_harness as H
+from .make_golden import OUT, PARAM_KEYS
+
+
+def export_setup(name, n_agents, seed, overrides=None, steps=0):
+    """steps > 0: run that many reference step()s after setup and export the state the next tick starts from."""
+    ref_model, _, _ = H.load_reference()
+    model = ref_model.ProtonOC(seed=seed)
+    if overrides:
+        model.override_dict(overrides)
+    t = time.time()
+    model.setup(n_agents)
+    for _ in range(steps):
+        model.step()
+    st = H.export_state(model)
+    d = {"pre_" + k: v for k, v in st.items()}
+    for k in PARAM_KEYS:
+        d["param_" + k] = np.float64(getattr(model, k))
+    d["tick"] = np.int32(model.tick)
+    d["crime_multiplier"] = np.float64(model.crime_multiplier)
+    d["overrides_json"] = np.array(json.dumps(overrides or {}))
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote %s (%.1f KB, setup %.1fs, %d OC, %d facilitators)" % (
+        path, os.path.getsize(path) / 1024, time.time() - t, int(st["oc_member"].sum()), int(st["facilitator"].sum())))
+
+
+def main(argv):
+    only = argv[1] if len(argv) > 1 else None
+    cases = [("state_n3000_s42_baseline", 3000, 42, None), ("state_n10000_s42_baseline", 10000, 42, None)]
+    with open(os.path.join(H.REFERENCE_ROOT, "samples", "sample_json.json")) as f:
+        sj = json.load(f)
+    for key, ov in sj.items():
+        ov = dict(ov)
+        n = ov.pop("initial_agents")
+        cases.append(("state_n%d_s42_sample%s" % (n, key), n, 42, ov))
+    cases = [c + (0,) for c in cases]
+    # the 10k state a quarter into the second year (friendship layer grown to ~8.9 per agent): bench workload
+    cases.append(("state_n10000_s42_t13", 10000, 42, None, 12))
+    for name, n, seed, ov, steps in cases:
+        if only and not name.startswith(only):
+            continue
+        export_setup(name, n, seed, ov, steps)
+
+
+if __name__ == "__main__":
+    main(sys.argv)

@@ -46,6 +46,7 @@ struct poc_ctx {
     double tm_ms[N_TIMERS] = {};
     long long tm_n[N_TIMERS] = {};
     long long launches = 0;
+    cudaEvent_t marker[16] = {};
 };
 
 static thread_local std::string g_err;
@@ -175,6 +176,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     ctx->h_nagents.assign(R, 0);
     ctx->ev.resize(EV_POOL); ctx->ev_class.assign(EV_POOL, 0);
     for (auto &evx : ctx->ev) cudaEventCreate(&evx);
+    for (auto &m : ctx->marker) cudaEventCreate(&m);
     cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_embeddedness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
@@ -190,6 +192,7 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
     for (auto &evx : ctx->ev) cudaEventDestroy(evx);
+    for (auto &m : ctx->marker) cudaEventDestroy(m);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return POC_OK;
@@ -221,6 +224,21 @@ int poc_timers_read(poc_ctx *ctx, double *ms_out, int64_t *launches_out) {
     return POC_OK;
 }
 long long poc_launch_count(poc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int poc_marker(poc_ctx *ctx, int slot) {
+    CHECK_CTX();
+    if (slot < 0 || slot >= 16) return fail(ctx, POC_ERR_ARG, "poc_marker: slot out of range");
+    CU(cudaEventRecord(ctx->marker[slot], ctx->stream));
+    return POC_OK;
+}
+int poc_marker_elapsed_ms(poc_ctx *ctx, int from, int to, double *ms_out) {
+    CHECK_CTX();
+    if (from < 0 || from >= 16 || to < 0 || to >= 16 || !ms_out) return fail(ctx, POC_ERR_ARG, "poc_marker_elapsed_ms: bad argument");
+    CU(cudaEventSynchronize(ctx->marker[to]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->marker[from], ctx->marker[to]));
+    *ms_out = ms;
+    return POC_OK;
+}
 
 int poc_set_params(poc_ctx *ctx, int replica, const poc_params *p) {
     CHECK_CTX();

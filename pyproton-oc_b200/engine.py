@@ -234,6 +234,14 @@ class CrimeEngine:
         self._ck(self.L.poc_timers_read(self.h, ms.ctypes.data, n.ctypes.data))
         return dict(zip(TIMER_CLASSES, ms.tolist())), dict(zip(TIMER_CLASSES, n.tolist()))
 
+    def marker(self, slot: int):
+        self._ck(self.L.poc_marker(self.h, slot))
+
+    def marker_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0)
+        self._ck(self.L.poc_marker_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(self.L.poc_launch_count(self.h))
 
