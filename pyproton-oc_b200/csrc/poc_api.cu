@@ -137,8 +137,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     d.scr_slots = R * ctx->gx;
     size_t wcap = (size_t)(N + 31) / 32;
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
-    ctx->smem_emb = 2 * wcap * sizeof(unsigned);
-    if (ctx->smem_search + 40 * 1024 > 220 * 1024) { delete ctx; return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps"); }
+    ctx->smem_emb = (size_t)DCAP * 8 + 256 * 8 + (size_t)ECAP * 4 + 2 * wcap * sizeof(unsigned);
+    if (ctx->smem_emb + 2 * 1024 > 220 * 1024) { delete ctx; return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps"); }
     size_t RN = (size_t)R * N;
     DA(d.n_agents, R);
     DA(d.attr, RN); DA(d.birth, RN); DA(d.ncrimes, RN); DA(d.ncrimes_tick, RN); DA(d.father, RN); DA(d.new_recruit, RN);
@@ -510,7 +510,7 @@ static int launch_commit(poc_ctx *ctx, int tick, bool cells_done, int report_t) 
     int rc = launch_search_rounds(ctx, tick);
     if (rc) return rc;
     { Timed t(ctx, TM_COMMIT); k_commit<<<d.R, 1024, 0, ctx->stream>>>(d); }
-    { Timed t(ctx, TM_ARREST); k_recruit_arrest<<<(d.R + 31) / 32, 32, 0, ctx->stream>>>(d, tick); }
+    { Timed t(ctx, TM_ARREST); k_recruit_arrest<<<d.R, 32, 0, ctx->stream>>>(d, tick); }
     if (report_t >= 0) { Timed t(ctx, TM_OTHER); k_report<<<d.R, 512, 0, ctx->stream>>>(d, report_t); }
     CU(cudaGetLastError());
     return POC_OK;

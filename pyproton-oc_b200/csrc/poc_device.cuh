@@ -163,6 +163,22 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+// Order-defined float64 running sum, executed redundantly by all 32 lanes of one warp: loads and stores are
+// coalesced, every lane carries the same accumulator, and the only serial part is the dependent DADD chain.
+// Adds v (lane l holds element base + l; lanes past the end must pass 0.0, acc + 0.0 == acc) left to right;
+// returns this lane's inclusive prefix, leaves the running total in acc.
+__device__ __forceinline__ double warp_chain32(double v, double &acc) {
+    double mine = 0.0;
+    int lane = lane_id();
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        double vj = __shfl_sync(FULL_MASK, v, j);
+        acc = acc + vj;
+        if (lane == j) mine = acc;
+    }
+    return mine;
+}
+
 // ---- multiplex traversal ---------------------------------------------------------------------------
 struct Graph {
     const int32_t *u_rowptr; const uint32_t *u_ent;

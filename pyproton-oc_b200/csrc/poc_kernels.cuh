@@ -149,13 +149,12 @@ __global__ void k_end_tick(DevCtx C) {
 // the strict counts calculate_crime_multiplier uses (model.py:1152, Q8) and, when `yearly`, the multiplier.
 // One block per replica.
 __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
-    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     int nc = P.n_cells;
     __shared__ unsigned char lut[512], luts[512];
-    __shared__ int cnt[POC_MAX_CELLS], cnts[POC_MAX_CELLS], base[POC_MAX_CELLS + 1], running[POC_MAX_CELLS];
-    __shared__ int wc[32][POC_MAX_CELLS + 1];
-    __shared__ int nalive;
+    __shared__ int cnt[POC_MAX_CELLS], cnts[POC_MAX_CELLS], base[POC_MAX_CELLS + 1];
+    __shared__ int wc[32][POC_MAX_CELLS], wcs[32][POC_MAX_CELLS], walive[32];
     for (int i = tid; i < 512; i += blockDim.x) {
         int male = i >> 8, age = i & 255, c = 255, cs = 255;
         for (int k = nc - 1; k >= 0; k--)
@@ -165,25 +164,34 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
             }
         lut[i] = (unsigned char)c; luts[i] = (unsigned char)cs;
     }
-    if (tid < POC_MAX_CELLS) { cnt[tid] = 0; cnts[tid] = 0; running[tid] = 0; }
-    if (tid == 0) nalive = 0;
+    for (int i = tid; i < 32 * POC_MAX_CELLS; i += blockDim.x) { (&wc[0][0])[i] = 0; (&wcs[0][0])[i] = 0; }
     __syncthreads();
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
-    int nround = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
-    for (int a = tid; a < nround; a += blockDim.x) {
-        int c = 255, cs = 255;
+    // every warp owns one contiguous slice of the slots (stable order = slice order, then lane order)
+    int chunk = (((n + nw - 1) / nw) + 31) & ~31;
+    int a_begin = w * chunk, a_end = min(n, a_begin + chunk);
+    int alive_cnt = 0;
+    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
+        int a = a0 + lane, c = 255, cs = 255;
         bool alive = false;
-        if (a < n) { uint32_t x = attr[a]; alive = x & F_ALIVE; if (alive) { int i = ((x & F_MALE) ? 256 : 0) | attr_age(x); c = lut[i]; cs = luts[i]; } }
-        unsigned ma = __ballot_sync(FULL_MASK, alive);
-        if (lane == 0 && ma) atomicAdd(&nalive, __popc(ma));
-        for (int k = 0; k < nc; k++) {
-            unsigned m = __ballot_sync(FULL_MASK, c == k), ms = __ballot_sync(FULL_MASK, cs == k);
-            if (lane == 0) { if (m) atomicAdd(&cnt[k], __popc(m)); if (ms) atomicAdd(&cnts[k], __popc(ms)); }
-        }
+        if (a < a_end) { uint32_t x = attr[a]; alive = x & F_ALIVE; if (alive) { int i = ((x & F_MALE) ? 256 : 0) | attr_age(x); c = lut[i]; cs = luts[i]; } }
+        alive_cnt += __popc(__ballot_sync(FULL_MASK, alive));
+        unsigned m = __match_any_sync(FULL_MASK, c), ms = __match_any_sync(FULL_MASK, cs);
+        if (c != 255 && lane == __ffs(m) - 1) wc[w][c] += __popc(m);
+        if (cs != 255 && lane == __ffs(ms) - 1) wcs[w][cs] += __popc(ms);
+        __syncwarp();
+    }
+    if (lane == 0) walive[w] = alive_cnt;
+    __syncthreads();
+    if (tid < nc) {  // per cell: total and the exclusive offset of every warp's slice
+        int s = 0, ss = 0;
+        for (int ww = 0; ww < nw; ww++) { int t = wc[ww][tid]; wc[ww][tid] = s; s += t; ss += wcs[ww][tid]; }
+        cnt[tid] = s; cnts[tid] = ss;
     }
     __syncthreads();
     if (tid == 0) {
-        int s = 0;
+        int s = 0, nalive = 0;
+        for (int ww = 0; ww < nw; ww++) nalive += walive[ww];
         for (int k = 0; k < nc; k++) { base[k] = s; s += cnt[k]; }
         base[nc] = s;
         int32_t *co = RP(C.cell_off, r, POC_MAX_CELLS + 1);
@@ -198,27 +206,14 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
     }
     __syncthreads();
     int32_t *members = RP(C.cell_members, r, C.Ncap);
-    int nw = blockDim.x >> 5;
-    for (int a0 = 0; a0 < nround; a0 += blockDim.x) {
-        int a = a0 + tid, c = 255;
-        if (a < n) { uint32_t x = attr[a]; if (x & F_ALIVE) c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)]; }
-        int myrank = 0;
-        for (int k = 0; k < nc; k++) {
-            unsigned m = __ballot_sync(FULL_MASK, c == k);
-            if (c == k) myrank = __popc(m & ((1u << lane) - 1));
-            if (lane == 0) wc[w][k] = __popc(m);
-        }
-        __syncthreads();
-        if (tid < nc) {  // exclusive prefix over warps for cell `tid`
-            int s = 0;
-            for (int ww = 0; ww < nw; ww++) { int t = wc[ww][tid]; wc[ww][tid] = s; s += t; }
-            cnt[tid] = s;  // tile total
-        }
-        __syncthreads();
-        if (c != 255) members[base[c] + running[c] + wc[w][c] + myrank] = a;
-        __syncthreads();
-        if (tid < nc) running[tid] += cnt[tid];
-        __syncthreads();
+    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
+        int a = a0 + lane, c = 255;
+        if (a < a_end) { uint32_t x = attr[a]; if (x & F_ALIVE) c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)]; }
+        unsigned m = __match_any_sync(FULL_MASK, c);
+        if (c != 255) members[base[c] + wc[w][c] + __popc(m & ((1u << lane) - 1))] = a;
+        __syncwarp();
+        if (c != 255 && lane == __ffs(m) - 1) wc[w][c] += __popc(m);
+        __syncwarp();
     }
 }
 
@@ -360,20 +355,28 @@ __global__ void __launch_bounds__(512) k_draw(DevCtx C, int tick) {
         if (lane == 0) { mn[k] = m; neg[k] = ng; }
     }
     __syncthreads();
-    // the two sequential chains, one thread per cell, spread over warps
-    if (lane == 0 && w < nc) {
-        for (int k = w; k < nc; k += nw) {
-            if (ncr[k] == 0) { nz[k] = 1; last[k] = 1.0; continue; }
-            int b = off[k], e = off[k + 1];
-            double sump = 0.0, shift = neg[k] ? mn[k] : 0.0;
-            int nzz = 0;
-            if (neg[k]) { for (int i = b; i < e; i++) { double p = cdf[i] - shift; cdf[i] = p; sump += p; nzz += (p != 0.0); } }
-            else { for (int i = b; i < e; i++) { double p = cdf[i]; sump += p; nzz += (p != 0.0); } }
-            double acc = 0.0;
-            if (sump != 0.0) for (int i = b; i < e; i++) { acc += cdf[i] / sump; cdf[i] = acc; }
-            nz[k] = (sump == 0.0) ? 0 : nzz;
-            last[k] = acc;
+    // the two order-defined chains (sum, then cumulative sum of p/sum): one warp per cell, see warp_chain32
+    for (int k = w; k < nc; k += nw) {
+        if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
+        int b = off[k], e = off[k + 1];
+        double shift = neg[k] ? mn[k] : 0.0, sump = 0.0;
+        int nzz = 0;
+        for (int base = b; base < e; base += 32) {
+            int i = base + lane;
+            double p = 0.0;
+            if (i < e) { p = cdf[i]; if (neg[k]) { p = p - shift; cdf[i] = p; } }
+            nzz += __popc(__ballot_sync(FULL_MASK, p != 0.0));
+            warp_chain32(p, sump);
         }
+        double acc = 0.0;
+        if (sump != 0.0)
+            for (int base = b; base < e; base += 32) {
+                int i = base + lane;
+                double q = (i < e) ? cdf[i] / sump : 0.0;
+                double mine = warp_chain32(q, acc);
+                if (i < e) cdf[i] = mine;
+            }
+        if (lane == 0) { nz[k] = (sump == 0.0) ? 0 : nzz; last[k] = acc; }
     }
     __syncthreads();
     for (int i = tid; i < total; i += blockDim.x) {
@@ -603,15 +606,18 @@ __global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, i
 //      by iterated relaxation with 64-bit atomicMin on the distance bit patterns (non-negative doubles
 //      order like integers) until a fixed point: the same least fixed point Dijkstra reaches;
 //   4. sum(1/dist) over OC members / over the ball, accumulated in 2^-34 fixed point (order independent).
+#define ECAP 8192 /* induced directed entries staged in shared memory per evaluation */
 __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
-    extern __shared__ unsigned smem_u[];
-    __shared__ int s_count, lvl_off[MAX_RADIUS + 3], s_flag[2], ws[33];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_count, lvl_off[MAX_RADIUS + 3], s_flag[2], ws[33], s_ne, s_over, carry;
     __shared__ unsigned long long s_num, s_den;
-    __shared__ unsigned long long s_dist[DCAP];
     int r = blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
     int tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
-    unsigned *bitmap = smem_u;
-    int *wprefix = (int *)(smem_u + wcap);
+    unsigned long long *s_dist = (unsigned long long *)smem_raw;
+    double *invw = (double *)(s_dist + DCAP);
+    unsigned *s_edges = (unsigned *)(invw + 256);
+    unsigned *bitmap = s_edges + ECAP;
+    int *wprefix = (int *)(bitmap + wcap);
     int slot = blockIdx.y * gridDim.x + blockIdx.x;
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
@@ -624,76 +630,161 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
     int R = P.oc_embeddedness_radius;
     unsigned long long edges = 0;
     int nevals = 0;
+    for (int i = tid; i < 256; i += blockDim.x) invw[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+#define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
+#define INBALL(v) (bitmap[(v) >> 5] & (1u << ((v) & 31)))
     for (int item = blockIdx.x; item < ne; item += gridDim.x) {
         int self = elist[item];
         if (tid == 0) { list[0] = self; s_flag[0] = 0; }
         __syncthreads();
         int total = bfs_levels(g, nwords, bitmap, list, 1, R, lvl_off, &s_count, edges);
-        int nb = total - 1;
         bool anyoc = false;
         for (int i = 1 + tid; i < total; i += blockDim.x) anyoc |= (attr[list[i]] & F_OC) != 0;
         if (anyoc) s_flag[0] = 1;
         __syncthreads();
         if (!s_flag[0]) { if (tid == 0) embv[self] = 0.0; __syncthreads(); continue; }
         nevals++;
-        // per-word exclusive popcount prefix -> rank(v)
-        {
-            __shared__ int carry;
-            if (tid == 0) carry = 0;
+        // per-word exclusive popcount prefix -> dense local index rank(v), ascending slot order
+        if (tid == 0) { carry = 0; s_ne = 0; s_over = 0; }
+        __syncthreads();
+        for (int base = 0; base < nwords; base += blockDim.x) {
+            int i = base + tid, v = (i < nwords) ? __popc(bitmap[i]) : 0, tot;
+            int ex = block_exscan(v, ws, &tot);
+            if (i < nwords) wprefix[i] = carry + ex;
             __syncthreads();
-            for (int base = 0; base < nwords; base += blockDim.x) {
-                int i = base + tid, v = (i < nwords) ? __popc(bitmap[i]) : 0, tot;
-                int ex = block_exscan(v, ws, &tot);
-                if (i < nwords) wprefix[i] = carry + ex;
-                __syncthreads();
-                if (tid == 0) carry += tot;
-                __syncthreads();
+            if (tid == 0) carry += tot;
+            __syncthreads();
+        }
+        bool staged = total <= DCAP;
+        if (staged) {
+            // one pass over the ball's rows: 32 nodes per warp, their entries flattened over the lanes so that
+            // every lane has an independent load in flight; in-ball entries go to shared memory as
+            // rank(u) | rank(v) << 12 | multiplicity << 24
+            for (int i0 = w * 32; i0 < total; i0 += nw * 32) {
+                int i = i0 + lane;
+                int u = -1, b0 = 0, len0 = 0, b1 = 0, len1 = 0, ru = 0;
+                if (i < total) {
+                    u = list[i];
+                    b0 = g.u_rowptr[u]; len0 = g.u_rowptr[u + 1] - b0;
+                    b1 = g.c_rowptr[u]; len1 = g.c_rowptr[u + 1] - b1;
+                    ru = RANK(u);
+                }
+                int len = len0 + len1, incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                int excl = incl - len, tot = __shfl_sync(FULL_MASK, incl, 31);
+                if (lane == 0) edges += (unsigned long long)tot;
+                for (int fb = 0; fb < tot; fb += 32) {
+                    int f = fb + lane, t = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {
+                        int e = __shfl_sync(FULL_MASK, excl, t + s);
+                        if (e <= f) t += s;
+                    }
+                    int tb0 = __shfl_sync(FULL_MASK, b0, t), tl0 = __shfl_sync(FULL_MASK, len0, t);
+                    int tb1 = __shfl_sync(FULL_MASK, b1, t), tl1 = __shfl_sync(FULL_MASK, len1, t);
+                    int tex = __shfl_sync(FULL_MASK, excl, t), tu = __shfl_sync(FULL_MASK, u, t), tru = __shfl_sync(FULL_MASK, ru, t);
+                    bool ok = false;
+                    int v = 0, wgt = 0;
+                    if (f < tot) {
+                        int j = f - tex;
+                        if (j < tl0) {
+                            uint32_t ent = g.u_ent[tb0 + j];
+                            v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
+                            if (wgt && INBALL(v)) {
+                                if (tl1 > 0) { int cc = crim_find(g, tu, v); if (cc > 0) wgt += cc; }
+                                ok = true;
+                            }
+                        } else {
+                            int2 ce = g.c_ent[tb1 + (j - tl0)];
+                            v = ce.x; wgt = ce.y;
+                            ok = INBALL(v) && wgt > 0 && !static_find_mask(g, tu, v);
+                        }
+                    }
+                    if (ok && wgt > 255) { s_over = 1; ok = false; }
+                    unsigned m = __ballot_sync(FULL_MASK, ok);
+                    if (m) {
+                        int basep = 0;
+                        if (lane == 0) basep = atomicAdd(&s_ne, __popc(m));
+                        basep = __shfl_sync(FULL_MASK, basep, 0);
+                        if (ok) {
+                            int pos = basep + __popc(m & ((1u << lane) - 1));
+                            if (pos < ECAP) s_edges[pos] = (unsigned)tru | ((unsigned)RANK(v) << 12) | ((unsigned)wgt << 24);
+                            else s_over = 1;
+                        }
+                    }
+                }
             }
+            __syncthreads();
+            if (s_over) staged = false;
         }
         unsigned long long *dist = (total <= DCAP) ? s_dist : gdist;
-#define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
         for (int i = tid; i < total; i += blockDim.x) dist[i] = DIST_INF;
         __syncthreads();
         if (tid == 0) { dist[RANK(self)] = 0ull; s_flag[1] = 1; }
         __syncthreads();
         int rounds = 0;
-        while (s_flag[1]) {
-            __syncthreads();
-            if (tid == 0) s_flag[1] = 0;
-            __syncthreads();
-            bool changed = false;
-            for (int i = w; i < total; i += nw) {
-                int u = list[i], ru = RANK(u);
-                int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1], b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
-                int len0 = e0 - b0, len = len0 + (e1 - b1);
-                for (int j = lane; j < len; j += 32) {
-                    int v, wgt;
-                    if (j < len0) {
-                        uint32_t ent = g.u_ent[b0 + j];
-                        v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
-                        if (wgt == 0) continue;  // cleared by an arrest (Q11)
-                        if (!(bitmap[v >> 5] & (1u << (v & 31)))) continue;
-                        if (e1 > b1) { int cc = crim_find(g, u, v); if (cc > 0) wgt += cc; }
-                    } else {
-                        int2 ce = g.c_ent[b1 + (j - len0)];
-                        v = ce.x; wgt = ce.y;
-                        if (!(bitmap[v >> 5] & (1u << (v & 31)))) continue;
-                        if (static_find_mask(g, u, v)) continue;  // counted with the static entry
-                        if (wgt <= 0) continue;                    // the reference divides by zero here
-                    }
-                    int rv = RANK(v);
-                    double wt = 1.0 / (double)wgt;
+        if (staged) {
+            // SSSP by iterated relaxation entirely in shared memory
+            int nedge = s_ne;
+            while (s_flag[1]) {
+                __syncthreads();
+                if (tid == 0) s_flag[1] = 0;
+                __syncthreads();
+                bool changed = false;
+                for (int e = tid; e < nedge; e += blockDim.x) {
+                    unsigned ed = s_edges[e];
+                    int ru = ed & 0xfffu, rv = (ed >> 12) & 0xfffu;
+                    double wt = invw[ed >> 24];
                     double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
-                    // undirected meta edge (CANON: each direction relaxes with its own weight = max multiplicity)
                     double nv = du + wt, nu = dv + wt;
                     if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
                     if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
                 }
-                if (lane == 0) edges += (unsigned long long)len;
+                if (changed) s_flag[1] = 1;
+                __syncthreads();
+                if (++rounds > total + 2) break;
             }
-            if (changed) s_flag[1] = 1;
-            __syncthreads();
-            if (++rounds > total + 2) break;  // cannot happen with positive weights
+        } else {
+            // large ball: relax straight from the rows in global memory, one warp per node per round
+            while (s_flag[1]) {
+                __syncthreads();
+                if (tid == 0) s_flag[1] = 0;
+                __syncthreads();
+                bool changed = false;
+                for (int i = w; i < total; i += nw) {
+                    int u = list[i], ru = RANK(u);
+                    int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1], b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
+                    int len0 = e0 - b0, len = len0 + (e1 - b1);
+                    for (int j = lane; j < len; j += 32) {
+                        int v, wgt;
+                        if (j < len0) {
+                            uint32_t ent = g.u_ent[b0 + j];
+                            v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
+                            if (wgt == 0) continue;  // cleared by an arrest (Q11)
+                            if (!INBALL(v)) continue;
+                            if (e1 > b1) { int cc = crim_find(g, u, v); if (cc > 0) wgt += cc; }
+                        } else {
+                            int2 ce = g.c_ent[b1 + (j - len0)];
+                            v = ce.x; wgt = ce.y;
+                            if (!INBALL(v)) continue;
+                            if (static_find_mask(g, u, v)) continue;  // counted with the static entry
+                            if (wgt <= 0) continue;                    // the reference divides by zero here
+                        }
+                        int rv = RANK(v);
+                        double wt = 1.0 / (double)wgt;
+                        double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
+                        // undirected meta edge (CANON: each direction relaxes with its own weight = max multiplicity)
+                        double nv = du + wt, nu = dv + wt;
+                        if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
+                        if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
+                    }
+                    if (lane == 0) edges += (unsigned long long)len;
+                }
+                if (changed) s_flag[1] = 1;
+                __syncthreads();
+                if (++rounds > total + 2) break;  // cannot happen with positive weights
+            }
         }
         if (tid == 0) { s_num = 0ull; s_den = 0ull; }
         __syncthreads();
@@ -710,9 +801,9 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
         __syncthreads();
         if (tid == 0) embv[self] = (double)(long long)s_num / (double)(long long)s_den;
         __syncthreads();
-#undef RANK
-        (void)nb;
     }
+#undef RANK
+#undef INBALL
     edges = warp_sum_u64(edges);
     if (lane == 0 && edges) atomicAdd(&C.edges[r], edges);
     if (tid == 0 && nevals) atomicAdd(&RP(C.counters, r, CN_COUNT)[CN_TICK_EMB], nevals);
@@ -876,22 +967,6 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
 // ============================================================================ A9-A11 recruitment and arrests
 // model.py:1452-1485, extra.py:102-132, 223-237, entities.py:573-603.  Order-defined and tiny (a few hundred
 // list entries): one thread per replica follows the reference's sequence exactly.
-__device__ int weighted_cdf(const double *w, int n, double *p, double *cdf) {
-    bool neg = false;
-    for (int i = 0; i < n; i++) if (w[i] < 0.0) { neg = true; break; }
-    double mn = 0.0;
-    if (neg) { mn = w[0]; for (int i = 1; i < n; i++) if (w[i] < mn) mn = w[i]; }
-    double sump = 0.0;
-    int nz = 0;
-    for (int i = 0; i < n; i++) { double v = neg ? (w[i] - mn) : w[i]; p[i] = v; sump += v; if (v != 0.0) nz++; }
-    if (sump == 0.0) return 0;
-    double acc = 0.0;
-    for (int i = 0; i < n; i++) { double q = p[i] / sump; p[i] = q; acc += q; cdf[i] = acc; }
-    double last = cdf[n - 1];
-    for (int i = 0; i < n; i++) cdf[i] /= last;
-    return nz;
-}
-
 __device__ double pw_sum_plain(const double *a, int n) {
     if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
     if (n <= 128) {
@@ -908,86 +983,157 @@ __device__ double pw_sum_plain(const double *a, int n) {
     return pw_sum_plain(a, n2) + pw_sum_plain(a + n2, n - n2);
 }
 
-__global__ void k_recruit_arrest(DevCtx C, int tick) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= C.R) return;
+// warp-cooperative version of weighted_cdf: coalesced passes, the two order-defined sums by warp_chain32
+__device__ int warp_weighted_cdf(const double *w, int n, double *p, double *cdf) {
+    int lane = lane_id();
+    bool neg = false;
+    double mn = INFINITY;
+    for (int i = lane; i < n; i += 32) { double v = w[i]; neg |= (v < 0.0); mn = fmin(mn, v); }
+    neg = __any_sync(FULL_MASK, neg);
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL_MASK, mn, o));
+    double sump = 0.0;
+    int nz = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        double v = 0.0;
+        if (i < n) { v = neg ? (w[i] - mn) : w[i]; p[i] = v; }
+        nz += __popc(__ballot_sync(FULL_MASK, v != 0.0));
+        warp_chain32(v, sump);
+    }
+    if (sump == 0.0) return 0;
+    double acc = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        double q = (i < n) ? p[i] / sump : 0.0;
+        double mine = warp_chain32(q, acc);
+        if (i < n) { p[i] = q; cdf[i] = mine; }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) cdf[i] = cdf[i] / acc;
+    __syncwarp();
+    return nz;
+}
+
+// one warp per replica; lane 0 walks the strictly sequential parts (recruitment order, the sampler, get_caught)
+__global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
+    int r = blockIdx.x, lane = lane_id();
     const poc_params &P = C.params[r];
     int *cn = RP(C.counters, r, CN_COUNT);
     int ncr = C.n_crimes[r];
     const int32_t *goff = RP(C.group_off, r, C.Ccap + 1), *gmem = RP(C.group_mem, r, C.Mcap);
+    const int32_t *cflags = RP(C.crime_flags, r, C.Ccap);
     uint32_t *attr = RP(C.attr, r, C.Ncap);
     const int32_t *father = RP(C.father, r, C.Ncap);
     int32_t *new_recruit = RP(C.new_recruit, r, C.Ncap);
     double *arrest_w = RP(C.arrest_w, r, C.Ncap);
     if (cn[CN_ERROR] >= 11 && cn[CN_ERROR] <= 13) return;
     int nm = goff[ncr];
-    // A9 recruitment, sequential (a father recruited earlier in the loop counts, model.py:1456-1458)
-    int nrec = 0;
-    for (int gidx = 0; gidx < ncr; gidx++) {
-        if (!(C.crime_flags[(size_t)r * C.Ccap + gidx] & 1)) continue;
-        for (int i = goff[gidx]; i < goff[gidx + 1]; i++) {
-            int a = gmem[i];
-            if (attr[a] & F_OC) continue;
-            new_recruit[a] = tick;
-            attr[a] |= F_OC;
-            nrec++;
-            if (father[a] >= 0 && (attr[father[a]] & F_OC)) cn[CN_OFFSPRING_RECRUITED] += 1;
-            if (attr[a] & F_TARGET) cn[CN_PROTECTED_RECRUITED] += 1;
+    // A9 recruitment, sequential over the OC-started groups (a father recruited earlier in the loop counts,
+    // model.py:1456-1458); the groups are found 32 at a time
+    int nrec = 0, noff = 0, nprot = 0;
+    for (int base = 0; base < ncr; base += 32) {
+        int g = base + lane;
+        unsigned m = __ballot_sync(FULL_MASK, g < ncr && (cflags[g] & 1));
+        while (m) {
+            int gi = base + (__ffs(m) - 1);
+            m &= m - 1;
+            if (lane == 0) {
+                for (int i = goff[gi]; i < goff[gi + 1]; i++) {
+                    int a = gmem[i];
+                    uint32_t x = attr[a];
+                    if (x & F_OC) continue;
+                    new_recruit[a] = tick;
+                    attr[a] = x | F_OC;
+                    nrec++;
+                    int f = father[a];
+                    if (f >= 0 && (attr[f] & F_OC)) noff++;
+                    if (x & F_TARGET) nprot++;
+                }
+            }
+            __syncwarp();
         }
     }
-    cn[CN_RECRUITED] += nrec; cn[CN_TICK_RECRUITED] = nrec;
+    if (lane == 0) {
+        cn[CN_OFFSPRING_RECRUITED] += noff; cn[CN_PROTECTED_RECRUITED] += nprot;
+        cn[CN_RECRUITED] += nrec; cn[CN_TICK_RECRUITED] = nrec;
+    }
+    __syncwarp();
     if (nm <= 0) return;
     // A10 arrest weights
     Graph g = graph_of(C, r);
     double *aw = RP(C.aw, r, C.Mcap), *ap = RP(C.ap, r, C.Mcap), *acdf = RP(C.acdf, r, C.Mcap);
     bool ion = (tick % P.ticks_between_intervention == 0) && P.intervention_start <= tick && tick < P.intervention_end;
     if (ion && P.facilitator_repression) {
-        for (int i = 0; i < nm; i++) arrest_w[gmem[i]] = (attr[gmem[i]] & F_FAC) ? P.facilitator_repression_multiplier : 1.0;
+        for (int i = lane; i < nm; i += 32) aw[i] = (attr[gmem[i]] & F_FAC) ? P.facilitator_repression_multiplier : 1.0;
     } else {
         bool anyoc = false;
-        for (int i = 0; i < nm; i++) anyoc |= (attr[gmem[i]] & F_OC) != 0;
-        if (ion && P.oc_boss_repression && anyoc) {
-            // extra.calculate_oc_status over the OC members of the list, duplicates included
+        if (ion && P.oc_boss_repression) {
+            for (int i = lane; i < nm; i += 32) anyoc |= (attr[gmem[i]] & F_OC) != 0;
+            anyoc = __any_sync(FULL_MASK, anyoc);
+        }
+        if (anyoc) {
+            // extra.calculate_oc_status over the OC members of the list (duplicates included, list order kept)
             int noc = 0;
-            double mn = 0.0;
-            for (int i = 0; i < nm; i++) {
-                int a = gmem[i];
-                if (!(attr[a] & F_OC)) { arrest_w[a] = 1.0; continue; }
-                int nn = 0, sumco = 0, cntoc = 0;
-                for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
-                    uint32_t ent = g.u_ent[e];
-                    if (ENT_MASK(ent) && (attr[ENT_COL(ent)] & F_OC)) nn++;
+            for (int base = 0; base < nm; base += 32) {
+                int i = base + lane;
+                bool isoc = false;
+                double pos = 0.0;
+                int a = -1;
+                if (i < nm) {
+                    a = gmem[i];
+                    isoc = (attr[a] & F_OC) != 0;
+                    if (isoc) {  // Person.calculate_oc_member_position, entities.py:573-580
+                        int nn = 0, sumco = 0, cntoc = 0;
+                        for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
+                            uint32_t ent = g.u_ent[e];
+                            if (ENT_MASK(ent) && (attr[ENT_COL(ent)] & F_OC)) nn++;
+                        }
+                        for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
+                            int2 ce = g.c_ent[e];
+                            if (attr[ce.x] & F_OC) { sumco += ce.y; cntoc++; if (!static_find_mask(g, a, ce.x)) nn++; }
+                        }
+                        pos = (double)(nn + sumco - cntoc);
+                    }
                 }
-                for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
-                    int2 ce = g.c_ent[e];
-                    if (attr[ce.x] & F_OC) { sumco += ce.y; cntoc++; if (!static_find_mask(g, a, ce.x)) nn++; }
+                unsigned m = __ballot_sync(FULL_MASK, isoc);
+                if (isoc) { ap[noc + __popc(m & ((1u << lane) - 1))] = pos; arrest_w[a] = pos; }
+                else if (i < nm) arrest_w[a] = 1.0;
+                noc += __popc(m);
+            }
+            __syncwarp();
+            double mn = INFINITY;
+            for (int i = lane; i < noc; i += 32) mn = fmin(mn, ap[i]);
+            for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL_MASK, mn, o));
+            for (int i = lane; i < noc; i += 32) ap[i] = ap[i] - mn;
+            __syncwarp();
+            if (lane == 0) {
+                double div = pw_sum_plain(ap, noc) / (double)noc;
+                // third loop of calculate_oc_status in list order: a duplicated agent is normalised once per
+                // occurrence, from its already-normalised value
+                for (int i = 0; i < nm; i++) {
+                    int a = gmem[i];
+                    if (!(attr[a] & F_OC)) continue;
+                    arrest_w[a] = (div > 0.0) ? (arrest_w[a] - mn) / div : 1.0;
                 }
-                double pos = (double)(nn + sumco - cntoc);
-                arrest_w[a] = pos;
-                ap[noc] = pos;
-                if (noc == 0 || pos < mn) mn = pos;
-                noc++;
             }
-            for (int i = 0; i < noc; i++) ap[i] = ap[i] - mn;
-            double div = pw_sum_plain(ap, noc) / (double)noc;
-            for (int i = 0; i < nm; i++) {
-                int a = gmem[i];
-                if (!(attr[a] & F_OC)) continue;
-                arrest_w[a] = (div > 0.0) ? (arrest_w[a] - mn) / div : 1.0;
-            }
+            __syncwarp();
+            for (int i = lane; i < nm; i += 32) aw[i] = arrest_w[gmem[i]];
         } else {
-            for (int i = 0; i < nm; i++) arrest_w[gmem[i]] = 1.0;
+            for (int i = lane; i < nm; i += 32) aw[i] = 1.0;
         }
     }
-    for (int i = 0; i < nm; i++) aw[i] = arrest_w[gmem[i]];
+    __syncwarp();
+    for (int i = lane; i < nm; i += 32) arrest_w[gmem[i]] = aw[i];   // Person.arrest_weight (duplicates agree)
     double arrest_mod = P.arrests_per_year / (double)P.ticks_per_year / 10000.0 * (double)cn[CN_N_ALIVE];
     const int32_t *hdr = RP(C.rp_hdr, r, 8);
     bool replay = hdr[0] == 1;
     double ua, ub;
     if (replay) ua = C.rp_u_arrest_count[r]; else philox_u2(C.philox_key[r], tick, ST_ARREST_N, 0, ua, ub);
     int target = (ua < (arrest_mod - floor(arrest_mod))) ? (int)floor(arrest_mod + 1.0) : 0;  // Q7
-    int nz = weighted_cdf(aw, nm, ap, acdf);
+    if (target <= 0) { if (lane == 0) { C.n_arrested[r] = 0; cn[CN_TICK_ARRESTS] = 0; } return; }
+    int nz = warp_weighted_cdf(aw, nm, ap, acdf);
     if (nz < target) target = nz;
+    if (lane != 0) return;
     int32_t *found = RP(C.arrested, r, C.Mcap);
     int nfound = 0;
     if (replay && hdr[4] >= 0) {
