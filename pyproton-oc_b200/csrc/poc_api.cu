@@ -111,7 +111,7 @@ int poc_sizeof_tick_out(void) { return (int)sizeof(poc_tick_out); }
 
 int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_static_entries,
                    int64_t max_criminal_entries, poc_ctx **out) {
-    if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 24) || max_static_entries < 0 || max_criminal_entries < 0)
+    if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 23) || max_static_entries < 0 || max_criminal_entries < 0)
         return fail(nullptr, POC_ERR_ARG, "poc_ctx_create: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -348,6 +348,7 @@ int poc_build_graph(poc_ctx *ctx, int replica) {
         k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 0, ctx->d_err);
         k_exscan_i32<<<1, 1024, 0, st>>>(lens, urp, n);
         k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 1, ctx->d_err);
+        k_link_criminal<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
     } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
     CU(cudaGetLastError());
     ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;
@@ -415,7 +416,7 @@ int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, in
     for (int a = 0; a < n; a++) {
         rowptr[a] = p;
         if (layer == POC_CRIMINAL) {
-            for (int e = crp[a]; e < crp[a + 1]; e++) { if (col) col[p] = cent[e].x; if (co) co[p] = cent[e].y; p++; }
+            for (int e = crp[a]; e < crp[a + 1]; e++) { if (col) col[p] = cent[e].x; if (co) co[p] = CE_CNT(cent[e].y); p++; }
         } else {
             uint32_t bit = 1u << layer_bit(layer);
             for (int e = urp[a]; e < urp[a + 1]; e++) if (ENT_MASK(uent[e]) & bit) { if (col) col[p] = ENT_COL(uent[e]); p++; }

@@ -5,8 +5,10 @@
 //   tendency  f64, propensity f64, sentence f64, arrest_w f64
 //   birth, ncrimes, ncrimes_tick, father, new_recruit   i32
 //   u_rowptr  i32 [Ncap+1], u_ent u32 [ucap]: the eight non-criminal layers merged into one directed CSR,
-//             entry = neighbour slot (24 bit) | layer mask (8 bit) << 24 ; rows ascending by slot
-//   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses}, rows ascending
+//             entry = neighbour slot (23 bit) | also-criminal flag (bit 23) | layer mask (8 bit) << 24 ; rows ascending
+//   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses | static mask << 24}, rows
+//             ascending.  The flag and the mask copy make the multiplicity of an edge (model.py:1528-1535) a single
+//             load from either row: no row intersection on the traversal paths.
 // Reference mapping: Person attributes entities.py:49-83, the nine neighbour sets entities.py:38-47.
 #pragma once
 #include <cuda_runtime.h>
@@ -35,8 +37,12 @@ __host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < PO
 #define MB_FRIEND 0x20u
 #define MB_PROF 0x40u
 #define MB_SCHOOL 0x80u
-#define ENT_COL(e) ((int)((e) & 0x00ffffffu))
+#define ENT_COL(e) ((int)((e) & 0x007fffffu))
+#define ENT_CRIM 0x00800000u /* the same neighbour also has an entry in the criminal row */
 #define ENT_MASK(e) ((e) >> 24)
+// criminal entry .y = num_co_offenses (24 bit) | copy of the static layer mask of the same neighbour << 24
+#define CE_CNT(y) ((int)((unsigned)(y) & 0x00ffffffu))
+#define CE_SMASK(y) ((unsigned)(y) >> 24)
 
 // counters per replica (ints), cumulative unless noted
 enum {
@@ -269,8 +275,13 @@ __device__ __forceinline__ double social_proximity(uint32_t self_attr, uint32_t 
 __device__ __forceinline__ int crim_find(const Graph &g, int u, int v) {  // returns count or -1
     int lo = g.c_rowptr[u], hi = g.c_rowptr[u + 1], end = hi;
     while (lo < hi) { int m = (lo + hi) >> 1; if (g.c_ent[m].x < v) lo = m + 1; else hi = m; }
-    if (lo < end) { int2 e = g.c_ent[lo]; if (e.x == v) return e.y; }
+    if (lo < end) { int2 e = g.c_ent[lo]; if (e.x == v) return CE_CNT(e.y); }
     return -1;
+}
+__device__ __forceinline__ int static_find_idx(const Graph &g, int u, int v) {  // entry index of v in u's row or -1
+    int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (ENT_COL(g.u_ent[m]) < v) lo = m + 1; else hi = m; }
+    return (lo < end && ENT_COL(g.u_ent[lo]) == v) ? lo : -1;
 }
 __device__ __forceinline__ uint32_t static_find_mask(const Graph &g, int u, int v) {  // layer mask of v in u's row or 0
     int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;

@@ -117,6 +117,23 @@ __global__ void k_pack_criminal(DevCtx C, int r, int n, const int32_t *rowptr, c
     }
 }
 
+// After both the multiplex CSR and the criminal CSR of a replica are in place: copy the static layer mask of the
+// same neighbour into every criminal entry and flag that static entry (see poc_device.cuh).
+__global__ void k_link_criminal(DevCtx C, int r, int n) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    Graph g = graph_of(C, r);
+    uint32_t *uent = RP(C.u_ent, r, C.ucap);
+    int2 *cent = RP(C.c_ent, r, C.ccap);
+    for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
+        int2 ce = cent[e];
+        int idx = static_find_idx(g, a, ce.x);
+        unsigned smask = 0;
+        if (idx >= 0) { smask = ENT_MASK(uent[idx]); uent[idx] |= ENT_CRIM; }
+        cent[e].y = CE_CNT(ce.y) | (int)(smask << 24);
+    }
+}
+
 // ============================================================================ tick bookkeeping
 // model.py:236-238 (+ extra.py:359-361): per scheduled agent zero the this-tick counter and recompute age.
 __global__ void k_begin_tick(DevCtx C, int tick) {
@@ -148,13 +165,26 @@ __global__ void k_end_tick(DevCtx C) {
 // Age/sex cell partition (model.py:1172-1173, 1430-1432): stable (ascending slot) member lists per cell,
 // the strict counts calculate_crime_multiplier uses (model.py:1152, Q8) and, when `yearly`, the multiplier.
 // One block per replica.
+// Counts of up to 32 cells are carried as 21-bit fields packed three to a 64-bit word (11 words), so the
+// block-wide exclusive scan that gives every thread its stable write offsets is 11 integer scans.
+#define CELL_WORDS 11
+__device__ __forceinline__ void pk_add(unsigned long long pk[CELL_WORDS], int c) {
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) if (q == c / 3) pk[q] += 1ull << (21 * (c % 3));
+}
+__device__ __forceinline__ int pk_get(const unsigned long long pk[CELL_WORDS], int c) {
+    unsigned long long v = 0;
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) if (q == c / 3) v = pk[q];
+    return (int)((v >> (21 * (c % 3))) & 0x1fffffull);
+}
 __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
     int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     int nc = P.n_cells;
     __shared__ unsigned char lut[512], luts[512];
-    __shared__ int cnt[POC_MAX_CELLS], cnts[POC_MAX_CELLS], base[POC_MAX_CELLS + 1];
-    __shared__ int wc[32][POC_MAX_CELLS], wcs[32][POC_MAX_CELLS], walive[32];
+    __shared__ int base[POC_MAX_CELLS + 1], cnts[POC_MAX_CELLS], s_alive;
+    __shared__ unsigned long long wtot[32][CELL_WORDS];
     for (int i = tid; i < 512; i += blockDim.x) {
         int male = i >> 8, age = i & 255, c = 255, cs = 255;
         for (int k = nc - 1; k >= 0; k--)
@@ -164,56 +194,84 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
             }
         lut[i] = (unsigned char)c; luts[i] = (unsigned char)cs;
     }
-    for (int i = tid; i < 32 * POC_MAX_CELLS; i += blockDim.x) { (&wc[0][0])[i] = 0; (&wcs[0][0])[i] = 0; }
+    if (tid < POC_MAX_CELLS) cnts[tid] = 0;
+    if (tid == 0) s_alive = 0;
     __syncthreads();
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
-    // every warp owns one contiguous slice of the slots (stable order = slice order, then lane order)
-    int chunk = (((n + nw - 1) / nw) + 31) & ~31;
-    int a_begin = w * chunk, a_end = min(n, a_begin + chunk);
+    // every thread owns a contiguous slice of the slots: stable order = (thread, position in slice)
+    int chunk = (n + blockDim.x - 1) / blockDim.x;
+    int a_begin = min(n, tid * chunk), a_end = min(n, a_begin + chunk);
+    unsigned long long pk[CELL_WORDS], pks[CELL_WORDS];
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) { pk[q] = 0; pks[q] = 0; }
     int alive_cnt = 0;
-    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
-        int a = a0 + lane, c = 255, cs = 255;
-        bool alive = false;
-        if (a < a_end) { uint32_t x = attr[a]; alive = x & F_ALIVE; if (alive) { int i = ((x & F_MALE) ? 256 : 0) | attr_age(x); c = lut[i]; cs = luts[i]; } }
-        alive_cnt += __popc(__ballot_sync(FULL_MASK, alive));
-        unsigned m = __match_any_sync(FULL_MASK, c), ms = __match_any_sync(FULL_MASK, cs);
-        if (c != 255 && lane == __ffs(m) - 1) wc[w][c] += __popc(m);
-        if (cs != 255 && lane == __ffs(ms) - 1) wcs[w][cs] += __popc(ms);
-        __syncwarp();
+    for (int a = a_begin; a < a_end; a++) {
+        uint32_t x = attr[a];
+        if (!(x & F_ALIVE)) continue;
+        alive_cnt++;
+        int i = ((x & F_MALE) ? 256 : 0) | attr_age(x);
+        int c = lut[i], cs = luts[i];
+        if (c != 255) pk_add(pk, c);
+        if (cs != 255) pk_add(pks, cs);
     }
-    if (lane == 0) walive[w] = alive_cnt;
+    // strict counts and the alive count: warp reduce, then one shared atomic per warp and word
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) pks[q] = warp_sum_u64(pks[q]);
+    for (int o = 16; o > 0; o >>= 1) alive_cnt += __shfl_xor_sync(FULL_MASK, alive_cnt, o);
+    if (lane == 0) {
+        atomicAdd(&s_alive, alive_cnt);
+        for (int k = 0; k < nc; k++) { int v = pk_get(pks, k); if (v) atomicAdd(&cnts[k], v); }
+    }
+    // exclusive scan of the packed per-thread counts across the block
+    unsigned long long inc[CELL_WORDS];
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) {
+        unsigned long long x = pk[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+        inc[q] = x;
+        if (lane == 31) wtot[w][q] = x;
+    }
     __syncthreads();
-    if (tid < nc) {  // per cell: total and the exclusive offset of every warp's slice
-        int s = 0, ss = 0;
-        for (int ww = 0; ww < nw; ww++) { int t = wc[ww][tid]; wc[ww][tid] = s; s += t; ss += wcs[ww][tid]; }
-        cnt[tid] = s; cnts[tid] = ss;
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < CELL_WORDS; q++) {
+            unsigned long long s = (lane < nw) ? wtot[lane][q] : 0ull, x = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+            wtot[lane][q] = x - s;  // exclusive prefix of the warp totals
+            if (lane == 31) {       // x = block total of word q
+                for (int j = 0; j < 3; j++) { int k = q * 3 + j; if (k < POC_MAX_CELLS) base[k] = (int)((x >> (21 * j)) & 0x1fffffull); }
+            }
+        }
     }
     __syncthreads();
     if (tid == 0) {
-        int s = 0, nalive = 0;
-        for (int ww = 0; ww < nw; ww++) nalive += walive[ww];
-        for (int k = 0; k < nc; k++) { base[k] = s; s += cnt[k]; }
+        int s = 0;
+        for (int k = 0; k < nc; k++) { int t = base[k]; base[k] = s; s += t; }
         base[nc] = s;
         int32_t *co = RP(C.cell_off, r, POC_MAX_CELLS + 1);
         for (int k = 0; k <= nc; k++) co[k] = base[k];
         for (int k = 0; k < nc; k++) RP(C.cell_strict, r, POC_MAX_CELLS)[k] = cnts[k];
-        RP(C.counters, r, CN_COUNT)[CN_N_ALIVE] = nalive;
+        RP(C.counters, r, CN_COUNT)[CN_N_ALIVE] = s_alive;
         if (yearly) {  // model.py:1150-1157, left-to-right float64
             double total = 0.0;
             for (int k = 0; k < nc; k++) total += P.cell_c[k] * (double)cnts[k];
-            C.crime_mult[r] = P.crimes_yearly_per10k / 10000.0 * (double)nalive / total;
+            C.crime_mult[r] = P.crimes_yearly_per10k / 10000.0 * (double)s_alive / total;
         }
     }
     __syncthreads();
+    // this thread's exclusive offsets, then the stable scatter of its slice
+#pragma unroll
+    for (int q = 0; q < CELL_WORDS; q++) pk[q] = inc[q] - pk[q] + wtot[w][q];
     int32_t *members = RP(C.cell_members, r, C.Ncap);
-    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
-        int a = a0 + lane, c = 255;
-        if (a < a_end) { uint32_t x = attr[a]; if (x & F_ALIVE) c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)]; }
-        unsigned m = __match_any_sync(FULL_MASK, c);
-        if (c != 255) members[base[c] + wc[w][c] + __popc(m & ((1u << lane) - 1))] = a;
-        __syncwarp();
-        if (c != 255 && lane == __ffs(m) - 1) wc[w][c] += __popc(m);
-        __syncwarp();
+    for (int a = a_begin; a < a_end; a++) {
+        uint32_t x = attr[a];
+        if (!(x & F_ALIVE)) continue;
+        int c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)];
+        if (c == 255) continue;
+        members[base[c] + pk_get(pk, c)] = a;
+        pk_add(pk, c);
     }
 }
 
@@ -660,8 +718,8 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
             // one pass over the ball's rows: 32 nodes per warp, their entries flattened over the lanes so that
             // every lane has an independent load in flight; in-ball entries go to shared memory as
             // rank(u) | rank(v) << 12 | multiplicity << 24
-            for (int i0 = w * 32; i0 < total; i0 += nw * 32) {
-                int i = i0 + lane;
+            for (int i0 = 0; i0 < total; i0 += nw * 32) {
+                int i = i0 + lane * nw + w;  // neighbouring list positions (e.g. the OC clique) go to different warps
                 int u = -1, b0 = 0, len0 = 0, b1 = 0, len1 = 0, ru = 0;
                 if (i < total) {
                     u = list[i];
@@ -682,8 +740,8 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                         if (e <= f) t += s;
                     }
                     int tb0 = __shfl_sync(FULL_MASK, b0, t), tl0 = __shfl_sync(FULL_MASK, len0, t);
-                    int tb1 = __shfl_sync(FULL_MASK, b1, t), tl1 = __shfl_sync(FULL_MASK, len1, t);
-                    int tex = __shfl_sync(FULL_MASK, excl, t), tu = __shfl_sync(FULL_MASK, u, t), tru = __shfl_sync(FULL_MASK, ru, t);
+                    int tb1 = __shfl_sync(FULL_MASK, b1, t);
+                    int tex = __shfl_sync(FULL_MASK, excl, t), tru = __shfl_sync(FULL_MASK, ru, t);
                     bool ok = false;
                     int v = 0, wgt = 0;
                     if (f < tot) {
@@ -691,14 +749,12 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                         if (j < tl0) {
                             uint32_t ent = g.u_ent[tb0 + j];
                             v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
-                            if (wgt && INBALL(v)) {
-                                if (tl1 > 0) { int cc = crim_find(g, tu, v); if (cc > 0) wgt += cc; }
-                                ok = true;
-                            }
+                            // a neighbour that also has a criminal entry is weighed there (mask copy + co-offences)
+                            ok = wgt && !(ent & ENT_CRIM) && INBALL(v);
                         } else {
                             int2 ce = g.c_ent[tb1 + (j - tl0)];
-                            v = ce.x; wgt = ce.y;
-                            ok = INBALL(v) && wgt > 0 && !static_find_mask(g, tu, v);
+                            v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
+                            ok = wgt > 0 && INBALL(v);  // wgt == 0: the reference divides by zero here
                         }
                     }
                     if (ok && wgt > 255) { s_over = 1; ok = false; }
@@ -761,15 +817,12 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                         if (j < len0) {
                             uint32_t ent = g.u_ent[b0 + j];
                             v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
-                            if (wgt == 0) continue;  // cleared by an arrest (Q11)
+                            if (wgt == 0 || (ent & ENT_CRIM)) continue;  // cleared by an arrest (Q11) / weighed below
                             if (!INBALL(v)) continue;
-                            if (e1 > b1) { int cc = crim_find(g, u, v); if (cc > 0) wgt += cc; }
                         } else {
                             int2 ce = g.c_ent[b1 + (j - len0)];
-                            v = ce.x; wgt = ce.y;
-                            if (!INBALL(v)) continue;
-                            if (static_find_mask(g, u, v)) continue;  // counted with the static entry
-                            if (wgt <= 0) continue;                    // the reference divides by zero here
+                            v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
+                            if (wgt <= 0 || !INBALL(v)) continue;       // the reference divides by zero at 0
                         }
                         int rv = RANK(v);
                         double wt = 1.0 / (double)wgt;
@@ -939,6 +992,7 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     __syncthreads();
     if (carry > C.ccap) return;
     // ---- merge old rows with the new pairs
+    uint32_t *uent_rw = RP(C.u_ent, r, C.ucap);
     for (int a = tid; a < n; a += blockDim.x) {
         int ob = g.c_rowptr[a], oe = g.c_rowptr[a + 1], out = rp_new[a];
         int pb = 0, pe = nu;  // lower_bound of (a,*) in the unique pair list
@@ -951,8 +1005,14 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
             if (j >= pe) { ent_new[out++] = g.c_ent[i++]; continue; }
             int b = (int)(pairs[j] & 0xffffffffu);
             if (i < oe && g.c_ent[i].x < b) { ent_new[out++] = g.c_ent[i++]; continue; }
-            if (i < oe && g.c_ent[i].x == b) i++;
-            ent_new[out++] = make_int2(b, pcnt[j]); j++;
+            unsigned smask;
+            if (i < oe && g.c_ent[i].x == b) { smask = CE_SMASK(g.c_ent[i].y); i++; }
+            else {  // new link: copy the static mask of the pair and flag the static entry
+                int idx = static_find_idx(g, a, b);
+                smask = 0;
+                if (idx >= 0) { smask = ENT_MASK(uent_rw[idx]); atomicOr(&uent_rw[idx], ENT_CRIM); }
+            }
+            ent_new[out++] = make_int2(b, pcnt[j] | (int)(smask << 24)); j++;
         }
     }
     __syncthreads();
@@ -1090,7 +1150,7 @@ __global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
                         }
                         for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
                             int2 ce = g.c_ent[e];
-                            if (attr[ce.x] & F_OC) { sumco += ce.y; cntoc++; if (!static_find_mask(g, a, ce.x)) nn++; }
+                            if (attr[ce.x] & F_OC) { sumco += CE_CNT(ce.y); cntoc++; if (!CE_SMASK(ce.y)) nn++; }
                         }
                         pos = (double)(nn + sumco - cntoc);
                     }
@@ -1167,6 +1227,7 @@ __global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
     // A11 get_caught
     double *sentence = RP(C.sentence, r, C.Ncap);
     uint32_t *uent = RP(C.u_ent, r, C.ucap);
+    int2 *cent_rw = RP(C.c_ent, r, C.ccap);
     for (int i = 0; i < nfound; i++) {
         int a = gmem[found[i]];
         found[i] = a;  // report slots
@@ -1182,6 +1243,7 @@ __global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
         x &= ~F_HASSCHOOL;
         attr[a] = x;
         for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) uent[e] &= ~((MB_PROF | MB_SCHOOL) << 24);  // Q11
+        for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) cent_rw[e].y &= ~(int)((MB_PROF | MB_SCHOOL) << 24);
     }
     C.n_arrested[r] = nfound;
     cn[CN_TICK_ARRESTS] = nfound;
