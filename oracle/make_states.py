@@ -53,6 +53,42 @@ def main(argv):
         if only and not name.startswith(only):
             continue
         export_setup(name, n, seed, ov, steps)
+    if not only or "dist_n1000_s42".startswith(only):
+        export_distribution()
+
+
+
+
+def export_distribution(name="dist_n1000_s42", n_agents=1000, seed=42, n_runs=40, ticks=24):
+    """Whole-run distribution fixture (north-star check 2): the reference continued from ONE setup state with
+    `n_runs` different RNG streams; per-tick number_crimes / current_oc_members / people_jailed."""
+    ref_model, _, _ = H.load_reference()
+    crimes, ocm, jailed, prisoners, links = [], [], [], [], []
+    for j in range(n_runs):
+        model = ref_model.ProtonOC(seed=seed)
+        model.setup(n_agents)
+        if j == 0:
+            st = H.export_state(model)
+            d = {"pre_" + k: v for k, v in st.items()}
+            for k in PARAM_KEYS:
+                d["param_" + k] = np.float64(getattr(model, k))
+            d["tick"] = np.int32(model.tick)
+            d["crime_multiplier"] = np.float64(model.crime_multiplier)
+        model.random = np.random.default_rng(1000 + j)
+        rows = []
+        for _ in range(ticks):
+            model.step()
+            rows.append((model.number_crimes, model.current_oc_members, model.people_jailed, model.current_prisoners,
+                         model.tot_criminal_link))
+        rows = np.array(rows, dtype=np.float64)
+        crimes.append(rows[:, 0]); ocm.append(rows[:, 1]); jailed.append(rows[:, 2]); prisoners.append(rows[:, 3]); links.append(rows[:, 4])
+        print("run", j, rows[-1])
+    d.update({"ref_number_crimes": np.array(crimes), "ref_current_oc_members": np.array(ocm),
+              "ref_people_jailed": np.array(jailed), "ref_current_prisoners": np.array(prisoners),
+              "ref_tot_criminal_link": np.array(links)})
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path)
 
 
 if __name__ == "__main__":
