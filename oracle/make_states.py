@@ -59,33 +59,46 @@ def main(argv):
 
 
 
-def export_distribution(name="dist_n1000_s42", n_agents=1000, seed=42, n_runs=40, ticks=24):
-    """Whole-run distribution fixture (north-star check 2): the reference continued from ONE setup state with
-    `n_runs` different RNG streams; per-tick number_crimes / current_oc_members / people_jailed."""
+OUT_OF_SCOPE_PHASES = ["wedding", "retire_persons", "make_baby", "remove_excess_friends",
+                       "remove_excess_professional_links", "make_friends", "make_people_die",
+                       "graduate_and_enter_jobmarket", "let_migrants_in", "return_kids"]
+
+
+def export_distribution(name="dist_n1000_s42", n_agents=1000, seed=42, n_runs=40, ticks=36):
+    """Whole-run distribution fixture (north-star check 2).  The reference is continued from ONE setup state
+    with `n_runs` different RNG streams, twice: `ref_*` = the full step(); `refhot_*` = step() with the phases
+    that are out of scope here (OUT_OF_SCOPE_PHASES) replaced by no-ops, i.e. the reference's own code for
+    exactly the path this repo implements.  Per tick: number_crimes, current_oc_members, people_jailed,
+    current_prisoners, tot_criminal_link."""
     ref_model, _, _ = H.load_reference()
-    crimes, ocm, jailed, prisoners, links = [], [], [], [], []
-    for j in range(n_runs):
-        model = ref_model.ProtonOC(seed=seed)
-        model.setup(n_agents)
-        if j == 0:
-            st = H.export_state(model)
-            d = {"pre_" + k: v for k, v in st.items()}
-            for k in PARAM_KEYS:
-                d["param_" + k] = np.float64(getattr(model, k))
-            d["tick"] = np.int32(model.tick)
-            d["crime_multiplier"] = np.float64(model.crime_multiplier)
-        model.random = np.random.default_rng(1000 + j)
-        rows = []
-        for _ in range(ticks):
-            model.step()
-            rows.append((model.number_crimes, model.current_oc_members, model.people_jailed, model.current_prisoners,
-                         model.tot_criminal_link))
-        rows = np.array(rows, dtype=np.float64)
-        crimes.append(rows[:, 0]); ocm.append(rows[:, 1]); jailed.append(rows[:, 2]); prisoners.append(rows[:, 3]); links.append(rows[:, 4])
-        print("run", j, rows[-1])
-    d.update({"ref_number_crimes": np.array(crimes), "ref_current_oc_members": np.array(ocm),
-              "ref_people_jailed": np.array(jailed), "ref_current_prisoners": np.array(prisoners),
-              "ref_tot_criminal_link": np.array(links)})
+    d = {}
+    for tag, hot_only in (("ref", False), ("refhot", True)):
+        rows_all = []
+        for j in range(n_runs):
+            model = ref_model.ProtonOC(seed=seed)
+            model.setup(n_agents)
+            if not d:
+                st = H.export_state(model)
+                d.update({"pre_" + k: v for k, v in st.items()})
+                for k in PARAM_KEYS:
+                    d["param_" + k] = np.float64(getattr(model, k))
+                d["tick"] = np.int32(model.tick)
+                d["crime_multiplier"] = np.float64(model.crime_multiplier)
+            model.random = np.random.default_rng(1000 + j)
+            if hot_only:
+                for ph in OUT_OF_SCOPE_PHASES:
+                    setattr(model, ph, lambda *a, **k: None)
+            rows = []
+            for _ in range(ticks):
+                model.step()
+                rows.append((model.number_crimes, model.current_oc_members, model.people_jailed,
+                             model.current_prisoners, model.tot_criminal_link))
+            rows_all.append(np.array(rows, dtype=np.float64))
+            print(tag, "run", j, rows_all[-1][-1])
+        arr = np.array(rows_all)
+        for i, col in enumerate(["number_crimes", "current_oc_members", "people_jailed", "current_prisoners",
+                                 "tot_criminal_link"]):
+            d["%s_%s" % (tag, col)] = arr[:, :, i]
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **d)
     print("wrote", path)

@@ -88,6 +88,7 @@ SYMBOLS = {
     "poc_timers_read": (C.c_int, [_P, _P, _P]),
     "poc_launch_count": (C.c_longlong, [_P]),
     "poc_read_counters": (C.c_int, [_P, _P, _P]),
+    "poc_read_stats": (C.c_int, [_P, _P, C.c_int]),
     "poc_marker": (C.c_int, [_P, C.c_int]),
     "poc_marker_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "poc_set_params": (C.c_int, [_P, C.c_int, C.POINTER(Params)]),

@@ -146,7 +146,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.u_rowptr, (size_t)R * (N + 1)); DA(d.u_ent, (size_t)R * d.ucap);
     DA(d.c_rowptr, (size_t)R * (N + 1)); DA(d.c_ent, (size_t)R * d.ccap);
     DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
-    DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R);
+    DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN);
     size_t RC = (size_t)R * d.Ccap, RM = (size_t)R * d.Mcap;
@@ -630,6 +630,18 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
             CU(cudaMemcpyAsync(reporters_out + (size_t)r * n_ticks * POC_N_REPORTERS, d.reporters + (size_t)r * d.Tcap * POC_N_REPORTERS,
                                sizeof(double) * (size_t)n_ticks * POC_N_REPORTERS, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return POC_OK;
+}
+
+int poc_read_stats(poc_ctx *ctx, uint64_t *stats_out /* [R][8] */, int reset) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (stats_out) CU(cudaMemcpyAsync(stats_out, d.stats, sizeof(unsigned long long) * (size_t)d.R * ST_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (reset) {
+        CU(cudaMemsetAsync(d.stats, 0, sizeof(unsigned long long) * (size_t)d.R * ST_COUNT, ctx->stream));
+        CU(cudaMemsetAsync(d.edges, 0, sizeof(unsigned long long) * (size_t)d.R, ctx->stream));
     }
     return POC_OK;
 }

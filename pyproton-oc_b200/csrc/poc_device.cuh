@@ -51,6 +51,10 @@ enum {
     CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_COUNT = 24
 };
 
+// algorithmic-work counters per replica (what an ideal implementation must move once)
+enum { ST_EMB_REQUESTS = 0, ST_EMB_FULL, ST_EMB_BYTES, ST_EMB_NODES, ST_SEARCH_CRIMES, ST_SEARCH_BYTES,
+       ST_SEARCH_CANDIDATES, ST_SPARE, ST_COUNT = 8 };
+
 struct DevCtx {
     int R, Ncap, Ccap, Mcap, Pcap;  // replicas, agent / crime / member / pair capacities per replica
     long long ucap, ccap;           // static / criminal entry capacity per replica
@@ -68,6 +72,7 @@ struct DevCtx {
     double *crime_mult;             // [R]
     int *counters;                  // [R][CN_COUNT]
     unsigned long long *edges;      // [R] traversed multiplex entries (bench metric)
+    unsigned long long *stats;      // [R][ST_COUNT] algorithmic-work counters, see enum below
     // cells
     int32_t *cell_members;          // [R][Ncap] ascending slot inside each cell
     int32_t *cell_off;              // [R][POC_MAX_CELLS+1]
@@ -204,7 +209,7 @@ __device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
 // newly discovered neighbours are compacted with ballot/popc and a single atomicAdd per warp.
 // bitmap: ceil(N/32) words of shared memory, cleared here.  Returns the total list length.
 __device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *list, int nsrc, int depth, int *lvl_off,
-                          int *s_count, unsigned long long &edges) {
+                          int *s_count, unsigned long long &edges, unsigned long long &rowbytes) {
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < nsrc; i += blockDim.x) { int v = list[i]; atomicOr(&bitmap[v >> 5], 1u << (v & 31)); }
@@ -237,7 +242,7 @@ __device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *lis
                     if (isnew) list[pos + __popc(m & ((1u << lane) - 1))] = v;
                 }
             }
-            if (lane == 0) edges += (unsigned long long)len;
+            if (lane == 0) { edges += (unsigned long long)len; rowbytes += 16ull + 4ull * len0 + 8ull * (len - len0); }
         }
         __syncthreads();
         if (threadIdx.x == 0) lvl_off[lvl + 1] = *s_count;

@@ -490,7 +490,8 @@ struct ArgBest { double key; int slot; int idx; };
 __device__ __forceinline__ bool better(double k1, int s1, double k2, int s2) { return (k1 < k2) || (k1 == k2 && s1 < s2); }
 
 __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch, int parity, unsigned *bitmap,
-                             unsigned *fbits, int *list, double *keys, unsigned long long &edges) {
+                             unsigned *fbits, int *list, double *keys, unsigned long long &edges, unsigned long long &abytes,
+                             unsigned long long &ncand) {
     __shared__ int s_count, lvl_off[MAX_RADIUS + 3];
     __shared__ int s_st[6];  // nacc, target, mrem, facneeded, pickidx, stop
     __shared__ double wkey[8];
@@ -522,7 +523,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     while (s_st[0] < s_st[1] && d <= maxrad && !s_st[5]) {
         if (tid == 0) list[0] = init;
         __syncthreads();
-        bfs_levels(g, nwords, bitmap, list, 1, d, lvl_off, &s_count, edges);
+        bfs_levels(g, nwords, bitmap, list, 1, d, lvl_off, &s_count, edges, abytes);
         int rb = lvl_off[d], m = lvl_off[d + 1] - rb;
         if (is_oc && !awaiting) {
             // request oc_embeddedness for every ring member not yet evaluated this tick (cache: entities.py:531)
@@ -543,6 +544,8 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
             uint32_t ca = attr[cand];
             bool shared = warp_friend_intersect(g, cand, fbits);
             if (lane == 0) {
+                abytes += 20ull + (is_oc ? 8ull : 0ull) + 4ull * (unsigned)(g.u_rowptr[cand + 1] - g.u_rowptr[cand]);
+                ncand++;
                 double prox = social_proximity(self_attr, ca, shared);
                 double key = is_oc ? -1.0 * ((prox * embv[cand]) * tend[cand]) : prox * tend[cand];
                 keys[i] = key;
@@ -584,7 +587,8 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     if (s_st[3] && nacc > 0) {
         for (int i = tid; i < nacc; i += blockDim.x) list[i] = acc[i];
         __syncthreads();
-        int total = bfs_levels(g, nwords, bitmap, list, nacc, maxrad, lvl_off, &s_count, edges);
+        int total = bfs_levels(g, nwords, bitmap, list, nacc, maxrad, lvl_off, &s_count, edges, abytes);
+        if (tid == 0) abytes += 4ull * (total - nacc);  // facilitator flag of every node reached
         // facilitators within max_accomplice_radius of any accomplice
         int *avail = (int *)keys;
         if (tid == 0) s_count = 0;
@@ -641,18 +645,25 @@ __global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, i
     int slot = blockIdx.y * gridDim.x + blockIdx.x;
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     double *keys = C.scr_key + (size_t)slot * (C.Ncap + 1);
-    unsigned long long edges = 0;
+    unsigned long long edges = 0, abytes = 0, ncand = 0, ncrimes = 0;
     // the next round's request list must start empty; nobody appends to it during this launch
     if (blockIdx.x == 0 && threadIdx.x == 0) C.n_emb[(parity ^ 1) * C.R + r] = 0;
     int ns = C.n_search[r];
     for (int item = blockIdx.x; item < ns; item += gridDim.x) {
         int c = RP(C.search_list, r, C.Ccap)[item];
         if (C.cr_state[(size_t)r * C.Ccap + c] & 4) continue;
-        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, edges);
+        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, edges, abytes, ncand);
+        if (threadIdx.x == 0) { ncrimes++; abytes += 8ull + 4ull * POC_MAX_GROUP; }  // friends row pointer + group out
         __syncthreads();
     }
-    edges = warp_sum_u64(edges);
-    if (lane_id() == 0 && edges) atomicAdd(&C.edges[r], edges);
+    edges = warp_sum_u64(edges); abytes = warp_sum_u64(abytes); ncand = warp_sum_u64(ncand);
+    if (lane_id() == 0) {
+        unsigned long long *stq = RP(C.stats, r, ST_COUNT);
+        if (edges) atomicAdd(&C.edges[r], edges);
+        if (abytes) atomicAdd(&stq[ST_SEARCH_BYTES], abytes);
+        if (ncand) atomicAdd(&stq[ST_SEARCH_CANDIDATES], ncand);
+        if (ncrimes) atomicAdd(&stq[ST_SEARCH_CRIMES], ncrimes);
+    }
 }
 
 // ============================================================================ A7 OC embeddedness
@@ -686,8 +697,8 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
     const int32_t *elist = C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
     int ne = C.n_emb[parity * C.R + r];
     int R = P.oc_embeddedness_radius;
-    unsigned long long edges = 0;
-    int nevals = 0;
+    unsigned long long edges = 0, bfsbytes = 0, abytes = 0, anodes = 0;
+    int nevals = 0, nreq = 0;
     for (int i = tid; i < 256; i += blockDim.x) invw[i] = (i > 0) ? 1.0 / (double)i : 0.0;
 #define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
 #define INBALL(v) (bitmap[(v) >> 5] & (1u << ((v) & 31)))
@@ -695,12 +706,21 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
         int self = elist[item];
         if (tid == 0) { list[0] = self; s_flag[0] = 0; }
         __syncthreads();
-        int total = bfs_levels(g, nwords, bitmap, list, 1, R, lvl_off, &s_count, edges);
+        bfsbytes = 0;
+        unsigned long long ib = 0;  // algorithmic bytes of this evaluation
+        int total = bfs_levels(g, nwords, bitmap, list, 1, R, lvl_off, &s_count, edges, bfsbytes);
+        nreq++;
         bool anyoc = false;
         for (int i = 1 + tid; i < total; i += blockDim.x) anyoc |= (attr[list[i]] & F_OC) != 0;
         if (anyoc) s_flag[0] = 1;
         __syncthreads();
-        if (!s_flag[0]) { if (tid == 0) embv[self] = 0.0; __syncthreads(); continue; }
+        if (tid == 0) { ib += 4ull * total + 8ull; anodes += total; }  // OC flag of every ball node + the result
+        if (!s_flag[0]) {  // no OC member in the ball: only the rows the BFS expanded were needed
+            abytes += ib + bfsbytes;
+            if (tid == 0) embv[self] = 0.0;
+            __syncthreads();
+            continue;
+        }
         nevals++;
         // per-word exclusive popcount prefix -> dense local index rank(v), ascending slot order
         if (tid == 0) { carry = 0; s_ne = 0; s_over = 0; }
@@ -732,6 +752,7 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                 for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
                 int excl = incl - len, tot = __shfl_sync(FULL_MASK, incl, 31);
                 if (lane == 0) edges += (unsigned long long)tot;
+                if (i < total) ib += 16ull + 4ull * len0 + 8ull * len1;  // every ball row once
                 for (int fb = 0; fb < tot; fb += 32) {
                     int f = fb + lane, t = 0;
 #pragma unroll
@@ -772,7 +793,7 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                 }
             }
             __syncthreads();
-            if (s_over) staged = false;
+            if (s_over) { staged = false; ib = (tid == 0) ? 4ull * total + 8ull : 0ull; }
         }
         unsigned long long *dist = (total <= DCAP) ? s_dist : gdist;
         for (int i = tid; i < total; i += blockDim.x) dist[i] = DIST_INF;
@@ -832,7 +853,7 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
                         if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
                         if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
                     }
-                    if (lane == 0) edges += (unsigned long long)len;
+                    if (lane == 0) { edges += (unsigned long long)len; if (rounds == 0) ib += 16ull + 4ull * len0 + 8ull * (len - len0); }
                 }
                 if (changed) s_flag[1] = 1;
                 __syncthreads();
@@ -853,12 +874,19 @@ __global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
         if (lane == 0) { atomicAdd(&s_num, num); atomicAdd(&s_den, den); }
         __syncthreads();
         if (tid == 0) embv[self] = (double)(long long)s_num / (double)(long long)s_den;
+        abytes += ib;
         __syncthreads();
     }
 #undef RANK
 #undef INBALL
-    edges = warp_sum_u64(edges);
-    if (lane == 0 && edges) atomicAdd(&C.edges[r], edges);
+    edges = warp_sum_u64(edges); abytes = warp_sum_u64(abytes); anodes = warp_sum_u64(anodes);
+    unsigned long long *stq = RP(C.stats, r, ST_COUNT);
+    if (lane == 0) {
+        if (edges) atomicAdd(&C.edges[r], edges);
+        if (abytes) atomicAdd(&stq[ST_EMB_BYTES], abytes);
+        if (anodes) atomicAdd(&stq[ST_EMB_NODES], anodes);
+    }
+    if (tid == 0 && nreq) { atomicAdd(&stq[ST_EMB_REQUESTS], (unsigned long long)nreq); atomicAdd(&stq[ST_EMB_FULL], (unsigned long long)nevals); }
     if (tid == 0 && nevals) atomicAdd(&RP(C.counters, r, CN_COUNT)[CN_TICK_EMB], nevals);
 }
 
@@ -1304,11 +1332,11 @@ __global__ void __launch_bounds__(256) k_rings_hook(DevCtx C, int r, int nsrc, c
     int n = C.n_agents[r], nwords = (n + 31) >> 5;
     int *list = C.scr_list + (size_t)blockIdx.x * (C.Ncap + 1);
     Graph g = graph_of(C, r);
-    unsigned long long edges = 0;
+    unsigned long long edges = 0, rb = 0;
     for (int s = blockIdx.x; s < nsrc; s += gridDim.x) {
         if (threadIdx.x == 0) list[0] = src[s];
         __syncthreads();
-        int total = bfs_levels(g, nwords, smem_u, list, 1, d, lvl_off, &s_count, edges);
+        int total = bfs_levels(g, nwords, smem_u, list, 1, d, lvl_off, &s_count, edges, rb);
         int b = exact ? lvl_off[d] : 1, m = total - b;
         if (threadIdx.x == 0) out_cnt[s] = m;
         for (int i = threadIdx.x; i < m && i < cap_per_src; i += blockDim.x) out_mem[(size_t)s * cap_per_src + i] = list[b + i];

@@ -222,6 +222,15 @@ class CrimeEngine:
         self._ck(self.L.poc_read_counters(self.h, cn.ctypes.data, ed.ctypes.data))
         return cn, ed
 
+    def stats(self, reset: bool = False) -> Dict[str, int]:
+        """Algorithmic-work counters summed over replicas."""
+        a = np.zeros((self.R, 8), np.uint64)
+        self._ck(self.L.poc_read_stats(self.h, a.ctypes.data, 1 if reset else 0))
+        s = a.sum(axis=0)
+        names = ["emb_requests", "emb_full", "emb_bytes", "emb_nodes", "search_crimes", "search_bytes",
+                 "search_candidates", "spare"]
+        return {k: int(v) for k, v in zip(names, s)}
+
     # ------------------------------------------------------------------ timers
     def set_timing(self, on: bool):
         self._ck(self.L.poc_set_timing(self.h, 1 if on else 0))
