@@ -218,30 +218,31 @@ def test_ensemble_on_gpu_equals_individual_runs(P, tmp_path):
 
 
 def test_whole_run_distribution_vs_reference(P):
-    """North-star check 2: whole-run outputs matched in distribution over seeds.  The reference was continued
-    from one 1000-agent setup state with 40 RNG streams for 24 ticks (oracle/make_states.export_distribution);
-    the device runs 40 replicas with 40 Philox keys from the same state.  Over that horizon the phases that are
-    out of scope here (births, deaths, new friends) move the population by < 2 %."""
+    """North-star check 2: whole-run outputs matched in distribution over seeds (KS tests).
+    oracle/make_states.export_distribution continued the reference from ONE 1000-agent setup state with 40 RNG
+    streams for 36 ticks, (a) with its full step() (`ref_*`) and (b) with the phases that are out of scope here
+    replaced by no-ops (`refhot_*`): the reference's own code for exactly the path this repo implements.  The
+    device runs 40 replicas with 40 Philox keys from the same state and must match (b) in distribution."""
     from scipy.stats import ks_2samp
-    path = os.path.join(U.GOLDEN, "dist_n1000_s42.npz")
-    fx = U.load_fixture(path)
+    fx = U.load_fixture(os.path.join(U.GOLDEN, "dist_n1000_s42.npz"))
     st, prm = U.pre_state(fx), U.fixture_params(fx)
-    ref_crimes, ref_oc = fx["ref_number_crimes"], fx["ref_current_oc_members"]
-    runs, ticks = ref_crimes.shape
-    n, stat, crim = P.CrimeEngine.capacity_for([st], 40000)
+    runs, ticks = fx["refhot_number_crimes"].shape
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 60000)
     with P.CrimeEngine(runs, n, stat, crim) as E:
         E.set_params(P.make_params(prm))
         for r in range(runs):
             E.upload_state(r, st)
             E.set_crime_multiplier(float(fx["crime_multiplier"]), r)
         rep = E.run_ticks(1, ticks, [5000 + r for r in range(runs)])
-    crimes, oc, jailed = rep[:, :, 0], rep[:, :, 7], rep[:, :, 6]
-    # Crimes per tick are round(expected crimes) per age/sex cell, i.e. nearly deterministic given the
-    # population, so a KS test on them only measures the population drift of the out-of-scope phases (the
-    # reference lets migrants in at tick 12: 18 -> 20 crimes per tick); compare means within 5 %.
-    assert abs(crimes[:, -1].mean() - ref_crimes[:, -1].mean()) / ref_crimes[:, -1].mean() < 0.05
-    assert abs(np.diff(crimes, axis=1).mean() - np.diff(ref_crimes, axis=1).mean()) / np.diff(ref_crimes, axis=1).mean() < 0.05
-    # first year (no migrants yet): per-tick crime counts are identical in distribution
-    assert ks_2samp(np.diff(crimes[:, :11], axis=1).ravel(), np.diff(ref_crimes[:, :11], axis=1).ravel()).pvalue > 0.01
-    assert ks_2samp(oc[:, -1], ref_oc[:, -1]).pvalue > 0.01
-    assert ks_2samp(jailed[:, -1], fx["ref_people_jailed"][:, -1]).pvalue > 0.01
+    mine = {"number_crimes": rep[:, :, 0], "current_oc_members": rep[:, :, 7], "people_jailed": rep[:, :, 6],
+            "current_prisoners": rep[:, :, 8], "tot_criminal_link": rep[:, :, 9]}
+    # per-tick crime counts: round(expected) per cell, identical tick by tick while the population is the same
+    assert np.array_equal(np.unique(np.diff(mine["number_crimes"], axis=1)), np.unique(np.diff(fx["refhot_number_crimes"], axis=1)))
+    assert ks_2samp(np.diff(mine["number_crimes"], axis=1).ravel(), np.diff(fx["refhot_number_crimes"], axis=1).ravel()).pvalue > 0.01
+    for col in ["current_oc_members", "people_jailed", "current_prisoners", "tot_criminal_link"]:
+        for t in (11, 23, ticks - 1):
+            p = ks_2samp(mine[col][:, t], fx["refhot_" + col][:, t]).pvalue
+            assert p > 0.01, (col, t, p, mine[col][:, t].mean(), fx["refhot_" + col][:, t].mean())
+    # against the full reference the out-of-scope phases show up as drift; keep it bounded and on record
+    drift = abs(mine["number_crimes"][:, -1].mean() - fx["ref_number_crimes"][:, -1].mean()) / fx["ref_number_crimes"][:, -1].mean()
+    assert drift < 0.06
