@@ -138,8 +138,8 @@ int poc_marker(poc_ctx *ctx, int slot);
 int poc_marker_elapsed_ms(poc_ctx *ctx, int from_slot, int to_slot, double *ms_out);
 /* raw per-replica counters [n_replicas][24] and traversed multiplex entries [n_replicas] */
 int poc_read_counters(poc_ctx *ctx, int32_t *counters_out, uint64_t *edges_out);
-/* algorithmic-work counters [n_replicas][8]: embeddedness requests, full evaluations, algorithmic bytes, ball nodes;
- * accomplice searches, algorithmic bytes, candidates scored; spare.  reset != 0 zeroes them (and the edge counter). */
+/* algorithmic-work counters [n_replicas][16]: embeddedness requests, full evaluations, algorithmic bytes, ball nodes;
+ * accomplice searches, algorithmic bytes, candidates scored; spare; 8..15 per-phase cycles of -DPOC_PHASES builds.  reset != 0 zeroes them (and the edge counter). */
 int poc_read_stats(poc_ctx *ctx, uint64_t *stats_out, int reset);
 
 /* ---- state in / out (replaces the Person object graph, entities.py:36-108) -------------------- */

@@ -118,7 +118,7 @@ _lib = None
 
 
 def sources():
-    return [os.path.join(SRC_DIR, f) for f in ("poc_api.cu", "poc_kernels.cuh", "poc_device.cuh")] + [HEADER]
+    return [os.path.join(SRC_DIR, f) for f in ("poc_api.cu", "poc_kernels.cuh", "poc_embed.cuh", "poc_device.cuh")] + [HEADER]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -24,7 +24,9 @@ struct poc_ctx {
     std::string err;
     int sticky = 0;
     int epoch = 0;
-    int gx = 4;            // blocks per replica for the search / embeddedness grids
+    int gx = 4;            // blocks per replica of the search grid (and of the block-per-evaluation embeddedness grid)
+    int emb_g = 256;       // threads per embeddedness evaluation: 256 (block) for small batches, 32 (warp) for large ones
+    int emb_gx = 4;        // blocks per replica of the embeddedness grid
     size_t smem_search = 0, smem_emb = 0;
     // staging
     StageCols stage{};
@@ -133,11 +135,21 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     d.ucap = std::max<long long>(max_static_entries, 1);
     d.ccap = std::max<long long>(max_criminal_entries, 1);
     d.Tcap = 1;
-    ctx->gx = std::max(4, std::min(64, 1184 / R));
-    d.scr_slots = R * ctx->gx;
+    // one block per accomplice search / embeddedness evaluation: at 10k agents a replica issues about 25 searches
+    // and 20-50 evaluations per tick, so 32-64 blocks per replica let every block take at most one or two items
+    // (blocks without work exit at once); 6 blocks of 256 threads are resident per SM
+    ctx->gx = (R >= 64) ? 32 : 64;
+    // embeddedness: a chain of dependent gathers per evaluation, so large batches run one evaluation per warp
+    // (about 24 resident per SM) and small ones one per block
+    ctx->emb_g = 256;  // the warp-per-evaluation variant (32) measured slower at every batch size (profiles/)
+    if (const char *e = getenv("POC_EMB_G")) ctx->emb_g = (atoi(e) == 32) ? 32 : 256;  // experiments
+    if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
+    ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : ctx->gx;
+    int emb_slots = R * ctx->emb_gx * (256 / ctx->emb_g);
+    d.scr_slots = std::max(R * ctx->gx, emb_slots);
     size_t wcap = (size_t)(N + 31) / 32;
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
-    ctx->smem_emb = (size_t)DCAP * 8 + 256 * 8 + (size_t)ECAP * 4 + 2 * wcap * sizeof(unsigned);
+    ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
     if (ctx->smem_emb + 2 * 1024 > 220 * 1024) { delete ctx; return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps"); }
     size_t RN = (size_t)R * N;
     DA(d.n_agents, R);
@@ -160,8 +172,9 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.rp_u_init, RC); DA(d.rp_u_size, RC); DA(d.rp_fac_pick, RC);
     DA(d.rp_u_arrest, RM); DA(d.rp_u_sentence, RM); DA(d.rp_arrest_idx, RM);
     DA(d.rp_hdr, (size_t)R * 8); DA(d.rp_u_arrest_count, R); DA(d.philox_key, R);
-    DA(d.scr_list, (size_t)d.scr_slots * (N + 1)); DA(d.scr_key, (size_t)d.scr_slots * (N + 1));
-    DA(d.scr_dist, (size_t)d.scr_slots * (N + 1));
+    DA(d.scr_list, (size_t)d.scr_slots * (N + 1)); DA(d.scr_key, (size_t)R * ctx->gx * (N + 1));
+    DA(d.scr_dist, (size_t)emb_slots * (N + 1));
+    DA(d.scr_edges, (size_t)emb_slots * ECAP);
     DA(d.reporters, (size_t)R * d.Tcap * POC_N_REPORTERS);
     // staging
     StageCols &s = ctx->stage;
@@ -178,7 +191,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     for (auto &evx : ctx->ev) cudaEventCreate(&evx);
     for (auto &m : ctx->marker) cudaEventCreate(&m);
     cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
-    cudaFuncSetAttribute(k_embeddedness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb);
+    cudaFuncSetAttribute(k_embeddedness<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(32, N));
+    cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaDeviceSetLimit(cudaLimitStackSize, 2048);  // pw_sum recursion
     CU(cudaStreamSynchronize(ctx->stream));
@@ -489,6 +503,12 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
     return POC_OK;
 }
 
+static void launch_emb(poc_ctx *ctx, int parity) {
+    dim3 grid(ctx->emb_gx, ctx->d.R);
+    if (ctx->emb_g == 32) k_embeddedness<32><<<grid, 256, ctx->smem_emb, ctx->stream>>>(ctx->d, parity);
+    else k_embeddedness<256><<<grid, 256, ctx->smem_emb, ctx->stream>>>(ctx->d, parity);
+}
+
 // search / embeddedness rounds shared by commit_crimes and the find_accomplices hook
 static int launch_search_rounds(poc_ctx *ctx, int tick) {
     DevCtx &d = ctx->d;
@@ -496,7 +516,7 @@ static int launch_search_rounds(poc_ctx *ctx, int tick) {
     dim3 grid(ctx->gx, d.R);
     for (int rd = 0; rd <= rounds; rd++) {
         { Timed t(ctx, TM_SEARCH); k_search<<<grid, 256, ctx->smem_search, ctx->stream>>>(d, tick, ctx->epoch, rd & 1); }
-        if (rd < rounds) { Timed t(ctx, TM_EMB); k_embeddedness<<<grid, 256, ctx->smem_emb, ctx->stream>>>(d, rd & 1); }
+        if (rd < rounds) { Timed t(ctx, TM_EMB); launch_emb(ctx, rd & 1); }
     }
     CU(cudaGetLastError());
     return POC_OK;
@@ -634,7 +654,7 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
     return POC_OK;
 }
 
-int poc_read_stats(poc_ctx *ctx, uint64_t *stats_out /* [R][8] */, int reset) {
+int poc_read_stats(poc_ctx *ctx, uint64_t *stats_out /* [R][16] */, int reset) {
     CHECK_CTX();
     DevCtx &d = ctx->d;
     if (stats_out) CU(cudaMemcpyAsync(stats_out, d.stats, sizeof(unsigned long long) * (size_t)d.R * ST_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
@@ -726,7 +746,7 @@ static int run_emb(poc_ctx *ctx, int replica, int n, const int32_t *agents) {
     zero[replica] = n;
     CU(cudaMemcpyAsync(d.n_emb, zero.data(), sizeof(int32_t) * zero.size(), cudaMemcpyHostToDevice, st));
     if (n) CU(cudaMemcpyAsync(d.emb_list + (size_t)replica * d.Ncap, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    { Timed t(ctx, TM_EMB); k_embeddedness<<<dim3(ctx->gx, d.R), 256, ctx->smem_emb, st>>>(d, 0); }
+    { Timed t(ctx, TM_EMB); launch_emb(ctx, 0); }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     return POC_OK;

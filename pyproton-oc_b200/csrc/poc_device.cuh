@@ -53,7 +53,7 @@ enum {
 
 // algorithmic-work counters per replica (what an ideal implementation must move once)
 enum { ST_EMB_REQUESTS = 0, ST_EMB_FULL, ST_EMB_BYTES, ST_EMB_NODES, ST_SEARCH_CRIMES, ST_SEARCH_BYTES,
-       ST_SEARCH_CANDIDATES, ST_SPARE, ST_COUNT = 8 };
+       ST_SEARCH_CANDIDATES, ST_SPARE, ST_PH0 = 8, ST_COUNT = 16 };  // ST_PH0..: per-phase cycles (POC_PHASES builds)
 
 struct DevCtx {
     int R, Ncap, Ccap, Mcap, Pcap;  // replicas, agent / crime / member / pair capacities per replica
@@ -106,6 +106,7 @@ struct DevCtx {
     int32_t *scr_list;              // [slots][Ncap+1]
     double *scr_key;                // [slots][Ncap+1]
     unsigned long long *scr_dist;   // [slots][Ncap+1]
+    unsigned *scr_edges;            // [slots][ECAP] staged induced entries of one embeddedness evaluation
     int scr_slots;
     double *reporters;              // [R][Tcap][POC_N_REPORTERS]
     int Tcap;
@@ -215,19 +216,37 @@ __device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *lis
     for (int i = threadIdx.x; i < nsrc; i += blockDim.x) { int v = list[i]; atomicOr(&bitmap[v >> 5], 1u << (v & 31)); }
     if (threadIdx.x == 0) { *s_count = nsrc; lvl_off[0] = 0; lvl_off[1] = nsrc; }
     __syncthreads();
-    int lane = lane_id(), nw = blockDim.x >> 5;
+    int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     for (int lvl = 1; lvl <= depth; lvl++) {
         int fb = lvl_off[lvl - 1], fe = lvl_off[lvl];
-        for (int fi = fb + warp_id(); fi < fe; fi += nw) {
-            int u = list[fi];
-            int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1];
-            int b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
-            int len0 = e0 - b0, len = len0 + (e1 - b1);
-            for (int base = 0; base < len; base += 32) {
-                int i = base + lane;
+        // frontier node fb + lane * nw + w (+ 32 * nw per sweep) belongs to lane `lane` of warp `w`; the rows of a
+        // warp's up-to-32 nodes are flattened over its lanes (exclusive scan of the row lengths + shuffle search)
+        for (int f0 = fb; f0 < fe; f0 += 32 * nw) {
+            int fi = f0 + lane * nw + w;
+            int b0 = 0, len0 = 0, b1 = 0, len1 = 0;
+            if (fi < fe) {
+                int u = list[fi];
+                b0 = g.u_rowptr[u]; len0 = g.u_rowptr[u + 1] - b0;
+                b1 = g.c_rowptr[u]; len1 = g.c_rowptr[u + 1] - b1;
+                rowbytes += 16ull + 4ull * len0 + 8ull * len1;
+            }
+            int len = len0 + len1, incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
+            int excl = incl - len, tot = __shfl_sync(FULL_MASK, incl, 31);
+            if (lane == 0) edges += (unsigned long long)tot;
+            for (int base = 0; base < tot; base += 32) {
+                int f = base + lane, t = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) { int e = __shfl_sync(FULL_MASK, excl, t + s); if (e <= f) t += s; }
+                int tb0 = __shfl_sync(FULL_MASK, b0, t), tl0 = __shfl_sync(FULL_MASK, len0, t);
+                int tb1 = __shfl_sync(FULL_MASK, b1, t), tex = __shfl_sync(FULL_MASK, excl, t);
                 int v = -1;
-                if (i < len0) { uint32_t ent = g.u_ent[b0 + i]; if (ENT_MASK(ent)) v = ENT_COL(ent); }
-                else if (i < len) v = g.c_ent[b1 + (i - len0)].x;
+                if (f < tot) {
+                    int j = f - tex;
+                    if (j < tl0) { uint32_t ent = g.u_ent[tb0 + j]; if (ENT_MASK(ent)) v = ENT_COL(ent); }
+                    else v = g.c_ent[tb1 + (j - tl0)].x;
+                }
                 bool isnew = false;
                 if (v >= 0) {
                     unsigned bit = 1u << (v & 31);
@@ -242,7 +261,6 @@ __device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *lis
                     if (isnew) list[pos + __popc(m & ((1u << lane) - 1))] = v;
                 }
             }
-            if (lane == 0) { edges += (unsigned long long)len; rowbytes += 16ull + 4ull * len0 + 8ull * (len - len0); }
         }
         __syncthreads();
         if (threadIdx.x == 0) lvl_off[lvl + 1] = *s_count;

@@ -5,10 +5,7 @@
 #include "poc_device.cuh"
 
 #define RP(ptr, r, stride) ((ptr) + (size_t)(r) * (size_t)(stride))
-#define MAX_RADIUS 16
-#define EMB_SCALE 17179869184.0 /* 2^34 */
-#define DIST_INF 0x7ff0000000000000ull
-#define DCAP 4096 /* ball size up to which the SSSP distance array lives in shared memory */
+#include "poc_embed.cuh"
 
 // ============================================================================ state I/O
 struct StageCols {
@@ -666,229 +663,7 @@ __global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, i
     }
 }
 
-// ============================================================================ A7 OC embeddedness
-// Person.oc_embeddedness, entities.py:526-558 + ProtonOC.update_meta_links, model.py:1515-1536, on the
-// caller's own ball.  One block per evaluation:
-//   1. radius-R ball by frontier BFS (shared-memory bitmap);
-//   2. dense local index = rank of the slot in the bitmap (per-word popcount prefix);
-//   3. SSSP from the caller over the induced meta graph, edge weight 1/(#shared layers + co-offences),
-//      by iterated relaxation with 64-bit atomicMin on the distance bit patterns (non-negative doubles
-//      order like integers) until a fixed point: the same least fixed point Dijkstra reaches;
-//   4. sum(1/dist) over OC members / over the ball, accumulated in 2^-34 fixed point (order independent).
-#define ECAP 8192 /* induced directed entries staged in shared memory per evaluation */
-__global__ void __launch_bounds__(256) k_embeddedness(DevCtx C, int parity) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_count, lvl_off[MAX_RADIUS + 3], s_flag[2], ws[33], s_ne, s_over, carry;
-    __shared__ unsigned long long s_num, s_den;
-    int r = blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
-    int tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
-    unsigned long long *s_dist = (unsigned long long *)smem_raw;
-    double *invw = (double *)(s_dist + DCAP);
-    unsigned *s_edges = (unsigned *)(invw + 256);
-    unsigned *bitmap = s_edges + ECAP;
-    int *wprefix = (int *)(bitmap + wcap);
-    int slot = blockIdx.y * gridDim.x + blockIdx.x;
-    int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
-    unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
-    const poc_params &P = C.params[r];
-    Graph g = graph_of(C, r);
-    const uint32_t *attr = RP(C.attr, r, C.Ncap);
-    double *embv = RP(C.emb_val, r, C.Ncap);
-    const int32_t *elist = C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
-    int ne = C.n_emb[parity * C.R + r];
-    int R = P.oc_embeddedness_radius;
-    unsigned long long edges = 0, bfsbytes = 0, abytes = 0, anodes = 0;
-    int nevals = 0, nreq = 0;
-    for (int i = tid; i < 256; i += blockDim.x) invw[i] = (i > 0) ? 1.0 / (double)i : 0.0;
-#define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
-#define INBALL(v) (bitmap[(v) >> 5] & (1u << ((v) & 31)))
-    for (int item = blockIdx.x; item < ne; item += gridDim.x) {
-        int self = elist[item];
-        if (tid == 0) { list[0] = self; s_flag[0] = 0; }
-        __syncthreads();
-        bfsbytes = 0;
-        unsigned long long ib = 0;  // algorithmic bytes of this evaluation
-        int total = bfs_levels(g, nwords, bitmap, list, 1, R, lvl_off, &s_count, edges, bfsbytes);
-        nreq++;
-        bool anyoc = false;
-        for (int i = 1 + tid; i < total; i += blockDim.x) anyoc |= (attr[list[i]] & F_OC) != 0;
-        if (anyoc) s_flag[0] = 1;
-        __syncthreads();
-        if (tid == 0) { ib += 4ull * total + 8ull; anodes += total; }  // OC flag of every ball node + the result
-        if (!s_flag[0]) {  // no OC member in the ball: only the rows the BFS expanded were needed
-            abytes += ib + bfsbytes;
-            if (tid == 0) embv[self] = 0.0;
-            __syncthreads();
-            continue;
-        }
-        nevals++;
-        // per-word exclusive popcount prefix -> dense local index rank(v), ascending slot order
-        if (tid == 0) { carry = 0; s_ne = 0; s_over = 0; }
-        __syncthreads();
-        for (int base = 0; base < nwords; base += blockDim.x) {
-            int i = base + tid, v = (i < nwords) ? __popc(bitmap[i]) : 0, tot;
-            int ex = block_exscan(v, ws, &tot);
-            if (i < nwords) wprefix[i] = carry + ex;
-            __syncthreads();
-            if (tid == 0) carry += tot;
-            __syncthreads();
-        }
-        bool staged = total <= DCAP;
-        if (staged) {
-            // one pass over the ball's rows: 32 nodes per warp, their entries flattened over the lanes so that
-            // every lane has an independent load in flight; in-ball entries go to shared memory as
-            // rank(u) | rank(v) << 12 | multiplicity << 24
-            for (int i0 = 0; i0 < total; i0 += nw * 32) {
-                int i = i0 + lane * nw + w;  // neighbouring list positions (e.g. the OC clique) go to different warps
-                int u = -1, b0 = 0, len0 = 0, b1 = 0, len1 = 0, ru = 0;
-                if (i < total) {
-                    u = list[i];
-                    b0 = g.u_rowptr[u]; len0 = g.u_rowptr[u + 1] - b0;
-                    b1 = g.c_rowptr[u]; len1 = g.c_rowptr[u + 1] - b1;
-                    ru = RANK(u);
-                }
-                int len = len0 + len1, incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
-                int excl = incl - len, tot = __shfl_sync(FULL_MASK, incl, 31);
-                if (lane == 0) edges += (unsigned long long)tot;
-                if (i < total) ib += 16ull + 4ull * len0 + 8ull * len1;  // every ball row once
-                for (int fb = 0; fb < tot; fb += 32) {
-                    int f = fb + lane, t = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) {
-                        int e = __shfl_sync(FULL_MASK, excl, t + s);
-                        if (e <= f) t += s;
-                    }
-                    int tb0 = __shfl_sync(FULL_MASK, b0, t), tl0 = __shfl_sync(FULL_MASK, len0, t);
-                    int tb1 = __shfl_sync(FULL_MASK, b1, t);
-                    int tex = __shfl_sync(FULL_MASK, excl, t), tru = __shfl_sync(FULL_MASK, ru, t);
-                    bool ok = false;
-                    int v = 0, wgt = 0;
-                    if (f < tot) {
-                        int j = f - tex;
-                        if (j < tl0) {
-                            uint32_t ent = g.u_ent[tb0 + j];
-                            v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
-                            // a neighbour that also has a criminal entry is weighed there (mask copy + co-offences)
-                            ok = wgt && !(ent & ENT_CRIM) && INBALL(v);
-                        } else {
-                            int2 ce = g.c_ent[tb1 + (j - tl0)];
-                            v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
-                            ok = wgt > 0 && INBALL(v);  // wgt == 0: the reference divides by zero here
-                        }
-                    }
-                    if (ok && wgt > 255) { s_over = 1; ok = false; }
-                    unsigned m = __ballot_sync(FULL_MASK, ok);
-                    if (m) {
-                        int basep = 0;
-                        if (lane == 0) basep = atomicAdd(&s_ne, __popc(m));
-                        basep = __shfl_sync(FULL_MASK, basep, 0);
-                        if (ok) {
-                            int pos = basep + __popc(m & ((1u << lane) - 1));
-                            if (pos < ECAP) s_edges[pos] = (unsigned)tru | ((unsigned)RANK(v) << 12) | ((unsigned)wgt << 24);
-                            else s_over = 1;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (s_over) { staged = false; ib = (tid == 0) ? 4ull * total + 8ull : 0ull; }
-        }
-        unsigned long long *dist = (total <= DCAP) ? s_dist : gdist;
-        for (int i = tid; i < total; i += blockDim.x) dist[i] = DIST_INF;
-        __syncthreads();
-        if (tid == 0) { dist[RANK(self)] = 0ull; s_flag[1] = 1; }
-        __syncthreads();
-        int rounds = 0;
-        if (staged) {
-            // SSSP by iterated relaxation entirely in shared memory
-            int nedge = s_ne;
-            while (s_flag[1]) {
-                __syncthreads();
-                if (tid == 0) s_flag[1] = 0;
-                __syncthreads();
-                bool changed = false;
-                for (int e = tid; e < nedge; e += blockDim.x) {
-                    unsigned ed = s_edges[e];
-                    int ru = ed & 0xfffu, rv = (ed >> 12) & 0xfffu;
-                    double wt = invw[ed >> 24];
-                    double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
-                    double nv = du + wt, nu = dv + wt;
-                    if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
-                    if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
-                }
-                if (changed) s_flag[1] = 1;
-                __syncthreads();
-                if (++rounds > total + 2) break;
-            }
-        } else {
-            // large ball: relax straight from the rows in global memory, one warp per node per round
-            while (s_flag[1]) {
-                __syncthreads();
-                if (tid == 0) s_flag[1] = 0;
-                __syncthreads();
-                bool changed = false;
-                for (int i = w; i < total; i += nw) {
-                    int u = list[i], ru = RANK(u);
-                    int b0 = g.u_rowptr[u], e0 = g.u_rowptr[u + 1], b1 = g.c_rowptr[u], e1 = g.c_rowptr[u + 1];
-                    int len0 = e0 - b0, len = len0 + (e1 - b1);
-                    for (int j = lane; j < len; j += 32) {
-                        int v, wgt;
-                        if (j < len0) {
-                            uint32_t ent = g.u_ent[b0 + j];
-                            v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
-                            if (wgt == 0 || (ent & ENT_CRIM)) continue;  // cleared by an arrest (Q11) / weighed below
-                            if (!INBALL(v)) continue;
-                        } else {
-                            int2 ce = g.c_ent[b1 + (j - len0)];
-                            v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
-                            if (wgt <= 0 || !INBALL(v)) continue;       // the reference divides by zero at 0
-                        }
-                        int rv = RANK(v);
-                        double wt = 1.0 / (double)wgt;
-                        double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
-                        // undirected meta edge (CANON: each direction relaxes with its own weight = max multiplicity)
-                        double nv = du + wt, nu = dv + wt;
-                        if (nv < dv) { atomicMin(&dist[rv], (unsigned long long)__double_as_longlong(nv)); changed = true; }
-                        if (nu < du) { atomicMin(&dist[ru], (unsigned long long)__double_as_longlong(nu)); changed = true; }
-                    }
-                    if (lane == 0) { edges += (unsigned long long)len; if (rounds == 0) ib += 16ull + 4ull * len0 + 8ull * (len - len0); }
-                }
-                if (changed) s_flag[1] = 1;
-                __syncthreads();
-                if (++rounds > total + 2) break;  // cannot happen with positive weights
-            }
-        }
-        if (tid == 0) { s_num = 0ull; s_den = 0ull; }
-        __syncthreads();
-        unsigned long long num = 0, den = 0;
-        for (int i = 1 + tid; i < total; i += blockDim.x) {
-            int v = list[i];
-            double dv = __longlong_as_double((long long)dist[RANK(v)]);
-            long long q = __double2ll_rn((1.0 / dv) * EMB_SCALE);
-            den += (unsigned long long)q;
-            if (attr[v] & F_OC) num += (unsigned long long)q;
-        }
-        num = warp_sum_u64(num); den = warp_sum_u64(den);
-        if (lane == 0) { atomicAdd(&s_num, num); atomicAdd(&s_den, den); }
-        __syncthreads();
-        if (tid == 0) embv[self] = (double)(long long)s_num / (double)(long long)s_den;
-        abytes += ib;
-        __syncthreads();
-    }
-#undef RANK
-#undef INBALL
-    edges = warp_sum_u64(edges); abytes = warp_sum_u64(abytes); anodes = warp_sum_u64(anodes);
-    unsigned long long *stq = RP(C.stats, r, ST_COUNT);
-    if (lane == 0) {
-        if (edges) atomicAdd(&C.edges[r], edges);
-        if (abytes) atomicAdd(&stq[ST_EMB_BYTES], abytes);
-        if (anodes) atomicAdd(&stq[ST_EMB_NODES], anodes);
-    }
-    if (tid == 0 && nreq) { atomicAdd(&stq[ST_EMB_REQUESTS], (unsigned long long)nreq); atomicAdd(&stq[ST_EMB_FULL], (unsigned long long)nevals); }
-    if (tid == 0 && nevals) atomicAdd(&RP(C.counters, r, CN_COUNT)[CN_TICK_EMB], nevals);
-}
+// ============================================================================ A7 OC embeddedness: poc_embed.cuh
 
 // ============================================================================ A8 commit: groups, counters, link merge
 // ProtonOC.commit_crime, model.py:1487-1504 + Person.add_criminal_link, entities.py:215-224, for all groups

@@ -224,11 +224,11 @@ class CrimeEngine:
 
     def stats(self, reset: bool = False) -> Dict[str, int]:
         """Algorithmic-work counters summed over replicas."""
-        a = np.zeros((self.R, 8), np.uint64)
+        a = np.zeros((self.R, 16), np.uint64)
         self._ck(self.L.poc_read_stats(self.h, a.ctypes.data, 1 if reset else 0))
         s = a.sum(axis=0)
         names = ["emb_requests", "emb_full", "emb_bytes", "emb_nodes", "search_crimes", "search_bytes",
-                 "search_candidates", "spare"]
+                 "search_candidates", "spare"] + ["phase%d" % i for i in range(8)]
         return {k: int(v) for k, v in zip(names, s)}
 
     # ------------------------------------------------------------------ timers

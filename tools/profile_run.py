@@ -44,6 +44,7 @@ def main():
     print("workload %s  replicas %d  ticks %d..%d  wall %.1f ms  (%.1f us/tick)" % (
         name, args.replicas, tick0, tick0 + args.ticks - 1, dt * 1e3, dt * 1e6 / args.ticks))
     print("crimes %d  oc members %d  emb evals(last tick) %d" % (rep[0, -1, 0], rep[0, -1, 7], E.counters()[0][0, 13]))
+    print("stats", E.stats())
     if args.timing:
         ms, nl = E.timers()
         for k in ms:
