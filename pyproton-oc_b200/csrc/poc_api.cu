@@ -49,6 +49,15 @@ struct poc_ctx {
     long long tm_n[N_TIMERS] = {};
     long long launches = 0;
     cudaEvent_t marker[16] = {};
+    // replica groups of poc_run_ticks: each group's tick pipeline runs on its own stream so that the
+    // latency-bound one-block-per-replica kernels of one group overlap the traversal kernels of another
+    int ngroups = 1;
+    cudaStream_t gstream[8] = {};
+    cudaEvent_t gev[9] = {};
+    cudaEvent_t gstag[8] = {};
+    int graph_ticks = 8;
+    TickInfo *d_ti = nullptr;
+    bool use_graph = true;
 };
 
 static thread_local std::string g_err;
@@ -87,16 +96,16 @@ static int dalloc(poc_ctx *ctx, T **p, size_t count) {
     } while (0)
 
 struct Timed {
-    poc_ctx *c; int cls; int idx;
-    Timed(poc_ctx *c_, int cls_) : c(c_), cls(cls_), idx(-1) {
+    poc_ctx *c; int cls; int idx; cudaStream_t s;
+    Timed(poc_ctx *c_, int cls_, cudaStream_t s_ = nullptr) : c(c_), cls(cls_), idx(-1), s(s_ ? s_ : c_->stream) {
         c->launches++;
         if (c->timing && c->ev_used + 2 <= (int)c->ev.size()) {
             idx = c->ev_used; c->ev_used += 2;
             c->ev_class[idx] = cls;
-            cudaEventRecord(c->ev[idx], c->stream);
+            cudaEventRecord(c->ev[idx], s);
         }
     }
-    ~Timed() { if (idx >= 0) cudaEventRecord(c->ev[idx + 1], c->stream); }
+    ~Timed() { if (idx >= 0) cudaEventRecord(c->ev[idx + 1], s); }
 };
 
 extern "C" {
@@ -126,7 +135,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, cudaGetErrorString(e)); }
     DevCtx &d = ctx->d;
     int R = n_replicas, N = max_agents;
-    d.R = R; d.Ncap = N;
+    d.R = R; d.Ncap = N; d.r0 = 0; d.Rg = R;
     d.Ccap = N / 16 + 64;
     d.Mcap = d.Ccap * 4 + 256;
     int pc = 16384;
@@ -185,11 +194,21 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     for (int l = 0; l < POC_NUM_LAYERS; l++) DA(ctx->st_rowptr[l], N + 1);
     DA(ctx->st_col, d.ucap + d.ccap); DA(ctx->st_co, d.ccap);
     DA(ctx->d_err, 1); DA(ctx->d_prev_counters, (size_t)R * CN_COUNT);
+    d.prev_counters = ctx->d_prev_counters;
     ctx->h_params.resize(R);
     ctx->h_nagents.assign(R, 0);
     ctx->ev.resize(EV_POOL); ctx->ev_class.assign(EV_POOL, 0);
     for (auto &evx : ctx->ev) cudaEventCreate(&evx);
     for (auto &m : ctx->marker) cudaEventCreate(&m);
+    ctx->ngroups = 1;  // measured: replica groups on separate streams gain < 12 % even fully independent (profiles/)
+    if (const char *e = getenv("POC_GROUPS")) ctx->ngroups = std::max(1, std::min(8, std::min(R, atoi(e))));
+    for (int g = 0; g < ctx->ngroups; g++) cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking);
+    for (auto &e : ctx->gev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto &e : ctx->gstag) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (const char *e = getenv("POC_GRAPH_TICKS")) ctx->graph_ticks = std::max(1, atoi(e));
+    d.r0 = 0; d.Rg = R; d.grp = 0;
+    DA(ctx->d_ti, 8); d.ti = ctx->d_ti;
+    if (const char *e = getenv("POC_GRAPH")) ctx->use_graph = atoi(e) != 0;
     cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_embeddedness<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(32, N));
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
@@ -207,6 +226,9 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     for (void *p : ctx->allocs) cudaFree(p);
     for (auto &evx : ctx->ev) cudaEventDestroy(evx);
     for (auto &m : ctx->marker) cudaEventDestroy(m);
+    for (int g = 0; g < ctx->ngroups; g++) cudaStreamDestroy(ctx->gstream[g]);
+    for (auto &e : ctx->gev) cudaEventDestroy(e);
+    for (auto &e : ctx->gstag) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return POC_OK;
@@ -444,11 +466,18 @@ int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, in
 static int max_n(poc_ctx *ctx) { int m = 0; for (int v : ctx->h_nagents) m = std::max(m, v); return m; }
 static int max_radius(poc_ctx *ctx) { int m = 1; for (auto &p : ctx->h_params) m = std::max(m, (int)p.max_accomplice_radius); return m; }
 
+static int set_tick(poc_ctx *ctx, int grp, int tick, int epoch, int rep, cudaStream_t s) {
+    TickInfo t{tick, epoch, rep, 0};
+    CU(cudaMemcpyAsync(ctx->d_ti + grp, &t, sizeof(t), cudaMemcpyHostToDevice, s));  // pageable source: staged before return
+    return POC_OK;
+}
+
 int poc_begin_tick(poc_ctx *ctx, int tick) {
     CHECK_CTX();
     int n = max_n(ctx);
     if (!n) return POC_OK;
-    { Timed t(ctx, TM_OTHER); k_begin_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d, tick); }
+    { int rc = set_tick(ctx, 0, tick, ctx->epoch, 0, ctx->stream); if (rc) return rc; }
+    { Timed t(ctx, TM_OTHER); k_begin_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d); }
     CU(cudaGetLastError());
     return POC_OK;
 }
@@ -457,36 +486,36 @@ int poc_end_tick(poc_ctx *ctx) {
     CHECK_CTX();
     int n = max_n(ctx);
     if (!n) return POC_OK;
-    { Timed t(ctx, TM_OTHER); k_end_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d); }
+    { Timed t(ctx, TM_OTHER); k_end_tick<<<dim3((n + 255) / 256, ctx->d.R), 256, 0, ctx->stream>>>(ctx->d, 0); }
     CU(cudaGetLastError());
     return POC_OK;
 }
 
-static int launch_cells(poc_ctx *ctx, int yearly) {
-    { Timed t(ctx, TM_CELLS); k_cells<<<ctx->d.R, 1024, 0, ctx->stream>>>(ctx->d, yearly); }
+static int launch_cells(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int yearly, int begin = 0) {
+    { Timed t(ctx, TM_CELLS, s); k_cells<<<D.Rg, 1024, 0, s>>>(D, yearly, begin); }
     CU(cudaGetLastError());
     return POC_OK;
 }
 
-static int launch_tendency(poc_ctx *ctx) {
+static int launch_tendency(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mode) {
     int n = max_n(ctx);
     if (!n) return POC_OK;
-    { Timed t(ctx, TM_TENDENCY); k_tendency_pre<<<dim3((n + 127) / 128, ctx->d.R), 128, 0, ctx->stream>>>(ctx->d); }
-    { Timed t(ctx, TM_TENDENCY); k_tendency_eps<<<ctx->d.R, 1024, 0, ctx->stream>>>(ctx->d); }
+    { Timed t(ctx, TM_TENDENCY, s); k_tendency_pre<<<dim3((n + 127) / 128, D.Rg), 128, 0, s>>>(D, mode); }
+    { Timed t(ctx, TM_TENDENCY, s); k_tendency_eps<<<D.Rg, 1024, 0, s>>>(D, mode); }
     CU(cudaGetLastError());
     return POC_OK;
 }
 
 int poc_tendency(poc_ctx *ctx) {
     CHECK_CTX();
-    int rc = launch_cells(ctx, 0);
+    int rc = launch_cells(ctx, ctx->d, ctx->stream, 0);
     if (rc) return rc;
-    return launch_tendency(ctx);
+    return launch_tendency(ctx, ctx->d, ctx->stream, 1);
 }
 
 int poc_crime_multiplier(poc_ctx *ctx, double *out) {
     CHECK_CTX();
-    int rc = launch_cells(ctx, 1);
+    int rc = launch_cells(ctx, ctx->d, ctx->stream, 1);
     if (rc) return rc;
     if (out) {
         CU(cudaMemcpyAsync(out, ctx->d.crime_mult, sizeof(double) * ctx->d.R, cudaMemcpyDeviceToHost, ctx->stream));
@@ -503,36 +532,36 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
     return POC_OK;
 }
 
-static void launch_emb(poc_ctx *ctx, int parity) {
-    dim3 grid(ctx->emb_gx, ctx->d.R);
-    if (ctx->emb_g == 32) k_embeddedness<32><<<grid, 256, ctx->smem_emb, ctx->stream>>>(ctx->d, parity);
-    else k_embeddedness<256><<<grid, 256, ctx->smem_emb, ctx->stream>>>(ctx->d, parity);
+static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity) {
+    dim3 grid(ctx->emb_gx, D.Rg);
+    if (ctx->emb_g == 32) k_embeddedness<32><<<grid, 256, ctx->smem_emb, s>>>(D, parity);
+    else k_embeddedness<256><<<grid, 256, ctx->smem_emb, s>>>(D, parity);
 }
 
 // search / embeddedness rounds shared by commit_crimes and the find_accomplices hook
-static int launch_search_rounds(poc_ctx *ctx, int tick) {
-    DevCtx &d = ctx->d;
+static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
     int rounds = max_radius(ctx);
-    dim3 grid(ctx->gx, d.R);
+    dim3 grid(ctx->gx, D.Rg);
     for (int rd = 0; rd <= rounds; rd++) {
-        { Timed t(ctx, TM_SEARCH); k_search<<<grid, 256, ctx->smem_search, ctx->stream>>>(d, tick, ctx->epoch, rd & 1); }
-        if (rd < rounds) { Timed t(ctx, TM_EMB); launch_emb(ctx, rd & 1); }
+        { Timed t(ctx, TM_SEARCH, s); k_search<<<grid, 256, ctx->smem_search, s>>>(D, rd & 1); }
+        if (rd < rounds) { Timed t(ctx, TM_EMB, s); launch_emb(ctx, D, s, rd & 1); }
     }
     CU(cudaGetLastError());
     return POC_OK;
 }
 
-static int launch_commit(poc_ctx *ctx, int tick, bool cells_done, int report_t) {
-    DevCtx &d = ctx->d;
-    ctx->epoch++;
-    if (!cells_done) { int rc = launch_cells(ctx, 0); if (rc) return rc; }
-    { Timed t(ctx, TM_OTHER); k_snapshot_counters<<<(d.R * CN_COUNT + 255) / 256, 256, 0, ctx->stream>>>(d, ctx->d_prev_counters); }
-    { Timed t(ctx, TM_DRAW); k_draw<<<d.R, 512, 0, ctx->stream>>>(d, tick); }
-    int rc = launch_search_rounds(ctx, tick);
+// one replica range, one stream: reset_oc_embeddedness + commit_crimes.  ctx->epoch must have been bumped.
+static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cells_done, bool report, cudaEvent_t after_draw = nullptr,
+                         int end_tick = 0) {
+    if (!cells_done) { int rc = launch_cells(ctx, D, s, 0); if (rc) return rc; }
+    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, 512, 0, s>>>(D); }
+    if (after_draw) CU(cudaEventRecord(after_draw, s));
+    int rc = launch_search_rounds(ctx, D, s);
     if (rc) return rc;
-    { Timed t(ctx, TM_COMMIT); k_commit<<<d.R, 1024, 0, ctx->stream>>>(d); }
-    { Timed t(ctx, TM_ARREST); k_recruit_arrest<<<d.R, 32, 0, ctx->stream>>>(d, tick); }
-    if (report_t >= 0) { Timed t(ctx, TM_OTHER); k_report<<<d.R, 512, 0, ctx->stream>>>(d, report_t); }
+    { Timed t(ctx, TM_COMMIT, s); k_commit<<<D.Rg, 1024, 0, s>>>(D); }
+    { Timed t(ctx, TM_ARREST, s); k_recruit_arrest<<<D.Rg, 256, 0, s>>>(D, end_tick); }
+    // the reporter row of the tick is written after the end-of-tick bookkeeping (model.py:286-287)
+    if (report) { Timed t(ctx, TM_OTHER, s); k_report<<<D.Rg, 512, 0, s>>>(D, end_tick == 2 ? 1 : 0); }
     CU(cudaGetLastError());
     return POC_OK;
 }
@@ -612,7 +641,10 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay, c
     CHECK_CTX();
     int rc = upload_replay(ctx, replay, keys);
     if (rc) return rc;
-    rc = launch_commit(ctx, tick, false, -1);
+    ctx->epoch++;
+    rc = set_tick(ctx, 0, tick, ctx->epoch, 0, ctx->stream);
+    if (rc) return rc;
+    rc = launch_commit(ctx, ctx->d, ctx->stream, false, false);
     if (rc) return rc;
     if (out || rec) return read_tick_out(ctx, out, rec);
     return POC_OK;
@@ -630,18 +662,75 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
         d.reporters = p; d.Tcap = n_ticks;
     }
     int n = max_n(ctx);
-    for (int i = 0; i < n_ticks; i++) {
-        int tick = tick0 + i;
-        if (n) { Timed t(ctx, TM_OTHER); k_begin_tick<<<dim3((n + 255) / 256, d.R), 256, 0, ctx->stream>>>(d, tick); }
-        bool yearly = false;  // model.py:248 -- evaluated per replica below only through ticks_per_year of replica 0
-        int tpy = ctx->h_params[0].ticks_per_year;
-        yearly = (tick % tpy == 0) || tick == 1;
-        rc = launch_cells(ctx, yearly ? 1 : 0);
+    int G = ctx->ngroups;
+    bool report = reporters_out != nullptr;
+    for (int g = 0; g < G; g++) { rc = set_tick(ctx, g, tick0, ctx->epoch + 1, 0, ctx->stream); if (rc) return rc; }
+    ctx->epoch += n_ticks;
+    // one tick of every replica group; each group's pipeline on its own stream, forked from / joined to the
+    // main stream.  Kernels take the tick from the device-side TickInfo, so the sequence has no per-tick
+    // arguments and can be captured once and replayed as a CUDA graph.
+    // K ticks per replica group as one independent chain per stream.  Group g starts its chain when group g-1
+    // has finished its first crime draw, so the groups run out of phase and the latency-bound one-block-per-
+    // replica kernels of one group overlap the traversal kernels of the others.
+    auto enqueue_ticks = [&](int K) -> int {
+        CU(cudaEventRecord(ctx->gev[8], ctx->stream));
+        for (int g = 0; g < G; g++) {
+            DevCtx D = d;
+            D.r0 = (int)((long long)d.R * g / G);
+            D.Rg = (int)((long long)d.R * (g + 1) / G) - D.r0;
+            D.grp = g;
+            if (D.Rg <= 0) continue;
+            cudaStream_t s = ctx->gstream[g];
+            CU(cudaStreamWaitEvent(s, ctx->gev[8], 0));
+            if (g > 0) CU(cudaStreamWaitEvent(s, ctx->gstag[g - 1], 0));
+            for (int k = 0; k < K; k++) {
+                // (fusing begin/end-of-tick bookkeeping into the one-block-per-replica kernels measured slower:
+                //  they are grid-wide passes, and the single blocks are the critical path)
+                if (n) { Timed t(ctx, TM_OTHER, s); k_begin_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D); }
+                int rc2 = launch_cells(ctx, D, s, 2, 0);
+                if (rc2) return rc2;
+                rc2 = launch_tendency(ctx, D, s, 2);
+                if (rc2) return rc2;
+                rc2 = launch_commit(ctx, D, s, true, false, (k == 0 && g + 1 < G) ? ctx->gstag[g] : nullptr, 0);
+                if (rc2) return rc2;
+                if (n) { Timed t(ctx, TM_OTHER, s); k_end_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, 0); }
+                // reporter row after the end-of-tick bookkeeping (model.py:286-287); it also moves the tick state on
+                { Timed t(ctx, TM_OTHER, s); k_report<<<D.Rg, 512, 0, s>>>(D, report ? 2 : 3); }
+            }
+            CU(cudaEventRecord(ctx->gev[g], s));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->gev[g], 0));
+        }
+        return POC_OK;
+    };
+    if (ctx->use_graph && !ctx->timing && n_ticks > 1 && n > 0) {
+        int K = std::min(ctx->graph_ticks, n_ticks);
+        int done = 0;
+        while (done < n_ticks) {
+            int kk = std::min(K, n_ticks - done);   // the tail gets its own (smaller) graph
+            int reps = (kk == K) ? (n_ticks - done) / K : 1;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            long long launches_before = ctx->launches;
+            CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+            rc = enqueue_ticks(kk);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            CU(cudaGraphInstantiate(&exec, graph, 0));
+            long long per_graph = ctx->launches - launches_before;
+            for (int i = 0; i < reps; i++) {
+                cudaError_t le = cudaGraphLaunch(exec, ctx->stream);
+                if (le != cudaSuccess) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return fail(ctx, POC_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le)); }
+            }
+            ctx->launches = launches_before + per_graph * reps;
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaGraphExecDestroy(exec);
+            cudaGraphDestroy(graph);
+            done += kk * reps;
+        }
+    } else {
+        rc = enqueue_ticks(n_ticks);
         if (rc) return rc;
-        if (yearly) { rc = launch_tendency(ctx); if (rc) return rc; }
-        rc = launch_commit(ctx, tick, true, reporters_out ? i : -1);
-        if (rc) return rc;
-        if (n) { Timed t(ctx, TM_OTHER); k_end_tick<<<dim3((n + 255) / 256, d.R), 256, 0, ctx->stream>>>(d); }
     }
     CU(cudaGetLastError());
     if (reporters_out && n_ticks) {
@@ -746,7 +835,7 @@ static int run_emb(poc_ctx *ctx, int replica, int n, const int32_t *agents) {
     zero[replica] = n;
     CU(cudaMemcpyAsync(d.n_emb, zero.data(), sizeof(int32_t) * zero.size(), cudaMemcpyHostToDevice, st));
     if (n) CU(cudaMemcpyAsync(d.emb_list + (size_t)replica * d.Ncap, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    { Timed t(ctx, TM_EMB); launch_emb(ctx, 0); }
+    { Timed t(ctx, TM_EMB); launch_emb(ctx, ctx->d, ctx->stream, 0); }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     return POC_OK;
@@ -808,10 +897,12 @@ int poc_find_accomplices(poc_ctx *ctx, int replica, int n, const int32_t *initia
     std::vector<int> cn_before((size_t)d.R * CN_COUNT);
     CU(cudaMemcpyAsync(cn_before.data(), d.counters, sizeof(int) * cn_before.size(), cudaMemcpyDeviceToHost, st));
     ctx->epoch++;
+    rc = set_tick(ctx, 0, 0, ctx->epoch, 0, st);
+    if (rc) return rc;
     k_hook_init_crimes<<<(std::max(n, 1) + 255) / 256, 256, 0, st>>>(d, replica, n, ctx->d_hook_a, ctx->d_hook_b);
     k_hook_fill_search<<<1, 32, 0, st>>>(d, replica, n);
     CU(cudaGetLastError());
-    rc = launch_search_rounds(ctx, 0);
+    rc = launch_search_rounds(ctx, ctx->d, ctx->stream);
     if (rc) return rc;
     std::vector<int32_t> acc((size_t)n * POC_MAX_GROUP), nacc(n), fails(n);
     if (n) {

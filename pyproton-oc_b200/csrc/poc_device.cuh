@@ -55,8 +55,14 @@ enum {
 enum { ST_EMB_REQUESTS = 0, ST_EMB_FULL, ST_EMB_BYTES, ST_EMB_NODES, ST_SEARCH_CRIMES, ST_SEARCH_BYTES,
        ST_SEARCH_CANDIDATES, ST_SPARE, ST_PH0 = 8, ST_COUNT = 16 };  // ST_PH0..: per-phase cycles (POC_PHASES builds)
 
+// per replica-group tick state kept on the device so that a whole tick is a parameter-free launch sequence
+// (CUDA graph replay): current tick, embeddedness-cache epoch, reporter row
+struct TickInfo { int tick, epoch, rep, pad; };
+
 struct DevCtx {
     int R, Ncap, Ccap, Mcap, Pcap;  // replicas, agent / crime / member / pair capacities per replica
+    int r0, Rg, grp;                // the replica range [r0, r0 + Rg) this launch serves (one range per stream)
+    TickInfo *ti;                   // [8] tick state per replica group
     long long ucap, ccap;           // static / criminal entry capacity per replica
     int *n_agents;                  // [R]
     // agents
@@ -71,6 +77,7 @@ struct DevCtx {
     poc_params *params;             // [R]
     double *crime_mult;             // [R]
     int *counters;                  // [R][CN_COUNT]
+    int *prev_counters;             // [R][CN_COUNT] snapshot taken by k_draw at the start of commit_crimes
     unsigned long long *edges;      // [R] traversed multiplex entries (bench metric)
     unsigned long long *stats;      // [R][ST_COUNT] algorithmic-work counters, see enum below
     // cells

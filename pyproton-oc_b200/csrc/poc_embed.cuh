@@ -124,7 +124,7 @@ template <int G>
 __global__ void __launch_bounds__(256, (G == 32) ? 4 : 6) k_embeddedness(DevCtx C, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPB = 256 / G, DCAP = EmbCfg<G>::DCAP, NW = G / 32;
-    int r = blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
+    int r = C.r0 + blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
     int gid = threadIdx.x / G, gt = threadIdx.x % G, lane = threadIdx.x & 31, w = gt >> 5;
     // shared memory: [invw 256 f64] then per group [dist DCAP u64][EmbShared][bitmap wcap][wprefix wcap]
     double *invw = (double *)smem_raw;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, (G == 32) ? 4 : 6) k_embeddedness(DevCtx 
     EmbShared *S = (EmbShared *)(gbase + (size_t)DCAP * 8);
     unsigned *bitmap = (unsigned *)((unsigned char *)S + ((sizeof(EmbShared) + 7) & ~(size_t)7));
     int *wprefix = (int *)((unsigned char *)bitmap + (((size_t)wcap * 4 + 7) & ~(size_t)7));
-    int slot = (blockIdx.y * gridDim.x + blockIdx.x) * GPB + gid;
+    int slot = (r * gridDim.x + blockIdx.x) * GPB + gid;
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
     unsigned *edgebuf = C.scr_edges + (size_t)slot * ECAP;

@@ -133,8 +133,9 @@ __global__ void k_link_criminal(DevCtx C, int r, int n) {
 
 // ============================================================================ tick bookkeeping
 // model.py:236-238 (+ extra.py:359-361): per scheduled agent zero the this-tick counter and recompute age.
-__global__ void k_begin_tick(DevCtx C, int tick) {
-    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_begin_tick(DevCtx C) {
+    int tick = C.ti[C.grp].tick;
+    int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= C.n_agents[r]) return;
     size_t o = (size_t)r * C.Ncap + a;
     uint32_t x = C.attr[o];
@@ -148,8 +149,10 @@ __global__ void k_begin_tick(DevCtx C, int tick) {
 }
 
 // model.py:279-283
-__global__ void k_end_tick(DevCtx C) {
-    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_end_tick(DevCtx C, int advance) {
+    // last kernel of the tick for this replica group: move the device-side tick state on
+    if (advance && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { TickInfo &t = C.ti[C.grp]; t.tick++; t.epoch++; t.rep++; }
+    int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= C.n_agents[r]) return;
     size_t o = (size_t)r * C.Ncap + a;
     uint32_t x = C.attr[o];
@@ -175,9 +178,16 @@ __device__ __forceinline__ int pk_get(const unsigned long long pk[CELL_WORDS], i
     for (int q = 0; q < CELL_WORDS; q++) if (q == c / 3) v = pk[q];
     return (int)((v >> (21 * (c % 3))) & 0x1fffffull);
 }
-__global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
-    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+// mode: 0 partition only, 1 also the crime multiplier, 2 the multiplier on yearly ticks (model.py:248)
+__device__ __forceinline__ bool is_yearly(const DevCtx &C, const poc_params &P) {
+    int tick = C.ti[C.grp].tick;
+    return (tick % P.ticks_per_year) == 0 || tick == 1;
+}
+// begin != 0 fuses k_begin_tick (age from birth_tick, this-tick counters) into the first pass
+__global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
+    int r = C.r0 + blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
+    bool yearly = mode == 1 || (mode == 2 && is_yearly(C, P));
     int nc = P.n_cells;
     __shared__ unsigned char lut[512], luts[512];
     __shared__ int base[POC_MAX_CELLS + 1], cnts[POC_MAX_CELLS], s_alive;
@@ -202,9 +212,18 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
 #pragma unroll
     for (int q = 0; q < CELL_WORDS; q++) { pk[q] = 0; pks[q] = 0; }
     int alive_cnt = 0;
+    int tick_now = C.ti[C.grp].tick, tpy = P.ticks_per_year;
     for (int a = a_begin; a < a_end; a++) {
         uint32_t x = attr[a];
         if (!(x & F_ALIVE)) continue;
+        if (begin) {  // model.py:236-238, extra.py:359-361
+            int dt = tick_now - RP(C.birth, r, C.Ncap)[a];
+            int age = (dt >= 0) ? dt / tpy : -((-dt + tpy - 1) / tpy);
+            age = age < 0 ? 0 : (age > 255 ? 255 : age);
+            x = (x & ~0xffu) | (uint32_t)age;
+            RP(C.attr, r, C.Ncap)[a] = x;
+            RP(C.ncrimes_tick, r, C.Ncap)[a] = 0;
+        }
         alive_cnt++;
         int i = ((x & F_MALE) ? 256 : 0) | attr_age(x);
         int c = lut[i], cs = luts[i];
@@ -274,8 +293,9 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int yearly) {
 
 // ============================================================================ A1 criminal tendency
 // Person.update_criminal_tendency, entities.py:337-367 (quirks Q2, Q3 kept).  One thread per agent.
-__global__ void k_tendency_pre(DevCtx C) {
-    int r = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_tendency_pre(DevCtx C, int mode) {
+    int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 2 && !is_yearly(C, C.params[r])) return;
     if (a >= C.n_agents[r]) return;
     size_t o = (size_t)r * C.Ncap + a;
     uint32_t x = C.attr[o];
@@ -337,9 +357,10 @@ __device__ double pw_sum(const double *t, const int *idx, int n) {
 
 // epsilon re-centring per cell, model.py:1180-1184.  One block per replica, one thread per cell for the
 // (order-defined) mean, then all threads add epsilon.
-__global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C) {
-    int r = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C, int mode) {
+    int r = C.r0 + blockIdx.x, tid = threadIdx.x;
     const poc_params &P = C.params[r];
+    if (mode == 2 && !is_yearly(C, P)) return;
     __shared__ double eps[POC_MAX_CELLS];
     __shared__ int off[POC_MAX_CELLS + 1];
     const int32_t *members = RP(C.cell_members, r, C.Ncap);
@@ -364,8 +385,9 @@ __global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C) {
 // model.py:1427-1440 + extra.py:102-149.  One block per replica.  The CDF is built exactly as
 // weighted_n_of + Generator.choice build it: optional min-shift, left-to-right sum, p/sum, sequential
 // cumsum, divide by the last element; one lane per cell runs the two order-defined chains.
-__global__ void __launch_bounds__(512) k_draw(DevCtx C, int tick) {
-    int r = blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+__global__ void __launch_bounds__(512) k_draw(DevCtx C) {
+    int tick = C.ti[C.grp].tick;
+    int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     int nc = P.n_cells;
     __shared__ int off[POC_MAX_CELLS + 1], ncr[POC_MAX_CELLS], coff[POC_MAX_CELLS + 1], nz[POC_MAX_CELLS];
@@ -389,6 +411,7 @@ __global__ void __launch_bounds__(512) k_draw(DevCtx C, int tick) {
         for (int k = 0; k < nc; k++) { coff[k] = s; s += ncr[k]; }
         coff[nc] = s;
         if (s > C.Ccap) { atomicExch(&cn[CN_ERROR], 10); s = C.Ccap; for (int k = 0; k <= nc; k++) if (coff[k] > s) coff[k] = s; }
+        for (int q = 0; q < CN_COUNT; q++) RP(C.prev_counters, r, CN_COUNT)[q] = cn[q];  // deltas of this tick
         C.n_crimes[r] = s;
         C.n_search[r] = 0;
         C.n_pairs[r] = 0;
@@ -634,12 +657,13 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     }
 }
 
-__global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, int parity) {
+__global__ void __launch_bounds__(256) k_search(DevCtx C, int parity) {
+    int tick = C.ti[C.grp].tick, epoch = C.ti[C.grp].epoch;
     extern __shared__ unsigned smem_u[];
-    int r = blockIdx.y;
+    int r = C.r0 + blockIdx.y;
     int wcap = (C.Ncap + 31) >> 5;
     unsigned *bitmap = smem_u, *fbits = smem_u + wcap;
-    int slot = blockIdx.y * gridDim.x + blockIdx.x;
+    int slot = r * gridDim.x + blockIdx.x;
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     double *keys = C.scr_key + (size_t)slot * (C.Ncap + 1);
     unsigned long long edges = 0, abytes = 0, ncand = 0, ncrimes = 0;
@@ -671,7 +695,7 @@ __global__ void __launch_bounds__(256) k_search(DevCtx C, int tick, int epoch, i
 // -> dedup with multiplicity -> merge into the criminal CSR (new links enter with 0 and every co-offence
 // adds 1).  One block per replica.
 __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
-    int r = blockIdx.x, tid = threadIdx.x, n = C.n_agents[r];
+    int r = C.r0 + blockIdx.x, tid = threadIdx.x, n = C.n_agents[r];
     __shared__ int ws[33];
     __shared__ int carry, s_np;
     const poc_params &P = C.params[r];
@@ -878,8 +902,8 @@ __device__ int warp_weighted_cdf(const double *w, int n, double *p, double *cdf)
 }
 
 // one warp per replica; lane 0 walks the strictly sequential parts (recruitment order, the sampler, get_caught)
-__global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
-    int r = blockIdx.x, lane = lane_id();
+__device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
+    int lane = lane_id();
     const poc_params &P = C.params[r];
     int *cn = RP(C.counters, r, CN_COUNT);
     int ncr = C.n_crimes[r];
@@ -1052,10 +1076,49 @@ __global__ void __launch_bounds__(32) k_recruit_arrest(DevCtx C, int tick) {
     cn[CN_TICK_ARRESTS] = nfound;
 }
 
+// end_tick: 0 = arrests only; 1 = also the prisoner countdown of model.py:279-283 (k_end_tick fused);
+// 2 = also advance the replica group's device-side tick state once the last block of the launch is through
+__global__ void __launch_bounds__(256) k_recruit_arrest(DevCtx C, int end_tick) {
+    int tick = C.ti[C.grp].tick;
+    int r = C.r0 + blockIdx.x;
+    if (warp_id() == 0) recruit_arrest_warp(C, r, tick);
+    if (!end_tick) return;
+    __syncthreads();
+    int n = C.n_agents[r];
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    double *sentence = RP(C.sentence, r, C.Ncap);
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        uint32_t x = attr[a];
+        if ((x & (F_ALIVE | F_PRISONER)) != (F_ALIVE | F_PRISONER)) continue;
+        double s = sentence[a] - 1.0;
+        sentence[a] = s;
+        if (s == 0.0) attr[a] = x & ~F_PRISONER;
+    }
+    if (end_tick == 2) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            TickInfo &t = C.ti[C.grp];
+            if (atomicAdd(&t.pad, 1) == (int)gridDim.x - 1) { t.pad = 0; t.tick++; t.epoch++; t.rep++; __threadfence(); }
+        }
+    }
+}
+
 // ============================================================================ reporters (calculate_fast_reporters subset)
 // model.py:1687-1735, the columns the hot path feeds.  One block per replica.
-__global__ void __launch_bounds__(512) k_report(DevCtx C, int t) {
-    int r = blockIdx.x, n = C.n_agents[r], tid = threadIdx.x;
+// mode 0/1: write the row (1: the tick state has already moved on); 2: write the row, then the last block moves the
+// replica group's tick state on; 3: only move the tick state on
+__global__ void __launch_bounds__(512) k_report(DevCtx C, int mode) {
+    int t = C.ti[C.grp].rep - (mode == 1 ? 1 : 0);
+    if (mode >= 2) {
+        __shared__ int s_last;
+        if (mode == 3) {
+            if (threadIdx.x == 0) { TickInfo &ti = C.ti[C.grp]; if (atomicAdd(&ti.pad, 1) == (int)gridDim.x - 1) { ti.pad = 0; ti.tick++; ti.epoch++; ti.rep++; } }
+            return;
+        }
+        (void)s_last;
+    }
+    int r = C.r0 + blockIdx.x, n = C.n_agents[r], tid = threadIdx.x;
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap), *nct = RP(C.ncrimes_tick, r, C.Ncap);
     const int32_t *crp = RP(C.c_rowptr, r, C.Ncap + 1);
@@ -1096,6 +1159,11 @@ __global__ void __launch_bounds__(512) k_report(DevCtx C, int t) {
         row[7] = (double)vi[0]; row[8] = (double)vi[1]; row[9] = (double)vi[2]; row[10] = (double)vi[3];
         row[11] = (double)vi[4]; row[12] = mean; row[13] = var > 0 ? sqrt(var) : 0.0; row[14] = nn;
         row[15] = C.crime_mult[r];
+        if (mode == 2) {
+            __threadfence();
+            TickInfo &ti = C.ti[C.grp];
+            if (atomicAdd(&ti.pad, 1) == (int)gridDim.x - 1) { ti.pad = 0; ti.tick++; ti.epoch++; ti.rep++; }
+        }
     }
 }
 
@@ -1167,5 +1235,5 @@ __global__ void k_hook_fill_search(DevCtx C, int r, int n) {  // deterministic s
 }
 __global__ void k_snapshot_counters(DevCtx C, int *prev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < C.R * CN_COUNT) prev[i] = C.counters[i];
+    if (i < C.Rg * CN_COUNT) prev[C.r0 * CN_COUNT + i] = C.counters[C.r0 * CN_COUNT + i];
 }

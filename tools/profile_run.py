@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--tick0", type=int, default=None)
     ap.add_argument("--warm-ticks", type=int, default=0, help="ticks run before the measured ones (state ages)")
     ap.add_argument("--timing", action="store_true")
+    ap.add_argument("--repeat", type=int, default=1, help="repeat upload+run and report the fastest")
     args = ap.parse_args()
     import bench
     import pyproton_oc_b200 as pkg
@@ -26,10 +27,23 @@ def main():
     n, stat, crim = pkg.CrimeEngine.capacity_for([st], 160000)
     E = pkg.CrimeEngine(args.replicas, n, stat, crim)
     E.set_params(pkg.make_params(prm))
+    keys = [r * 7919 + 17 for r in range(args.replicas)]
+    best = None
+    for rep_i in range(args.repeat - 1):
+        for r in range(args.replicas):
+            E.upload_state(r, st)
+            E.set_crime_multiplier(mult, r)
+        E.sync(); E.marker(0)
+        E.run_ticks(tick0, args.ticks, keys, reporters=False)
+        E.marker(1); E.sync()
+        ms = E.marker_elapsed_ms(0, 1)
+        best = ms if best is None else min(best, ms)
+    if best is not None:
+        print("device time, best of %d: %.2f ms (%.1f us/tick, %.1f M agent-ticks/s)" % (
+            args.repeat - 1, best, 1e3 * best / args.ticks, 1e-6 * int(st["alive"].sum()) * args.ticks * args.replicas / (best / 1e3)))
     for r in range(args.replicas):
         E.upload_state(r, st)
         E.set_crime_multiplier(mult, r)
-    keys = [r * 7919 + 17 for r in range(args.replicas)]
     if args.warm_ticks:
         E.run_ticks(tick0, args.warm_ticks, keys, reporters=False)
         tick0 += args.warm_ticks
