@@ -145,7 +145,9 @@ int poc_read_stats(poc_ctx *ctx, uint64_t *stats_out, int reset);
 /* ---- state in / out (replaces the Person object graph, entities.py:36-108) -------------------- */
 int poc_set_params(poc_ctx *ctx, int replica /* -1: all */, const poc_params *p);
 int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *cols);
-/* rows sorted ascending by col; co_off only for POC_CRIMINAL (Person.num_co_offenses, entities.py:83) */
+/* rows sorted ascending by col; co_off only for POC_CRIMINAL (Person.num_co_offenses, entities.py:83).
+ * poc_upload_agents / poc_upload_layer are asynchronous: the caller's buffers must stay valid, and invalid input is
+ * reported, when poc_build_graph (which synchronises) returns. */
 int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr, const int32_t *col,
                      const int32_t *co_off_or_null);
 /* merge the eight non-criminal layers into the packed multiplex CSR the kernels traverse */

@@ -210,6 +210,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(ctx->d_ti, 8); d.ti = ctx->d_ti;
     if (const char *e = getenv("POC_GRAPH")) ctx->use_graph = atoi(e) != 0;
     cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, POC_MAX_CELLS * 1024 * (int)sizeof(int));
     cudaFuncSetAttribute(k_embeddedness<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(32, N));
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
@@ -326,7 +327,9 @@ int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *c)
     ctx->h_nagents[replica] = n;
     if (n) k_pack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s, ctx->d_err);
     CU(cudaGetLastError());
-    return read_err(ctx, "poc_upload_agents");
+    // the staging columns are reused by the next upload: order it behind this pack kernel (same stream), and
+    // report invalid input at the next synchronising call (poc_build_graph / poc_sync)
+    return POC_OK;
 }
 
 int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr, const int32_t *col, const int32_t *co) {
@@ -346,7 +349,7 @@ int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr
         k_pack_criminal<<<(n + 256) / 256, 256, 0, st>>>(ctx->d, replica, n, ctx->st_rowptr[layer], dcol, co ? ctx->st_co : nullptr, ctx->d_err);
         CU(cudaGetLastError());
         ctx->st_have |= 1 << layer;
-        return read_err(ctx, "poc_upload_layer(criminal)");
+        return POC_OK;
     }
     // static layers are staged back to back in upload order; poc_build_graph merges them
     int idx = 0;
@@ -359,8 +362,7 @@ int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr
     ctx->st_off[idx + 1] = off + ne;
     ctx->st_have |= 1 << layer;
     ctx->st_idx[layer] = idx;
-    CU(cudaStreamSynchronize(st));  // host buffers may be reused by the caller
-    return POC_OK;
+    return POC_OK;  // asynchronous: the caller's buffers must stay valid until poc_build_graph returns
 }
 
 int poc_build_graph(poc_ctx *ctx, int replica) {
@@ -492,7 +494,9 @@ int poc_end_tick(poc_ctx *ctx) {
 }
 
 static int launch_cells(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int yearly, int begin = 0) {
-    { Timed t(ctx, TM_CELLS, s); k_cells<<<D.Rg, 1024, 0, s>>>(D, yearly, begin); }
+    int nc = 1;
+    for (auto &hp : ctx->h_params) nc = std::max(nc, (int)hp.n_cells);
+    { Timed t(ctx, TM_CELLS, s); k_cells<<<D.Rg, 1024, (size_t)nc * 1024 * sizeof(int), s>>>(D, yearly, begin); }
     CU(cudaGetLastError());
     return POC_OK;
 }
@@ -554,7 +558,7 @@ static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
 static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cells_done, bool report, cudaEvent_t after_draw = nullptr,
                          int end_tick = 0) {
     if (!cells_done) { int rc = launch_cells(ctx, D, s, 0); if (rc) return rc; }
-    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, 512, 0, s>>>(D); }
+    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, 1024, 0, s>>>(D); }
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);
     if (rc) return rc;

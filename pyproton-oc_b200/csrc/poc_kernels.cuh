@@ -165,34 +165,24 @@ __global__ void k_end_tick(DevCtx C, int advance) {
 // Age/sex cell partition (model.py:1172-1173, 1430-1432): stable (ascending slot) member lists per cell,
 // the strict counts calculate_crime_multiplier uses (model.py:1152, Q8) and, when `yearly`, the multiplier.
 // One block per replica.
-// Counts of up to 32 cells are carried as 21-bit fields packed three to a 64-bit word (11 words), so the
-// block-wide exclusive scan that gives every thread its stable write offsets is 11 integer scans.
-#define CELL_WORDS 11
-__device__ __forceinline__ void pk_add(unsigned long long pk[CELL_WORDS], int c) {
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) if (q == c / 3) pk[q] += 1ull << (21 * (c % 3));
-}
-__device__ __forceinline__ int pk_get(const unsigned long long pk[CELL_WORDS], int c) {
-    unsigned long long v = 0;
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) if (q == c / 3) v = pk[q];
-    return (int)((v >> (21 * (c % 3))) & 0x1fffffull);
-}
-// mode: 0 partition only, 1 also the crime multiplier, 2 the multiplier on yearly ticks (model.py:248)
+// Every thread owns a contiguous slice of the slots and counts its members per cell into its own column of a
+// shared-memory table cnt[cell][thread]; warp `c` then turns row c into exclusive prefixes (a 1024-element scan
+// per cell, all cells in parallel), which are exactly the stable write offsets of the second pass.
+// Dynamic shared memory: n_cells_max * blockDim.x ints.
 __device__ __forceinline__ bool is_yearly(const DevCtx &C, const poc_params &P) {
     int tick = C.ti[C.grp].tick;
     return (tick % P.ticks_per_year) == 0 || tick == 1;
 }
-// begin != 0 fuses k_begin_tick (age from birth_tick, this-tick counters) into the first pass
+// mode: 0 partition only, 1 also the crime multiplier, 2 the multiplier on yearly ticks (model.py:248)
 __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
+    extern __shared__ int cnt_tab[];  // [nc][blockDim.x]
     int r = C.r0 + blockIdx.x, n = C.n_agents[r], tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     bool yearly = mode == 1 || (mode == 2 && is_yearly(C, P));
-    int nc = P.n_cells;
+    int nc = P.n_cells, NT = blockDim.x;
     __shared__ unsigned char lut[512], luts[512];
-    __shared__ int base[POC_MAX_CELLS + 1], cnts[POC_MAX_CELLS], s_alive;
-    __shared__ unsigned long long wtot[32][CELL_WORDS];
-    for (int i = tid; i < 512; i += blockDim.x) {
+    __shared__ int base[POC_MAX_CELLS + 1], tot[POC_MAX_CELLS], adj[POC_MAX_CELLS], s_alive;
+    for (int i = tid; i < 512; i += NT) {
         int male = i >> 8, age = i & 255, c = 255, cs = 255;
         for (int k = nc - 1; k >= 0; k--)
             if (P.cell_male[k] == male) {
@@ -201,16 +191,13 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
             }
         lut[i] = (unsigned char)c; luts[i] = (unsigned char)cs;
     }
-    if (tid < POC_MAX_CELLS) cnts[tid] = 0;
+    for (int k = 0; k < nc; k++) cnt_tab[k * NT + tid] = 0;
+    if (tid < POC_MAX_CELLS) adj[tid] = 0;
     if (tid == 0) s_alive = 0;
     __syncthreads();
-    const uint32_t *attr = RP(C.attr, r, C.Ncap);
-    // every thread owns a contiguous slice of the slots: stable order = (thread, position in slice)
-    int chunk = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    int chunk = (n + NT - 1) / NT;
     int a_begin = min(n, tid * chunk), a_end = min(n, a_begin + chunk);
-    unsigned long long pk[CELL_WORDS], pks[CELL_WORDS];
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) { pk[q] = 0; pks[q] = 0; }
     int alive_cnt = 0;
     int tick_now = C.ti[C.grp].tick, tpy = P.ticks_per_year;
     for (int a = a_begin; a < a_end; a++) {
@@ -221,73 +208,56 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
             int age = (dt >= 0) ? dt / tpy : -((-dt + tpy - 1) / tpy);
             age = age < 0 ? 0 : (age > 255 ? 255 : age);
             x = (x & ~0xffu) | (uint32_t)age;
-            RP(C.attr, r, C.Ncap)[a] = x;
+            attr[a] = x;
             RP(C.ncrimes_tick, r, C.Ncap)[a] = 0;
         }
         alive_cnt++;
         int i = ((x & F_MALE) ? 256 : 0) | attr_age(x);
         int c = lut[i], cs = luts[i];
-        if (c != 255) pk_add(pk, c);
-        if (cs != 255) pk_add(pks, cs);
-    }
-    // strict counts and the alive count: warp reduce, then one shared atomic per warp and word
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) pks[q] = warp_sum_u64(pks[q]);
-    for (int o = 16; o > 0; o >>= 1) alive_cnt += __shfl_xor_sync(FULL_MASK, alive_cnt, o);
-    if (lane == 0) {
-        atomicAdd(&s_alive, alive_cnt);
-        for (int k = 0; k < nc; k++) { int v = pk_get(pks, k); if (v) atomicAdd(&cnts[k], v); }
-    }
-    // exclusive scan of the packed per-thread counts across the block
-    unsigned long long inc[CELL_WORDS];
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) {
-        unsigned long long x = pk[q];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
-        inc[q] = x;
-        if (lane == 31) wtot[w][q] = x;
-    }
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int q = 0; q < CELL_WORDS; q++) {
-            unsigned long long s = (lane < nw) ? wtot[lane][q] : 0ull, x = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
-            wtot[lane][q] = x - s;  // exclusive prefix of the warp totals
-            if (lane == 31) {       // x = block total of word q
-                for (int j = 0; j < 3; j++) { int k = q * 3 + j; if (k < POC_MAX_CELLS) base[k] = (int)((x >> (21 * j)) & 0x1fffffull); }
-            }
+        if (c != 255) cnt_tab[c * NT + tid]++;
+        if (cs != c) {  // the strict membership of calculate_crime_multiplier (Q8) differs: record the difference
+            if (c != 255) atomicSub(&adj[c], 1);
+            if (cs != 255) atomicAdd(&adj[cs], 1);
         }
+    }
+    for (int o = 16; o > 0; o >>= 1) alive_cnt += __shfl_xor_sync(FULL_MASK, alive_cnt, o);
+    if (lane == 0) atomicAdd(&s_alive, alive_cnt);
+    __syncthreads();
+    // warp c: exclusive scan of row c (one element per thread of the block), 32 elements per step
+    for (int c = w; c < nc; c += nw) {
+        int carry = 0;
+        for (int base_t = 0; base_t < NT; base_t += 32) {
+            int v = cnt_tab[c * NT + base_t + lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+            cnt_tab[c * NT + base_t + lane] = carry + x - v;
+            carry += __shfl_sync(FULL_MASK, x, 31);
+        }
+        if (lane == 0) tot[c] = carry;
     }
     __syncthreads();
     if (tid == 0) {
         int s = 0;
-        for (int k = 0; k < nc; k++) { int t = base[k]; base[k] = s; s += t; }
+        for (int k = 0; k < nc; k++) { base[k] = s; s += tot[k]; }
         base[nc] = s;
         int32_t *co = RP(C.cell_off, r, POC_MAX_CELLS + 1);
         for (int k = 0; k <= nc; k++) co[k] = base[k];
-        for (int k = 0; k < nc; k++) RP(C.cell_strict, r, POC_MAX_CELLS)[k] = cnts[k];
+        for (int k = 0; k < nc; k++) RP(C.cell_strict, r, POC_MAX_CELLS)[k] = tot[k] + adj[k];
         RP(C.counters, r, CN_COUNT)[CN_N_ALIVE] = s_alive;
         if (yearly) {  // model.py:1150-1157, left-to-right float64
             double total = 0.0;
-            for (int k = 0; k < nc; k++) total += P.cell_c[k] * (double)cnts[k];
+            for (int k = 0; k < nc; k++) total += P.cell_c[k] * (double)(tot[k] + adj[k]);
             C.crime_mult[r] = P.crimes_yearly_per10k / 10000.0 * (double)s_alive / total;
         }
     }
     __syncthreads();
-    // this thread's exclusive offsets, then the stable scatter of its slice
-#pragma unroll
-    for (int q = 0; q < CELL_WORDS; q++) pk[q] = inc[q] - pk[q] + wtot[w][q];
     int32_t *members = RP(C.cell_members, r, C.Ncap);
     for (int a = a_begin; a < a_end; a++) {
         uint32_t x = attr[a];
         if (!(x & F_ALIVE)) continue;
         int c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)];
         if (c == 255) continue;
-        members[base[c] + pk_get(pk, c)] = a;
-        pk_add(pk, c);
+        members[base[c] + cnt_tab[c * NT + tid]++] = a;
     }
 }
 
@@ -385,7 +355,7 @@ __global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C, int mode) {
 // model.py:1427-1440 + extra.py:102-149.  One block per replica.  The CDF is built exactly as
 // weighted_n_of + Generator.choice build it: optional min-shift, left-to-right sum, p/sum, sequential
 // cumsum, divide by the last element; one lane per cell runs the two order-defined chains.
-__global__ void __launch_bounds__(512) k_draw(DevCtx C) {
+__global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
     int tick = C.ti[C.grp].tick;
     int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
@@ -422,7 +392,8 @@ __global__ void __launch_bounds__(512) k_draw(DevCtx C) {
     }
     // stage weights cell-ordered, and per-cell min / any-negative (one warp per cell, round robin)
     int total = off[nc];
-    for (int i = tid; i < total; i += blockDim.x) cdf[i] = tend[members[i]];
+#pragma unroll 4
+    for (int i = tid; i < total; i += blockDim.x) cdf[i] = tend[members[i]];  // 4 independent gathers in flight
     __syncthreads();
     for (int k = w; k < nc; k += nw) {
         double m = INFINITY;
@@ -800,6 +771,7 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
         int cab = crim_find(g, a, b), cba = crim_find(g, b, a);
         int old = (cab >= 0 && cba >= 0) ? cab : 0;  // CANON: a half-present link is re-created with 0
         pcnt[i] = old + pcnt[i];
+        atomicOr(&addlen[a], 0x40000000);          // row a has pairs: it must be merged, not just moved
         if (cab < 0) atomicAdd(&addlen[a], 1);
     }
     __syncthreads();
@@ -808,7 +780,7 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     __syncthreads();
     for (int base = 0; base < n; base += blockDim.x) {
         int a = base + tid, v = 0, tot;
-        if (a < n) v = (g.c_rowptr[a + 1] - g.c_rowptr[a]) + addlen[a];
+        if (a < n) v = (g.c_rowptr[a + 1] - g.c_rowptr[a]) + (addlen[a] & 0x3fffffff);
         int ex = block_exscan(v, ws, &tot);
         if (a < n) rp_new[a] = carry + ex;
         __syncthreads();
@@ -822,6 +794,10 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     uint32_t *uent_rw = RP(C.u_ent, r, C.ucap);
     for (int a = tid; a < n; a += blockDim.x) {
         int ob = g.c_rowptr[a], oe = g.c_rowptr[a + 1], out = rp_new[a];
+        if (!(addlen[a] & 0x40000000)) {  // no pair starts at a: the row only moves
+            for (int i = ob; i < oe; i++) ent_new[out++] = g.c_ent[i];
+            continue;
+        }
         int pb = 0, pe = nu;  // lower_bound of (a,*) in the unique pair list
         { int lo = 0, hi = nu; unsigned long long key = (unsigned long long)(unsigned)a << 32;
           while (lo < hi) { int m = (lo + hi) >> 1; if (pairs[m] < key) lo = m + 1; else hi = m; } pb = lo; }

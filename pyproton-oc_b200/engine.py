@@ -101,6 +101,7 @@ class CrimeEngine:
         for l in range(NUM_LAYERS):
             rp, col = _i32(st["rowptr_%d" % l]), _i32(st["col_%d" % l])
             co = _i32(st["co_off"]) if l == CRIMINAL else None
+            keep += [rp, col, co]  # the uploads are asynchronous until poc_build_graph returns
             self._ck(self.L.poc_upload_layer(self.h, replica, l, rp.ctypes.data, col.ctypes.data if len(col) else None,
                                              co.ctypes.data if (co is not None and len(co)) else None))
         self._ck(self.L.poc_build_graph(self.h, replica))
