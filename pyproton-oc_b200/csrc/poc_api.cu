@@ -167,7 +167,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.u_rowptr, (size_t)R * (N + 1)); DA(d.u_ent, (size_t)R * d.ucap);
     DA(d.c_rowptr, (size_t)R * (N + 1)); DA(d.c_ent, (size_t)R * d.ccap);
     DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
-    DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT);
+    DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN);
     size_t RC = (size_t)R * d.Ccap, RM = (size_t)R * d.Mcap;
@@ -387,6 +387,8 @@ int poc_build_graph(poc_ctx *ctx, int replica) {
         k_exscan_i32<<<1, 1024, 0, st>>>(lens, urp, n);
         k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 1, ctx->d_err);
         k_link_criminal<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
+        CU(cudaMemsetAsync(ctx->d.layer_tot + (size_t)replica * 8, 0, sizeof(long long) * 8, st));
+        k_layer_totals<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
     } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
     CU(cudaGetLastError());
     ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;

@@ -80,6 +80,7 @@ struct DevCtx {
     int *prev_counters;             // [R][CN_COUNT] snapshot taken by k_draw at the start of commit_crimes
     unsigned long long *edges;      // [R] traversed multiplex entries (bench metric)
     unsigned long long *stats;      // [R][ST_COUNT] algorithmic-work counters, see enum below
+    long long *layer_tot;           // [R][8] directed entries per non-criminal layer over alive agents (tot_*_link)
     // cells
     int32_t *cell_members;          // [R][Ncap] ascending slot inside each cell
     int32_t *cell_off;              // [R][POC_MAX_CELLS+1]

@@ -131,6 +131,27 @@ __global__ void k_link_criminal(DevCtx C, int r, int n) {
     }
 }
 
+// tot_<layer>_link of calculate_fast_reporters (model.py:1715-1732) for the eight static layers: computed once here
+// and kept current by get_caught (the only place on the path that removes entries)
+__global__ void k_layer_totals(DevCtx C, int r, int n) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (a < n && (RP(C.attr, r, C.Ncap)[a] & F_ALIVE)) {
+        Graph g = graph_of(C, r);
+        for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
+            uint32_t m = ENT_MASK(g.u_ent[e]);
+#pragma unroll
+            for (int l = 0; l < 8; l++) cnt[l] += (m >> l) & 1;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        int v = cnt[l];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+        if (lane_id() == 0 && v) atomicAdd((unsigned long long *)&RP(C.layer_tot, r, 8)[l], (unsigned long long)v);
+    }
+}
+
 // ============================================================================ tick bookkeeping
 // model.py:236-238 (+ extra.py:359-361): per scheduled agent zero the this-tick counter and recompute age.
 __global__ void k_begin_tick(DevCtx C) {
@@ -368,6 +389,8 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
     double *cdf = RP(C.cdf, r, C.Ncap);
     int *cn = RP(C.counters, r, CN_COUNT);
     if (tid <= nc) off[tid] = RP(C.cell_off, r, POC_MAX_CELLS + 1)[tid];
+    // counter snapshot for the per-tick deltas (read before thread 0 updates the cumulative counters below)
+    if (tid >= 64 && tid < 64 + CN_COUNT) RP(C.prev_counters, r, CN_COUNT)[tid - 64] = cn[tid - 64];
     __syncthreads();
     if (tid < nc) {
         int m = off[tid + 1] - off[tid];
@@ -381,7 +404,6 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
         for (int k = 0; k < nc; k++) { coff[k] = s; s += ncr[k]; }
         coff[nc] = s;
         if (s > C.Ccap) { atomicExch(&cn[CN_ERROR], 10); s = C.Ccap; for (int k = 0; k <= nc; k++) if (coff[k] > s) coff[k] = s; }
-        for (int q = 0; q < CN_COUNT; q++) RP(C.prev_counters, r, CN_COUNT)[q] = cn[q];  // deltas of this tick
         C.n_crimes[r] = s;
         C.n_search[r] = 0;
         C.n_pairs[r] = 0;
@@ -1045,7 +1067,13 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
         if (x & F_HASJOB) x = (x & ~(F_HASJOB | (0xfu << 16))) | (1u << 16);
         x &= ~F_HASSCHOOL;
         attr[a] = x;
-        for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) uent[e] &= ~((MB_PROF | MB_SCHOOL) << 24);  // Q11
+        int nprof = 0, nschool = 0;
+        for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {  // Q11: own sets only
+            uint32_t en = uent[e];
+            nprof += (ENT_MASK(en) & MB_PROF) != 0; nschool += (ENT_MASK(en) & MB_SCHOOL) != 0;
+            uent[e] = en & ~((MB_PROF | MB_SCHOOL) << 24);
+        }
+        if (x & F_ALIVE) { RP(C.layer_tot, r, 8)[6] -= nprof; RP(C.layer_tot, r, 8)[7] -= nschool; }
         for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) cent_rw[e].y &= ~(int)((MB_PROF | MB_SCHOOL) << 24);
     }
     C.n_arrested[r] = nfound;
@@ -1099,42 +1127,55 @@ __global__ void __launch_bounds__(512) k_report(DevCtx C, int mode) {
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap), *nct = RP(C.ncrimes_tick, r, C.Ncap);
     const int32_t *crp = RP(C.c_rowptr, r, C.Ncap + 1);
     const double *tend = RP(C.tendency, r, C.Ncap);
-    long long noc = 0, npris = 0, nlink = 0, sumcr = 0, ococ = 0;
-    double st = 0.0, st2 = 0.0;
-    long long nal = 0;
+    enum { I_OC = 0, I_PRIS, I_LINK, I_SUMCR, I_OCOC, I_ALIVE, I_AGE, I_AGE2, I_EDU, I_EDU2, I_CR2, I_EMPL, I_FAC, I_STUD, NI };
+    long long vi[NI];
+#pragma unroll
+    for (int k = 0; k < NI; k++) vi[k] = 0;
+    double vd[2] = { 0.0, 0.0 };
     for (int a = tid; a < n; a += blockDim.x) {
         uint32_t x = attr[a];
         if (!(x & F_ALIVE)) continue;
-        nal++;
-        if (x & F_OC) { noc++; ococ += nct[a]; }
-        if (x & F_PRISONER) npris++;
-        nlink += crp[a + 1] - crp[a];
-        sumcr += ncr[a];
+        long long age = attr_age(x), edu = attr_edu(x), c = ncr[a];
+        vi[I_ALIVE]++;
+        if (x & F_OC) { vi[I_OC]++; vi[I_OCOC] += nct[a]; }
+        vi[I_PRIS] += (x & F_PRISONER) != 0; vi[I_EMPL] += (x & F_HASJOB) != 0; vi[I_FAC] += (x & F_FAC) != 0;
+        vi[I_STUD] += (x & F_HASSCHOOL) != 0;
+        vi[I_LINK] += crp[a + 1] - crp[a];
+        vi[I_SUMCR] += c; vi[I_CR2] += c * c; vi[I_AGE] += age; vi[I_AGE2] += age * age; vi[I_EDU] += edu; vi[I_EDU2] += edu * edu;
         double tv = tend[a];
-        st += tv; st2 += tv * tv;
+        vd[0] += tv; vd[1] += tv * tv;
     }
-    long long vi[6] = { noc, npris, nlink, sumcr, ococ, nal };
-    double vd[2] = { st, st2 };
     for (int o = 16; o > 0; o >>= 1) {
-        for (int k = 0; k < 6; k++) vi[k] += __shfl_xor_sync(FULL_MASK, vi[k], o);
+#pragma unroll
+        for (int k = 0; k < NI; k++) vi[k] += __shfl_xor_sync(FULL_MASK, vi[k], o);
         for (int k = 0; k < 2; k++) vd[k] += __shfl_xor_sync(FULL_MASK, vd[k], o);
     }
-    __shared__ long long wi[16][6];
+    __shared__ long long wi[16][NI];
     __shared__ double wd[16][2];
-    if (lane_id() == 0) { for (int k = 0; k < 6; k++) wi[warp_id()][k] = vi[k]; for (int k = 0; k < 2; k++) wd[warp_id()][k] = vd[k]; }
+    if (lane_id() == 0) { for (int k = 0; k < NI; k++) wi[warp_id()][k] = vi[k]; for (int k = 0; k < 2; k++) wd[warp_id()][k] = vd[k]; }
     __syncthreads();
     if (tid == 0) {
         int nw = blockDim.x >> 5;
-        for (int ww = 1; ww < nw; ww++) { for (int k = 0; k < 6; k++) vi[k] += wi[ww][k]; for (int k = 0; k < 2; k++) vd[k] += wd[ww][k]; }
+        for (int ww = 1; ww < nw; ww++) { for (int k = 0; k < NI; k++) vi[k] += wi[ww][k]; for (int k = 0; k < 2; k++) vd[k] += wd[ww][k]; }
         const int *cn = RP(C.counters, r, CN_COUNT);
+        const int *pv = RP(C.prev_counters, r, CN_COUNT);
+        const long long *lt = RP(C.layer_tot, r, 8);
         double *row = C.reporters + ((size_t)r * C.Tcap + t) * POC_N_REPORTERS;
-        double nn = (double)vi[5];
-        double mean = nn > 0 ? vd[0] / nn : 0.0, var = nn > 0 ? vd[1] / nn - mean * mean : 0.0;
+        double nn = (double)vi[I_ALIVE], inv = nn > 0 ? 1.0 / nn : 0.0;
+        auto sd = [&](double s1, double s2) { double m = s1 * inv, v = s2 * inv - m * m; return v > 0 ? sqrt(v) : 0.0; };
         row[0] = cn[CN_NUMBER_CRIMES]; row[1] = cn[CN_SIZE_FAILS]; row[2] = cn[CN_FAC_CRIMES]; row[3] = cn[CN_FAC_FAILS];
         row[4] = cn[CN_BIG_CRIME]; row[5] = cn[CN_OFFSPRING_RECRUITED]; row[6] = cn[CN_PEOPLE_JAILED];
-        row[7] = (double)vi[0]; row[8] = (double)vi[1]; row[9] = (double)vi[2]; row[10] = (double)vi[3];
-        row[11] = (double)vi[4]; row[12] = mean; row[13] = var > 0 ? sqrt(var) : 0.0; row[14] = nn;
+        row[7] = (double)vi[I_OC]; row[8] = (double)vi[I_PRIS]; row[9] = (double)vi[I_LINK]; row[10] = (double)vi[I_SUMCR];
+        row[11] = (double)vi[I_OCOC]; row[12] = vd[0] * inv; row[13] = sd(vd[0], vd[1]); row[14] = nn;
         row[15] = C.crime_mult[r];
+        row[16] = (double)vi[I_AGE] * inv; row[17] = sd((double)vi[I_AGE], (double)vi[I_AGE2]);
+        row[18] = (double)vi[I_EDU] * inv; row[19] = sd((double)vi[I_EDU], (double)vi[I_EDU2]);
+        row[20] = (double)vi[I_SUMCR] * inv; row[21] = sd((double)vi[I_SUMCR], (double)vi[I_CR2]);
+        row[22] = (double)vi[I_EMPL]; row[23] = (double)vi[I_FAC]; row[24] = (double)vi[I_STUD];
+        // sibling, offspring, parent, partner, household, friendship, professional, school
+        for (int l = 0; l < 8; l++) row[25 + l] = (double)lt[l];
+        row[33] = cn[CN_PROTECTED_RECRUITED]; row[34] = cn[CN_PEOPLE_JAILED] - pv[CN_PEOPLE_JAILED];
+        row[35] = C.ti[C.grp].tick; row[36] = cn[CN_RECRUITED]; row[37] = cn[CN_TICK_CRIMES]; row[38] = cn[CN_TICK_EMB]; row[39] = cn[CN_ERROR];
         if (mode == 2) {
             __threadfence();
             TickInfo &ti = C.ti[C.grp];

@@ -31,7 +31,13 @@ REPORTER_NAMES = ["number_crimes", "crime_size_fails", "facilitator_crimes", "fa
                   "big_crime_from_small_fish", "number_offspring_recruited_this_tick", "people_jailed",
                   "current_oc_members", "current_prisoners", "tot_criminal_link",
                   "number_crimes_committed_of_persons", "crimes_committed_by_oc_this_tick",
-                  "criminal_tendency_mean", "criminal_tencency_sd", "current_num_persons", "crime_multiplier"]
+                  "criminal_tendency_mean", "criminal_tencency_sd", "current_num_persons", "crime_multiplier",
+                  "age_mean", "age_sd", "education_level_mean", "education_level_sd", "num_crime_committed_mean",
+                  "num_crime_committed_sd", "employed", "facilitators", "number_students", "tot_sibling_link",
+                  "tot_offspring_link", "tot_parent_link", "tot_partner_link", "tot_household_link",
+                  "tot_friendship_link", "tot_professional_link", "tot_school_link",
+                  "number_protected_recruited_this_tick", "number_law_interventions_this_tick", "tick",
+                  "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code"]
 TIMER_CLASSES = ["cells", "tendency", "draw", "search", "embeddedness", "commit", "arrests", "other"]
 
 

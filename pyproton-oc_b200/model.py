@@ -611,14 +611,14 @@ class ProtonOC:
         cn, _ = e.counters()
         if cn[0, 9]:
             raise RuntimeError("crime path error code %d" % cn[0, 9])
+        floats = {"criminal_tendency_mean", "criminal_tencency_sd", "crime_multiplier", "age_mean", "age_sd",
+                  "education_level_mean", "education_level_sd", "num_crime_committed_mean", "num_crime_committed_sd"}
+        skip = {"tick", "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code"}
         for t in range(self.num_ticks):
-            for name, v in zip(REPORTER_NAMES, rep[t]):
-                setattr(self, name, float(v) if name in ("criminal_tendency_mean", "criminal_tencency_sd", "crime_multiplier")
-                        else int(v))
-            self.num_crime_committed_mean = (self.number_crimes_committed_of_persons / self.current_num_persons
-                                             if self.current_num_persons else float("nan"))
-            if t == self.num_ticks - 1:
-                self.calculate_fast_reporters()  # exact values of every column from the final state
+            for name, v in zip(REPORTER_NAMES, rep[t]):  # every calculate_fast_reporters column comes from k_report
+                if name not in skip:
+                    setattr(self, name, float(v) if name in floats else int(v))
+            self.number_jobs = self.employed
             self.schedule.step()
             self.datacollector.collect(self)
             self.tick += 1

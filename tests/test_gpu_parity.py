@@ -273,3 +273,33 @@ def test_batched_replicas_equal_single_runs(P):
                 assert np.array_equal(got["col_%d" % l], want["col_%d" % l]), (r, l)
             assert np.array_equal(got["co_off"], want["co_off"])
             assert np.array_equal(rep[r], wrep)
+
+
+# ------------------------------------------------------------------ BASELINE config 4: synthetic 100k agents
+def test_synthetic_100k_matches_oracle(P, O):
+    """The reference cannot produce this size; parity here is kernel vs CPU restatement,
+    plus size-independent properties: symmetric criminal links with equal counts, every link >= 1 co-offence,
+    crime participations = sum of group sizes."""
+    from pyproton_oc_b200 import synth
+    tpl = U.pre_state(U.load_fixture(U.GOLDEN + "/state_n10000_s42_baseline.npz"))
+    st = synth.synthetic_state(100000, seed=42, template=tpl, num_oc_persons=30)
+    assert int(st["oc_member"].sum()) == 300
+    prm = {}
+    ticks, key = 6, 4242
+    S = O.OracleState(st)
+    mult, totals = S.run_ticks(O.make_params(prm), 1, ticks, key, 0.0)
+    with engine_for(P, [st], crim_headroom=400000) as E:
+        E.set_params(P.make_params(prm))
+        E.upload_state(0, st)
+        rep = E.run_ticks(1, ticks, [key])
+        after = E.download_state(0)
+        cn, _ = E.counters()
+    assert cn[0, 9] == 0
+    assert_state_equal(after, S, what="100k after %d ticks" % ticks)
+    assert rep[0, -1, 0] == totals[0] and rep[0, -1, 15] == mult
+    n = len(st["alive"])
+    src = np.repeat(np.arange(n), np.diff(after["rowptr_6"]))
+    fwd = dict(zip(zip(src.tolist(), after["col_6"].tolist()), after["co_off"].tolist()))
+    assert all(fwd.get((b, a)) == c for (a, b), c in fwd.items())
+    assert (after["co_off"] >= 1).all()
+    assert int(after["num_crimes_committed"].sum()) == int(totals[1])
