@@ -150,11 +150,13 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     ctx->gx = (R >= 64) ? 32 : 64;
     // embeddedness: a chain of dependent gathers per evaluation, so large batches run one evaluation per warp
     // (about 24 resident per SM) and small ones one per block
-    ctx->emb_g = 256;  // the warp-per-evaluation variant (32) measured slower at every batch size (profiles/)
-    if (const char *e = getenv("POC_EMB_G")) ctx->emb_g = (atoi(e) == 32) ? 32 : 256;  // experiments
+    // threads per evaluation: measured 32 / 64 / 128 / 256 / 512 / 1024 -> 1197+ / 1197 / 885 / 782 / 777 / 856 us per
+    // 128-replica tick and - / 371 / 276 / 242 / 224 / 219 us per single-replica tick (profiles/)
+    ctx->emb_g = (R < 8) ? 1024 : 512;
+    if (const char *e = getenv("POC_EMB_G")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128 || g == 256 || g == 512 || g == 1024) ctx->emb_g = g; }  // experiments
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
     ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : ctx->gx;
-    int emb_slots = R * ctx->emb_gx * (256 / ctx->emb_g);
+    int emb_slots = R * ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1);
     d.scr_slots = std::max(R * ctx->gx, emb_slots);
     size_t wcap = (size_t)(N + 31) / 32;
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
@@ -212,6 +214,10 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, POC_MAX_CELLS * 1024 * (int)sizeof(int));
     cudaFuncSetAttribute(k_embeddedness<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(32, N));
+    cudaFuncSetAttribute(k_embeddedness<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(64, N));
+    cudaFuncSetAttribute(k_embeddedness<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(512, N));
+    cudaFuncSetAttribute(k_embeddedness<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(1024, N));
+    cudaFuncSetAttribute(k_embeddedness<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(128, N));
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaDeviceSetLimit(cudaLimitStackSize, 2048);  // pw_sum recursion
@@ -541,6 +547,10 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
 static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity) {
     dim3 grid(ctx->emb_gx, D.Rg);
     if (ctx->emb_g == 32) k_embeddedness<32><<<grid, 256, ctx->smem_emb, s>>>(D, parity);
+    else if (ctx->emb_g == 64) k_embeddedness<64><<<grid, 64, ctx->smem_emb, s>>>(D, parity);
+    else if (ctx->emb_g == 128) k_embeddedness<128><<<grid, 128, ctx->smem_emb, s>>>(D, parity);
+    else if (ctx->emb_g == 512) k_embeddedness<512><<<grid, 512, ctx->smem_emb, s>>>(D, parity);
+    else if (ctx->emb_g == 1024) k_embeddedness<1024><<<grid, 1024, ctx->smem_emb, s>>>(D, parity);
     else k_embeddedness<256><<<grid, 256, ctx->smem_emb, s>>>(D, parity);
 }
 

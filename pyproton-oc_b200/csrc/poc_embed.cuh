@@ -22,6 +22,10 @@
 
 template <int G> struct EmbCfg;
 template <> struct EmbCfg<256> { static constexpr int DCAP = 2048; };  // distances in shared memory up to this ball size
+template <> struct EmbCfg<1024> { static constexpr int DCAP = 2048; };
+template <> struct EmbCfg<512> { static constexpr int DCAP = 2048; };
+template <> struct EmbCfg<128> { static constexpr int DCAP = 1024; };
+template <> struct EmbCfg<64> { static constexpr int DCAP = 1024; };
 template <> struct EmbCfg<32> { static constexpr int DCAP = 512; };
 
 struct EmbShared {
@@ -121,9 +125,10 @@ __device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list
 }
 
 template <int G>
-__global__ void __launch_bounds__(256, (G == 32) ? 4 : 6) k_embeddedness(DevCtx C, int parity) {
+__global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 1024 ? 2 : (G == 512 ? 3 : (G == 256 ? 6 : (G == 128 ? 10 : 16))))) k_embeddedness(DevCtx C, int parity) {
+    // G == 32: eight warp-sized groups per 256-thread block; otherwise the block is the group
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int GPB = 256 / G, DCAP = EmbCfg<G>::DCAP, NW = G / 32;
+    constexpr int GPB = (G == 32) ? 8 : 1, DCAP = EmbCfg<G>::DCAP, NW = G / 32;
     int r = C.r0 + blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
     int gid = threadIdx.x / G, gt = threadIdx.x % G, lane = threadIdx.x & 31, w = gt >> 5;
     // shared memory: [invw 256 f64] then per group [dist DCAP u64][EmbShared][bitmap wcap][wprefix wcap]
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(256, (G == 32) ? 4 : 6) k_embeddedness(DevCtx 
 
 static inline size_t emb_smem_bytes(int G, int Ncap) {
     size_t wcap = (size_t)(Ncap + 31) / 32;
-    size_t dcap = (G == 32) ? EmbCfg<32>::DCAP : EmbCfg<256>::DCAP;
+    size_t dcap = (G == 32) ? EmbCfg<32>::DCAP : (G >= 256 ? EmbCfg<256>::DCAP : EmbCfg<128>::DCAP);
     size_t per_group = dcap * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * ((wcap * 4 + 7) & ~(size_t)7);
-    return 256 * 8 + (size_t)(256 / G) * per_group;
+    return 256 * 8 + (size_t)((G == 32) ? 8 : 1) * per_group;
 }
