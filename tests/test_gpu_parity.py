@@ -303,3 +303,43 @@ def test_synthetic_100k_matches_oracle(P, O):
     assert all(fwd.get((b, a)) == c for (a, b), c in fwd.items())
     assert (after["co_off"] >= 1).all()
     assert int(after["num_crimes_committed"].sum()) == int(totals[1])
+
+
+# ------------------------------------------------------------------ BASELINE configs 2 and 3 at full length
+@pytest.mark.parametrize("name,overrides", [
+    ("state_n3000_s42_baseline", {}),                                                       # config 2
+    ("state_n10000_s42_sample0", {"intervention": "facilitators", "number_arrests_per_year": 20}),   # config 3, run "0"
+    ("state_n10000_s42_sample2", {"intervention": "students", "number_arrests_per_year": 28}),       # config 3, run "2"
+])
+def test_full_length_runs_match_oracle(P, O, name, overrides):
+    """480 ticks of the hot path from the reference's own setup state: final state, criminal layer and the
+    per-tick reporter series equal the oracle's (Philox production mode).  The intervention presets of
+    samples/sample_json.json reach the path through facilitator_repression / ticks_between_intervention."""
+    from pyproton_oc_b200.model import ProtonOC
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st = U.pre_state(fx)
+    m = ProtonOC(seed=1)
+    m.override_dict(overrides)
+    m.choose_intervention_setting()
+    prm = {k: getattr(m, k) for k in P.HOT_PATH_DEFAULTS}
+    ticks, key = 480, 20261020
+    S = O.OracleState(st)
+    OP = O.make_params(prm)
+    mult, crimes, oc_series = 0.0, 0, []
+    for t in range(ticks):
+        mult, tot = S.run_ticks(OP, 1 + t, 1, key, mult)
+        crimes += int(tot[0])
+        if t % 60 == 59:
+            c = S.cols()
+            oc_series.append((crimes, int(c["oc_member"][c["alive"] > 0].sum()), int(c["prisoner"][c["alive"] > 0].sum())))
+    with engine_for(P, [st], crim_headroom=400000) as E:
+        E.set_params(P.make_params(prm))
+        E.upload_state(0, st)
+        rep = E.run_ticks(1, ticks, [key])
+        after = E.download_state(0)
+        cn, _ = E.counters()
+    assert cn[0, 9] == 0
+    assert_state_equal(after, S, what="%s after %d ticks" % (name, ticks))
+    got = [(int(rep[0, t, 0]), int(rep[0, t, 7]), int(rep[0, t, 8])) for t in range(59, ticks, 60)]
+    assert got == oc_series
+    assert rep[0, -1, 15] == mult
