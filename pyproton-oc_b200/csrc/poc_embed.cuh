@@ -129,6 +129,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
     // G == 32: eight warp-sized groups per 256-thread block; otherwise the block is the group
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPB = (G == 32) ? 8 : 1, DCAP = EmbCfg<G>::DCAP, NW = G / 32;
+    if ((int)blockIdx.x * GPB >= C.n_emb[parity * C.R + C.r0 + blockIdx.y]) return;  // one block per request; the rest leave at once
     int r = C.r0 + blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
     int gid = threadIdx.x / G, gt = threadIdx.x % G, lane = threadIdx.x & 31, w = gt >> 5;
     // shared memory: [invw 256 f64] then per group [dist DCAP u64][EmbShared][bitmap wcap][wprefix wcap]
@@ -152,10 +153,8 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
     int R = P.oc_embeddedness_radius;
     unsigned long long edges = 0, bfsbytes = 0, abytes = 0, anodes = 0;
     int nevals = 0, nreq = 0;
-    if (blockIdx.x * GPB < nreqs) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) invw[i] = (i > 0) ? 1.0 / (double)i : 0.0;
-        __syncthreads();
-    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) invw[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+    __syncthreads();
 #define RANK(v) (wprefix[(v) >> 5] + __popc(bitmap[(v) >> 5] & ((1u << ((v) & 31)) - 1)))
 #define INBALL(v) (bitmap[(v) >> 5] & (1u << ((v) & 31)))
     for (int item = blockIdx.x * GPB + gid; item < nreqs; item += gridDim.x * GPB) {
@@ -208,29 +207,30 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                 for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
                 int excl = incl - len, tot = __shfl_sync(FULL_MASK, incl, 31);
                 if (lane == 0) edges += (unsigned long long)tot;
+                // flattened index f of node t: multiplex entry (b0 - excl) + f while f < excl + len0, else criminal
+                // entry (b1 - excl - len0) + f
+                int adr0 = b0 - excl, split = excl + len0, adr1 = b1 - split;
                 for (int fb = 0; fb < tot; fb += 32) {
                     int f = fb + lane, t = 0;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) { int e = __shfl_sync(FULL_MASK, excl, t + s); if (e <= f) t += s; }
-                    int tb0 = __shfl_sync(FULL_MASK, b0, t), tl0 = __shfl_sync(FULL_MASK, len0, t);
-                    int tb1 = __shfl_sync(FULL_MASK, b1, t), tex = __shfl_sync(FULL_MASK, excl, t);
-                    int tru = __shfl_sync(FULL_MASK, ru, t);
+                    int ta0 = __shfl_sync(FULL_MASK, adr0, t), tsp = __shfl_sync(FULL_MASK, split, t);
+                    int ta1 = __shfl_sync(FULL_MASK, adr1, t), tru = __shfl_sync(FULL_MASK, ru, t);
                     bool ok = false;
                     int v = 0, wgt = 0;
                     if (f < tot) {
-                        int j = f - tex;
-                        if (j < tl0) {
-                            uint32_t ent = g.u_ent[tb0 + j];
+                        if (f < tsp) {
+                            uint32_t ent = g.u_ent[ta0 + f];
                             v = ENT_COL(ent); wgt = __popc(ENT_MASK(ent));
                             // a neighbour that also has a criminal entry is weighed there (mask copy + co-offences)
                             ok = wgt && !(ent & ENT_CRIM) && INBALL(v);
                         } else {
-                            int2 ce = g.c_ent[tb1 + (j - tl0)];
+                            int2 ce = g.c_ent[ta1 + f];
                             v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
                             ok = wgt > 0 && INBALL(v);  // 0: the reference divides by zero here
+                            if (ok && wgt > 255) { S->over = 1; ok = false; }
                         }
                     }
-                    if (ok && wgt > 255) { S->over = 1; ok = false; }
                     unsigned m = __ballot_sync(FULL_MASK, ok);
                     if (m) {
                         int basep = 0;
