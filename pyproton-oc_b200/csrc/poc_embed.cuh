@@ -267,7 +267,8 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                 for (int e = gt; e < nedge; e += G) {
                     unsigned ed = edgebuf[e];
                     int ru = ed & 0xfffu, rv = (ed >> 12) & 0xfffu;
-                    bool cu = chg0[ru >> 5] & (1u << (ru & 31)), cv = chg0[rv >> 5] & (1u << (rv & 31));
+                    // moved last round, or already this round (racy read: can only let more entries through)
+                    bool cu = (chg0[ru >> 5] | chg1[ru >> 5]) & (1u << (ru & 31)), cv = (chg0[rv >> 5] | chg1[rv >> 5]) & (1u << (rv & 31));
                     if (!(cu | cv)) continue;
                     double wt = invw[ed >> 24];
                     double du = __longlong_as_double((long long)dist[ru]), dv = __longlong_as_double((long long)dist[rv]);
