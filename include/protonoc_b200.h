@@ -175,6 +175,9 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay_or
  * reporters_out: [n_replicas][n_ticks][POC_N_REPORTERS] doubles, copied back at the end (may be NULL). */
 #define POC_N_REPORTERS 40 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
 int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *philox_keys, double *reporters_out);
+/* ProtonOC.calculate_fast_reporters, model.py:1687-1735, for the current device state: one row of POC_N_REPORTERS
+ * doubles per replica (columns: engine.REPORTER_NAMES). */
+int poc_report(poc_ctx *ctx, double *out /* [n_replicas][POC_N_REPORTERS] */);
 
 /* ---- stage hooks: the Person methods the reference's tests call directly ----------------------- */
 /* Person.agents_at_distance (exact = 1) / agents_in_radius (exact = 0), entities.py:482-524.

@@ -14,6 +14,13 @@
 enum { TM_CELLS = 0, TM_TENDENCY, TM_DRAW, TM_SEARCH, TM_EMB, TM_COMMIT, TM_ARREST, TM_OTHER };
 #define EV_POOL 32768
 
+#define POC_STAGE_COLS(X) \
+    X(propensity, double) X(tendency, double) X(sentence, double) X(arrest_weight, double) \
+    X(age, int32_t) X(birth_tick, int32_t) X(num_crimes, int32_t) X(num_crimes_tick, int32_t) X(father, int32_t) X(new_recruit, int32_t) \
+    X(alive, uint8_t) X(male, uint8_t) X(oc_member, uint8_t) X(facilitator, uint8_t) X(prisoner, uint8_t) \
+    X(has_job, uint8_t) X(has_school, uint8_t) X(target, uint8_t) \
+    X(job_level, int8_t) X(education_level, int8_t) X(wealth_level, int8_t)
+
 struct poc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -30,6 +37,10 @@ struct poc_ctx {
     size_t smem_search = 0, smem_emb = 0;
     // staging
     StageCols stage{};
+    uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
+    size_t stage_bytes = 0, stage_off[24] = {};
+    cudaEvent_t stage_ev = nullptr; bool stage_busy = false;
+    int draw_threads = 1024;        // k_draw block size: one block per SM is latency-bound, several need fewer registers per block
     int32_t *st_rowptr[POC_NUM_LAYERS] = {};
     int32_t *st_col = nullptr;      // all staged layers back to back
     int32_t *st_co = nullptr;
@@ -155,6 +166,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     ctx->emb_g = (R < 8) ? 1024 : 512;
     if (const char *e = getenv("POC_EMB_G")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128 || g == 256 || g == 512 || g == 1024) ctx->emb_g = g; }  // experiments
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
+    ctx->draw_threads = (R > 148) ? 256 : 1024;
+    if (const char *e = getenv("POC_DRAW_T")) { int t = atoi(e); if (t == 256 || t == 384 || t == 512 || t == 1024) ctx->draw_threads = t; }
     ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : ctx->gx;
     int emb_slots = R * ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1);
     d.scr_slots = std::max(R * ctx->gx, emb_slots);
@@ -172,6 +185,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN);
+    d.pw_cap = N / 64 + POC_MAX_CELLS + 8;
+    DA(d.pw_leaf, (size_t)R * d.pw_cap); DA(d.pw_sum, (size_t)R * d.pw_cap);
     size_t RC = (size_t)R * d.Ccap, RM = (size_t)R * d.Mcap;
     DA(d.n_crimes, R); DA(d.crime_init, RC); DA(d.crime_k, RC); DA(d.crime_flags, RC);
     DA(d.cr_target, RC); DA(d.cr_nacc, RC); DA(d.cr_d, RC); DA(d.cr_state, RC); DA(d.cr_fails, RC);
@@ -188,11 +203,22 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.scr_edges, (size_t)emb_slots * ECAP);
     DA(d.reporters, (size_t)R * d.Tcap * POC_N_REPORTERS);
     // staging
+    // the 21 staging columns share one device block (and one pinned host mirror for downloads), 8-byte columns first
     StageCols &s = ctx->stage;
-    DA(s.alive, N); DA(s.male, N); DA(s.oc_member, N); DA(s.facilitator, N); DA(s.prisoner, N); DA(s.has_job, N);
-    DA(s.has_school, N); DA(s.target, N); DA(s.job_level, N); DA(s.education_level, N); DA(s.wealth_level, N);
-    DA(s.age, N); DA(s.birth_tick, N); DA(s.num_crimes, N); DA(s.num_crimes_tick, N); DA(s.father, N); DA(s.new_recruit, N);
-    DA(s.propensity, N); DA(s.tendency, N); DA(s.sentence, N); DA(s.arrest_weight, N);
+    {
+        size_t o = 0, k = 0;
+#define SZ(f, T) ctx->stage_off[k++] = o; o += (sizeof(T) * (size_t)N + 15) & ~(size_t)15;
+        POC_STAGE_COLS(SZ)
+#undef SZ
+        ctx->stage_bytes = o;
+        DA(ctx->stage_dev, o);
+        cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
+        if (cudaHostAlloc((void **)&ctx->stage_host, o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
+        k = 0;
+#define PT(f, T) s.f = (T *)(ctx->stage_dev + ctx->stage_off[k++]);
+        POC_STAGE_COLS(PT)
+#undef PT
+    }
     for (int l = 0; l < POC_NUM_LAYERS; l++) DA(ctx->st_rowptr[l], N + 1);
     DA(ctx->st_col, d.ucap + d.ccap); DA(ctx->st_co, d.ccap);
     DA(ctx->d_err, 1); DA(ctx->d_prev_counters, (size_t)R * CN_COUNT);
@@ -231,6 +257,8 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
     for (auto &evx : ctx->ev) cudaEventDestroy(evx);
     for (auto &m : ctx->marker) cudaEventDestroy(m);
     for (int g = 0; g < ctx->ngroups; g++) cudaStreamDestroy(ctx->gstream[g]);
@@ -321,14 +349,18 @@ int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *c)
     if (!c || replica < 0 || replica >= ctx->d.R || n < 0 || n > ctx->d.Ncap) return fail(ctx, POC_ERR_ARG, "poc_upload_agents: bad argument");
     StageCols &s = ctx->stage;
     cudaStream_t st = ctx->stream;
-#define UP(f, T) CU(cudaMemcpyAsync(s.f, c->f, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st))
-    UP(alive, uint8_t); UP(male, uint8_t); UP(oc_member, uint8_t); UP(facilitator, uint8_t); UP(prisoner, uint8_t);
-    UP(has_job, uint8_t); UP(has_school, uint8_t); UP(target, uint8_t);
-    UP(job_level, int8_t); UP(education_level, int8_t); UP(wealth_level, int8_t);
-    UP(age, int32_t); UP(birth_tick, int32_t); UP(num_crimes, int32_t); UP(num_crimes_tick, int32_t); UP(father, int32_t);
-    UP(new_recruit, int32_t);
-    UP(propensity, double); UP(tendency, double); UP(sentence, double); UP(arrest_weight, double);
+    // the columns are gathered in the pinned mirror of the staging block and go up in one copy; the mirror is free
+    // again once the previous upload's copy has completed
+    if (ctx->stage_busy) { CU(cudaEventSynchronize(ctx->stage_ev)); ctx->stage_busy = false; }
+    {
+        size_t k = 0;
+#define UP(f, T) { if (!c->f && n) return fail(ctx, POC_ERR_ARG, "poc_upload_agents: column " #f " is NULL"); \
+                   if (n) memcpy(ctx->stage_host + ctx->stage_off[k], c->f, sizeof(T) * (size_t)n); k++; }
+        POC_STAGE_COLS(UP)
 #undef UP
+    }
+    CU(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, ctx->stage_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ctx->stage_ev, st)); ctx->stage_busy = true;
     CU(cudaMemcpyAsync(ctx->d.n_agents + replica, &n, sizeof(int), cudaMemcpyHostToDevice, st));
     ctx->h_nagents[replica] = n;
     if (n) k_pack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s, ctx->d_err);
@@ -409,15 +441,15 @@ int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *c) {
     cudaStream_t st = ctx->stream;
     if (n) k_unpack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s);
     CU(cudaGetLastError());
-#define DN(f, T) if (c->f) CU(cudaMemcpyAsync(c->f, s.f, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, st))
-    DN(alive, uint8_t); DN(male, uint8_t); DN(oc_member, uint8_t); DN(facilitator, uint8_t); DN(prisoner, uint8_t);
-    DN(has_job, uint8_t); DN(has_school, uint8_t); DN(target, uint8_t);
-    DN(job_level, int8_t); DN(education_level, int8_t); DN(wealth_level, int8_t);
-    DN(age, int32_t); DN(birth_tick, int32_t); DN(num_crimes, int32_t); DN(num_crimes_tick, int32_t); DN(father, int32_t);
-    DN(new_recruit, int32_t);
-    DN(propensity, double); DN(tendency, double); DN(sentence, double); DN(arrest_weight, double);
-#undef DN
+    // one device-to-host copy of the whole staging block into the pinned mirror, then plain memcpy per column
+    CU(cudaMemcpyAsync(ctx->stage_host, ctx->stage_dev, ctx->stage_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+        size_t k = 0;
+#define DN(f, T) { if (c->f && n) memcpy(c->f, ctx->stage_host + ctx->stage_off[k], sizeof(T) * (size_t)n); k++; }
+        POC_STAGE_COLS(DN)
+#undef DN
+    }
     return POC_OK;
 }
 
@@ -512,7 +544,7 @@ static int launch_cells(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int yearl
 static int launch_tendency(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mode) {
     int n = max_n(ctx);
     if (!n) return POC_OK;
-    { Timed t(ctx, TM_TENDENCY, s); k_tendency_pre<<<dim3((n + 127) / 128, D.Rg), 128, 0, s>>>(D, mode); }
+    { Timed t(ctx, TM_TENDENCY, s); k_tendency_pre<<<dim3(std::max(1, std::min((n + 31) / 32, (148 * 16 + D.Rg - 1) / D.Rg)), D.Rg), 256, 0, s>>>(D, mode); }
     { Timed t(ctx, TM_TENDENCY, s); k_tendency_eps<<<D.Rg, 1024, 0, s>>>(D, mode); }
     CU(cudaGetLastError());
     return POC_OK;
@@ -570,7 +602,7 @@ static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
 static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cells_done, bool report, cudaEvent_t after_draw = nullptr,
                          int end_tick = 0) {
     if (!cells_done) { int rc = launch_cells(ctx, D, s, 0); if (rc) return rc; }
-    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, 1024, 0, s>>>(D); }
+    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, ctx->draw_threads, 0, s>>>(D); }
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);
     if (rc) return rc;
@@ -756,6 +788,22 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
                                sizeof(double) * (size_t)n_ticks * POC_N_REPORTERS, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
+    return POC_OK;
+}
+
+int poc_report(poc_ctx *ctx, double *out /* [R][POC_N_REPORTERS] */) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (!out) return fail(ctx, POC_ERR_ARG, "poc_report: out is NULL");
+    int rep0 = 0;
+    // the row index lives in the tick state of group 0; write row 0 without touching the tick
+    CU(cudaMemcpyAsync(&ctx->d_ti[0].rep, &rep0, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    { Timed t(ctx, TM_OTHER); k_report<<<d.R, 512, 0, ctx->stream>>>(d, 0); }
+    CU(cudaGetLastError());
+    for (int r = 0; r < d.R; r++)
+        CU(cudaMemcpyAsync(out + (size_t)r * POC_N_REPORTERS, d.reporters + (size_t)r * d.Tcap * POC_N_REPORTERS,
+                           sizeof(double) * POC_N_REPORTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return POC_OK;
 }
 

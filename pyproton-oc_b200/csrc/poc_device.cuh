@@ -83,6 +83,7 @@ struct DevCtx {
     long long *layer_tot;           // [R][8] directed entries per non-criminal layer over alive agents (tot_*_link)
     // cells
     int32_t *cell_members;          // [R][Ncap] ascending slot inside each cell
+    int2 *pw_leaf; double *pw_sum; int pw_cap;   // [R][pw_cap] pieces of the pairwise sums in k_tendency_eps
     int32_t *cell_off;              // [R][POC_MAX_CELLS+1]
     int32_t *cell_strict;           // [R][POC_MAX_CELLS] counts with age_from < age (Q8)
     double *cdf;                    // [R][Ncap]

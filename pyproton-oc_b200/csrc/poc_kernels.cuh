@@ -283,88 +283,136 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
 }
 
 // ============================================================================ A1 criminal tendency
-// Person.update_criminal_tendency, entities.py:337-367 (quirks Q2, Q3 kept).  One thread per agent.
-__global__ void k_tendency_pre(DevCtx C, int mode) {
-    int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+// Person.update_criminal_tendency, entities.py:337-367 (quirks Q2, Q3 kept).
+// Eight lanes share one agent: the row is read coalesced and the five neighbour counts (integers, so the
+// order of the partial sums does not matter) are combined with three shuffles.
+// The grid is a few blocks per replica striding over the agents, so that the eleven launches a year that
+// only find out it is not a yearly tick cost one small wave.
+__global__ void __launch_bounds__(256) k_tendency_pre(DevCtx C, int mode) {
+    int r = C.r0 + blockIdx.y, sub = threadIdx.x & 7;
     if (mode == 2 && !is_yearly(C, C.params[r])) return;
-    if (a >= C.n_agents[r]) return;
-    size_t o = (size_t)r * C.Ncap + a;
-    uint32_t x = C.attr[o];
-    if (!(x & F_ALIVE)) return;
     const poc_params &P = C.params[r];
-    int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, cell = -1;
-    for (int k = 0; k < P.n_cells; k++)
-        if (P.cell_male[k] == male && P.cell_age_from[k] <= age && age <= P.cell_age_to[k]) { cell = k; break; }
-    if (cell < 0) return;
     Graph g = graph_of(C, r);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap);
-    double t = P.cell_c[cell];
-    t *= (attr_job(x) == 1) ? 1.30 : 1.0;
-    t *= (attr_edu(x) >= 2) ? 0.94 : 1.0;
-    t *= (C.propensity[o] > P.propensity_threshold) ? 1.97 : 1.0;
-    t *= 1.62;
-    int fam = 0, famc = 0, nf = 0, np = 0, pc = 0;
-    for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
-        uint32_t ent = g.u_ent[e];
-        uint32_t m = ENT_MASK(ent);
-        int f = __popc(m & (MB_SIB | MB_OFF | MB_PARTNER));
-        bool crim = false;
-        if (f || (m & MB_PROF)) crim = ncr[ENT_COL(ent)] > 0;
-        fam += f; if (crim) famc += f;
-        if (m & MB_FRIEND) nf++;
-        if (m & MB_PROF) { np++; if (crim) pc++; }
+    int n = C.n_agents[r];
+    for (int a0 = blockIdx.x * 32; a0 < n; a0 += gridDim.x * 32) {   // block-uniform trip count
+        int a = a0 + (threadIdx.x >> 3);
+        size_t o = (size_t)r * C.Ncap + a;
+        uint32_t x = (a < n) ? C.attr[o] : 0u;
+        bool live = (x & F_ALIVE) != 0;
+        int fam = 0, famc = 0, nf = 0, np = 0, pc = 0;
+        int e0 = live ? g.u_rowptr[a] : 0, e1 = live ? g.u_rowptr[a + 1] : 0;
+        for (int e = e0 + sub; e < e1; e += 8) {
+            uint32_t ent = g.u_ent[e];
+            uint32_t m = ENT_MASK(ent);
+            int f = __popc(m & (MB_SIB | MB_OFF | MB_PARTNER));
+            bool crim = false;
+            if (f || (m & MB_PROF)) crim = ncr[ENT_COL(ent)] > 0;
+            fam += f; if (crim) famc += f;
+            if (m & MB_FRIEND) nf++;
+            if (m & MB_PROF) { np++; if (crim) pc++; }
+        }
+#pragma unroll
+        for (int s = 1; s < 8; s <<= 1) {
+            fam += __shfl_xor_sync(FULL_MASK, fam, s); famc += __shfl_xor_sync(FULL_MASK, famc, s);
+            nf += __shfl_xor_sync(FULL_MASK, nf, s); np += __shfl_xor_sync(FULL_MASK, np, s); pc += __shfl_xor_sync(FULL_MASK, pc, s);
+        }
+        if (!live || sub) continue;
+        int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, cell = -1;
+        for (int k = 0; k < P.n_cells; k++)
+            if (P.cell_male[k] == male && P.cell_age_from[k] <= age && age <= P.cell_age_to[k]) { cell = k; break; }
+        if (cell < 0) continue;
+        double t = P.cell_c[cell];
+        t *= (attr_job(x) == 1) ? 1.30 : 1.0;
+        t *= (attr_edu(x) >= 2) ? 0.94 : 1.0;
+        t *= (C.propensity[o] > P.propensity_threshold) ? 1.97 : 1.0;
+        t *= 1.62;
+        t *= (fam > 0 && ((double)famc / (double)fam) > 0.5) ? 1.45 : 1.0;
+        bool neigh = nf > 0;
+        if (!neigh && np > 0) neigh = ((double)pc / (double)(nf + np)) > 0.5;
+        t *= neigh ? 1.81 : 1.0;
+        t *= (x & F_OC) ? 4.50 : 1.0;
+        C.tendency[o] = t;
     }
-    t *= (fam > 0 && ((double)famc / (double)fam) > 0.5) ? 1.45 : 1.0;
-    bool neigh = nf > 0;
-    if (!neigh && np > 0) neigh = ((double)pc / (double)(nf + np)) > 0.5;
-    t *= neigh ? 1.81 : 1.0;
-    t *= (x & F_OC) ? 4.50 : 1.0;
-    C.tendency[o] = t;
 }
 
-// numpy's pairwise add.reduce over tend[idx[0..n)] (what np.mean uses at model.py:1182)
-__device__ double pw_sum(const double *t, const int *idx, int n) {
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; i++) r += t[idx[i]];
-        return r;
-    } else if (n <= 128) {
-        double q[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = t[idx[j]];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) q[j] += t[idx[i + j]];
-        }
-        double res = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-        for (; i < n; i++) res += t[idx[i]];
-        return res;
-    }
+// numpy's pairwise add.reduce over tend[idx[0..n)] (what np.mean uses at model.py:1182) splits the range in halves
+// (left half rounded down to a multiple of 8) until a piece has <= 128 elements, sums each piece with eight strided
+// accumulators, and adds the pieces up the same tree.  The pieces are independent, so the tree is walked three
+// times: pw_split lists the pieces, eight lanes per piece sum them, pw_combine adds the sums in tree order.
+__device__ void pw_split(int start, int n, int2 *leaf, int &cur) {
+    if (n <= 128) { leaf[cur++] = make_int2(start, n); return; }
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return pw_sum(t, idx, n2) + pw_sum(t, idx + n2, n - n2);
+    pw_split(start, n2, leaf, cur);
+    pw_split(start + n2, n - n2, leaf, cur);
+}
+__device__ double pw_combine(int n, const double *sum, int &cur) {
+    if (n <= 128) return sum[cur++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    double l = pw_combine(n2, sum, cur);
+    double h = pw_combine(n - n2, sum, cur);
+    return l + h;
+}
+// one piece (n <= 128) by the eight lanes of a group; the result is valid in every lane of the group
+__device__ __forceinline__ double pw_piece8(const double *t, const int *idx, int n, int sub) {
+    // every lane of the warp runs the shuffles (groups with different n share a warp)
+    int full = (n >= 8) ? n - (n % 8) : 0;
+    double q = 0.0;
+    if (full) {
+        q = t[idx[sub]];
+        for (int i = 8; i < full; i += 8) q += t[idx[i + sub]];
+    }
+    // ((q0+q1)+(q2+q3))+((q4+q5)+(q6+q7)): each level adds two operands, so the exchange order within a pair is free
+    q += __shfl_xor_sync(FULL_MASK, q, 1);
+    q += __shfl_xor_sync(FULL_MASK, q, 2);
+    q += __shfl_xor_sync(FULL_MASK, q, 4);
+    if (!full) q = 0.0;                             // n < 8: plain left-to-right sum from 0.0
+    for (int i = full; i < n; i++) q += t[idx[i]];
+    return q;
 }
 
-// epsilon re-centring per cell, model.py:1180-1184.  One block per replica, one thread per cell for the
-// (order-defined) mean, then all threads add epsilon.
+// epsilon re-centring per cell, model.py:1180-1184.  One block per replica.
 __global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C, int mode) {
     int r = C.r0 + blockIdx.x, tid = threadIdx.x;
     const poc_params &P = C.params[r];
     if (mode == 2 && !is_yearly(C, P)) return;
     __shared__ double eps[POC_MAX_CELLS];
-    __shared__ int off[POC_MAX_CELLS + 1];
+    __shared__ int off[POC_MAX_CELLS + 1], lbase[POC_MAX_CELLS + 1];
     const int32_t *members = RP(C.cell_members, r, C.Ncap);
     double *tend = RP(C.tendency, r, C.Ncap);
-    if (tid <= P.n_cells) off[tid] = RP(C.cell_off, r, POC_MAX_CELLS + 1)[tid];
+    int2 *leaf = RP(C.pw_leaf, r, C.pw_cap);
+    double *lsum = RP(C.pw_sum, r, C.pw_cap);
+    int nc = P.n_cells;
+    if (tid <= nc) off[tid] = RP(C.cell_off, r, POC_MAX_CELLS + 1)[tid];
     __syncthreads();
-    // spread the per-cell chains over different warps
-    if ((tid & 31) == 0 && (tid >> 5) < P.n_cells) {
-        int k = tid >> 5, m = off[k + 1] - off[k];
-        eps[k] = (m > 0) ? P.cell_c[k] - pw_sum(tend, members + off[k], m) / (double)m : 0.0;
+    if (tid == 0) {  // a cell of m members has at most m / 64 + 1 pieces
+        int s = 0;
+        for (int k = 0; k < nc; k++) { lbase[k] = s; s += (off[k + 1] - off[k]) / 64 + 1; }
+        lbase[nc] = s;
     }
     __syncthreads();
-    int total = off[P.n_cells];
+    if (tid < nc) {
+        int cur = lbase[tid], m = off[tid + 1] - off[tid];
+        if (m > 0) pw_split(off[tid], m, leaf, cur);
+        for (; cur < lbase[tid + 1]; cur++) leaf[cur] = make_int2(0, 0);
+    }
+    __syncthreads();
+    int nl = lbase[nc], sub = tid & 7;
+    for (int j0 = 0; j0 < nl; j0 += blockDim.x >> 3) {   // warp-uniform trip count: the shuffles stay convergent
+        int j = j0 + (tid >> 3);
+        int2 lf = (j < nl) ? leaf[j] : make_int2(0, 0);
+        double s = pw_piece8(tend, members + lf.x, lf.y, sub);
+        if (j < nl && sub == 0) lsum[j] = s;
+    }
+    __syncthreads();
+    if (tid < nc) {
+        int cur = lbase[tid], m = off[tid + 1] - off[tid];
+        eps[tid] = (m > 0) ? P.cell_c[tid] - pw_combine(m, lsum, cur) / (double)m : 0.0;
+    }
+    __syncthreads();
+    int total = off[nc];
     for (int i = tid; i < total; i += blockDim.x) {
         int k = 0;
         while (i >= off[k + 1]) k++;

@@ -223,6 +223,12 @@ class CrimeEngine:
                                       rep.ctypes.data if rep is not None else None))
         return rep
 
+    def report(self) -> np.ndarray:
+        """calculate_fast_reporters for the current device state: [R, len(REPORTER_NAMES)]."""
+        out = np.zeros((self.R, N_REPORTERS), np.float64)
+        self._ck(self.L.poc_report(self.h, out.ctypes.data))
+        return out
+
     def counters(self):
         cn = np.zeros((self.R, _cabi.CN_COUNT), np.int32)
         ed = np.zeros(self.R, np.uint64)

@@ -531,8 +531,24 @@ class ProtonOC:
     def calculate_arrest_rate(self) -> None:
         self.arrest_rate = self.number_arrests_per_year / self.ticks_per_year / self.number_crimes_yearly_per10k / 10000 * self.initial_agents
 
-    def calculate_fast_reporters(self) -> None:
-        """model.py:1687-1735 from the downloaded columns."""
+    _FLOAT_REPORTERS = {"criminal_tendency_mean", "criminal_tencency_sd", "crime_multiplier", "age_mean", "age_sd",
+                        "education_level_mean", "education_level_sd", "num_crime_committed_mean",
+                        "num_crime_committed_sd"}
+    _DEVICE_ONLY = {"tick", "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick",
+                    "error_code", "crime_multiplier", "number_crimes", "crime_size_fails", "facilitator_crimes",
+                    "facilitator_fails", "big_crime_from_small_fish", "number_offspring_recruited_this_tick",
+                    "people_jailed", "number_protected_recruited_this_tick", "number_law_interventions_this_tick"}
+
+    def calculate_fast_reporters(self, from_device: bool = True) -> None:
+        """model.py:1687-1735.  With the state on the device the indicators come from the reporter kernel
+        (poc_report); from_device=False recomputes them on the host from the downloaded columns."""
+        if from_device and self._engine is not None and not self._dirty:
+            row = self._engine.report()[0]
+            for name, v in zip(REPORTER_NAMES, row):
+                if name not in self._DEVICE_ONLY:   # the cumulative counters are kept by commit_crimes() here
+                    setattr(self, name, float(v) if name in self._FLOAT_REPORTERS else int(v))
+            self.number_jobs = self.employed
+            return
         self._pull()
         st = self._st
         alive = st["alive"].astype(bool)

@@ -131,3 +131,54 @@ def test_synthetic_state_is_well_formed():
     S = O.OracleState(st)
     mult, totals = S.run_ticks(O.make_params({}), 1, 13, 5, 0.0)
     assert totals[0] > 0 and mult > 0
+
+
+def test_person_api_builds_the_same_state_as_the_fixture_helper():
+    """The Person link makers (entities.py:133-224 mirror) edit the host-side multiplex net; the resulting upload
+    state equals the one tests/util.py builds directly for the reference's micro net (test_protonoc.py:577-625).
+    Pure host logic: no engine is created before the first hot-path call."""
+    import pyproton_oc_b200 as P
+    import util as U
+    model = P.ProtonOC(seed=2)
+    for i in range(18):
+        a = P.Person(model)
+        model.schedule.add(a)
+        a.gender_is_male = i % 2 == 0
+        a.age = i * 149 % 45 + 10
+        a.education_level = i * 149 % 4
+        a.criminal_tendency = i * 149 % 100 / 100
+        a.wealth_level = i * 149 % 4
+        a.job_level = i * 149 % 4
+        a.propensity = i * 149 % 100 / 100
+    ag = model.schedule.agents
+    for x, y in [(0, 1), (7, 8)]:
+        ag[x].make_partner_link(ag[y])
+    for x, y in [(0, 2), (6, 5), (8, 9), (13, 15)]:
+        ag[x].make_friendship_link(ag[y])
+    for x, y in [(0, 3), (10, 9), (10, 11), (11, 12), (12, 13), (12, 14), (12, 16), (14, 15)]:
+        ag[x].make_professional_link(ag[y])
+    for x, y in [(0, 4), (10, 13)]:
+        ag[x].make_school_link(ag[y])
+    ag[0].add_criminal_link(ag[5])
+    ag[0].num_co_offenses[ag[5]] = 5
+    ag[5].num_co_offenses[ag[0]] = 5
+    ag[5].make_parent_offsprings_link(ag[0])
+    ag[7].make_parent_offsprings_link(ag[9])
+    ag[14].make_household_link([ag[17]])
+    ag[16].make_household_link([ag[12]])
+    ag[16].make_household_link([ag[17]])
+    ag[5].oc_member = True
+    ag[17].oc_member = True
+    ag[9].facilitator = True
+    ag[3].facilitator = True
+    assert model._engine is None
+    got, want = model.state_dict(), U.micro_net_state()
+    for k in ["male", "age", "education_level", "wealth_level", "job_level", "criminal_tendency", "propensity",
+              "oc_member", "facilitator", "alive"]:
+        assert np.array_equal(np.asarray(got[k]).astype(np.float64), np.asarray(want[k]).astype(np.float64)), k
+    for li in range(9):
+        assert np.array_equal(got["rowptr_%d" % li], want["rowptr_%d" % li]), li
+        assert np.array_equal(got["col_%d" % li], want["col_%d" % li]), li
+    assert np.array_equal(got["co_off"], want["co_off"])
+    # the reference's parent link is one-directional offspring + reverse parent (entities.py:206-215)
+    assert ag[5].neighbors["offspring"] == {ag[0]} and ag[0].neighbors["parent"] == {ag[5]}
