@@ -245,6 +245,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     cudaFuncSetAttribute(k_embeddedness<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(1024, N));
     cudaFuncSetAttribute(k_embeddedness<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(128, N));
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
+    cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaDeviceSetLimit(cudaLimitStackSize, 2048);  // pw_sum recursion
     CU(cudaStreamSynchronize(ctx->stream));
@@ -544,7 +545,7 @@ static int launch_cells(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int yearl
 static int launch_tendency(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mode) {
     int n = max_n(ctx);
     if (!n) return POC_OK;
-    { Timed t(ctx, TM_TENDENCY, s); k_tendency_pre<<<dim3(std::max(1, std::min((n + 31) / 32, (148 * 16 + D.Rg - 1) / D.Rg)), D.Rg), 256, 0, s>>>(D, mode); }
+    { Timed t(ctx, TM_TENDENCY, s); k_tendency_pre<<<dim3(std::max(1, std::min((n + 127) / 128, (148 * 16 + D.Rg - 1) / D.Rg)), D.Rg), 256, 0, s>>>(D, mode); }
     { Timed t(ctx, TM_TENDENCY, s); k_tendency_eps<<<D.Rg, 1024, 0, s>>>(D, mode); }
     CU(cudaGetLastError());
     return POC_OK;
@@ -602,7 +603,13 @@ static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
 static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cells_done, bool report, cudaEvent_t after_draw = nullptr,
                          int end_tick = 0) {
     if (!cells_done) { int rc = launch_cells(ctx, D, s, 0); if (rc) return rc; }
-    { Timed t(ctx, TM_DRAW, s); k_draw<<<D.Rg, ctx->draw_threads, 0, s>>>(D); }
+    {
+        // weights of one replica in shared memory when they fit (k_draw falls back to the global cdf array otherwise)
+        int nd = max_n(ctx);
+        if ((size_t)nd * sizeof(double) > 160 * 1024) nd = 0;
+        Timed t(ctx, TM_DRAW, s);
+        k_draw<<<D.Rg, ctx->draw_threads, (size_t)nd * sizeof(double), s>>>(D, nd);
+    }
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);
     if (rc) return rc;

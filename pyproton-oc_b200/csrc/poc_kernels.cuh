@@ -295,29 +295,60 @@ __global__ void __launch_bounds__(256) k_tendency_pre(DevCtx C, int mode) {
     Graph g = graph_of(C, r);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap);
     int n = C.n_agents[r];
-    for (int a0 = blockIdx.x * 32; a0 < n; a0 += gridDim.x * 32) {   // block-uniform trip count
-        int a = a0 + (threadIdx.x >> 3);
-        size_t o = (size_t)r * C.Ncap + a;
-        uint32_t x = (a < n) ? C.attr[o] : 0u;
-        bool live = (x & F_ALIVE) != 0;
-        int fam = 0, famc = 0, nf = 0, np = 0, pc = 0;
-        int e0 = live ? g.u_rowptr[a] : 0, e1 = live ? g.u_rowptr[a + 1] : 0;
-        for (int e = e0 + sub; e < e1; e += 8) {
-            uint32_t ent = g.u_ent[e];
-            uint32_t m = ENT_MASK(ent);
-            int f = __popc(m & (MB_SIB | MB_OFF | MB_PARTNER));
-            bool crim = false;
-            if (f || (m & MB_PROF)) crim = ncr[ENT_COL(ent)] > 0;
-            fam += f; if (crim) famc += f;
-            if (m & MB_FRIEND) nf++;
-            if (m & MB_PROF) { np++; if (crim) pc++; }
+    // four agents per lane group and trip, so that four chains of dependent loads (row bounds -> entry ->
+    // neighbour's crime count) are in flight per lane
+    for (int a0 = blockIdx.x * 128; a0 < n; a0 += gridDim.x * 128) {   // block-uniform trip count
+        int av[4], e0[4], e1[4], fam4[4], famc4[4], nf4[4], np4[4], pc4[4];
+        uint32_t xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            av[q] = a0 + q * 32 + (threadIdx.x >> 3);
+            bool in = av[q] < n;
+            xv[q] = in ? C.attr[(size_t)r * C.Ncap + av[q]] : 0u;
+            e0[q] = in ? g.u_rowptr[av[q]] + sub : 0; e1[q] = in ? g.u_rowptr[av[q] + 1] : 0;
+            fam4[q] = famc4[q] = nf4[q] = np4[q] = pc4[q] = 0;
         }
 #pragma unroll
-        for (int s = 1; s < 8; s <<= 1) {
-            fam += __shfl_xor_sync(FULL_MASK, fam, s); famc += __shfl_xor_sync(FULL_MASK, famc, s);
-            nf += __shfl_xor_sync(FULL_MASK, nf, s); np += __shfl_xor_sync(FULL_MASK, np, s); pc += __shfl_xor_sync(FULL_MASK, pc, s);
+        for (int q = 0; q < 4; q++) if (!(xv[q] & F_ALIVE)) e1[q] = 0;
+        while (e0[0] < e1[0] || e0[1] < e1[1] || e0[2] < e1[2] || e0[3] < e1[3]) {
+            uint32_t ent[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) ent[q] = (e0[q] < e1[q]) ? g.u_ent[e0[q]] : 0u;
+            int nc4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t m = ENT_MASK(ent[q]);
+                nc4[q] = (m & (MB_SIB | MB_OFF | MB_PARTNER | MB_PROF)) ? ncr[ENT_COL(ent[q])] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t m = ENT_MASK(ent[q]);   // a padding entry (0) has an empty mask
+                int f = __popc(m & (MB_SIB | MB_OFF | MB_PARTNER));
+                bool crim = nc4[q] > 0;
+                fam4[q] += f; if (crim) famc4[q] += f;
+                if (m & MB_FRIEND) nf4[q]++;
+                if (m & MB_PROF) { np4[q]++; if (crim) pc4[q]++; }
+                e0[q] += 8;
+            }
         }
-        if (!live || sub) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) {
+                fam4[q] += __shfl_xor_sync(FULL_MASK, fam4[q], s); famc4[q] += __shfl_xor_sync(FULL_MASK, famc4[q], s);
+                nf4[q] += __shfl_xor_sync(FULL_MASK, nf4[q], s); np4[q] += __shfl_xor_sync(FULL_MASK, np4[q], s);
+                pc4[q] += __shfl_xor_sync(FULL_MASK, pc4[q], s);
+            }
+        }
+        // lane q of the group finishes agent q
+        if (sub >= 4) continue;
+        int a = a0 + sub * 32 + (threadIdx.x >> 3);
+        int fam = 0, famc = 0, nf = 0, np = 0, pc = 0;
+        uint32_t x = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (sub == q) { fam = fam4[q]; famc = famc4[q]; nf = nf4[q]; np = np4[q]; pc = pc4[q]; x = xv[q]; }
+        if (!(x & F_ALIVE)) continue;
+        size_t o = (size_t)r * C.Ncap + a;
         int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, cell = -1;
         for (int k = 0; k < P.n_cells; k++)
             if (P.cell_male[k] == male && P.cell_age_from[k] <= age && age <= P.cell_age_to[k]) { cell = k; break; }
@@ -424,14 +455,16 @@ __global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C, int mode) {
 // model.py:1427-1440 + extra.py:102-149.  One block per replica.  The CDF is built exactly as
 // weighted_n_of + Generator.choice build it: optional min-shift, left-to-right sum, p/sum, sequential
 // cumsum, divide by the last element; one lane per cell runs the two order-defined chains.
-__global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
+__global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
+    extern __shared__ double wt_sm[];
     int tick = C.ti[C.grp].tick;
     int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     int nc = P.n_cells;
     __shared__ int off[POC_MAX_CELLS + 1], ncr[POC_MAX_CELLS], coff[POC_MAX_CELLS + 1], nz[POC_MAX_CELLS];
     __shared__ double mn[POC_MAX_CELLS], last[POC_MAX_CELLS];
-    __shared__ int neg[POC_MAX_CELLS];
+    __shared__ int neg[POC_MAX_CELLS], nzc[POC_MAX_CELLS];
+    __shared__ double s_sum[POC_MAX_CELLS];
     const int32_t *members = RP(C.cell_members, r, C.Ncap);
     const double *tend = RP(C.tendency, r, C.Ncap);
     double *cdf = RP(C.cdf, r, C.Ncap);
@@ -461,47 +494,106 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
         C.n_arrested[r] = 0;
     }
     // stage weights cell-ordered, and per-cell min / any-negative (one warp per cell, round robin)
+    // the cell-ordered weights live in shared memory when the population fits (every pass below is then on chip and
+    // the serial chains cost one LDS + DADD per element); larger populations work in the global cdf array
     int total = off[nc];
+    const bool fit = total <= smem_doubles;
+    double *wt = fit ? wt_sm : cdf;
 #pragma unroll 4
-    for (int i = tid; i < total; i += blockDim.x) cdf[i] = tend[members[i]];  // 4 independent gathers in flight
+    for (int i = tid; i < total; i += blockDim.x) wt[i] = tend[members[i]];  // 4 independent gathers in flight
     __syncthreads();
     for (int k = w; k < nc; k += nw) {
         double m = INFINITY;
         bool ng = false;
-        for (int i = off[k] + lane; i < off[k + 1]; i += 32) { double v = cdf[i]; m = fmin(m, v); ng |= (v < 0.0); }
+        for (int i = off[k] + lane; i < off[k + 1]; i += 32) { double v = wt[i]; m = fmin(m, v); ng |= (v < 0.0); }
         for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL_MASK, m, o));
         ng = __any_sync(FULL_MASK, ng);
         if (lane == 0) { mn[k] = m; neg[k] = ng; }
     }
     __syncthreads();
-    // the two order-defined chains (sum, then cumulative sum of p/sum): one warp per cell, see warp_chain32
-    for (int k = w; k < nc; k += nw) {
-        if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
-        int b = off[k], e = off[k + 1];
-        double shift = neg[k] ? mn[k] : 0.0, sump = 0.0;
-        int nzz = 0;
-        for (int base = b; base < e; base += 32) {
-            int i = base + lane;
-            double p = 0.0;
-            if (i < e) { p = cdf[i]; if (neg[k]) { p = p - shift; cdf[i] = p; } }
-            nzz += __popc(__ballot_sync(FULL_MASK, p != 0.0));
-            warp_chain32(p, sump);
+    if (fit) {
+        // The two order-defined chains (sum, then cumulative sum of p/sum) are serial within a cell and independent
+        // across cells: lane k of warp 0 walks cell k in shared memory; shift, count, divisions stay parallel.
+        for (int k = w; k < nc; k += nw) {
+            if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
+            int cnt = 0;
+            for (int base = off[k]; base < off[k + 1]; base += 32) {
+                int i = base + lane;
+                double p = 0.0;
+                if (i < off[k + 1]) { p = wt_sm[i]; if (neg[k]) { p = p - mn[k]; wt_sm[i] = p; } }
+                cnt += __popc(__ballot_sync(FULL_MASK, p != 0.0));
+            }
+            if (lane == 0) nzc[k] = cnt;
         }
-        double acc = 0.0;
-        if (sump != 0.0)
+        __syncthreads();
+        bool act = lane < nc && ncr[lane] > 0;
+        int cb = act ? off[lane] : 0, len = act ? off[lane + 1] - off[lane] : 0, maxlen = len;
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL_MASK, maxlen, o));
+        // (the next eight values are fetched from shared memory while the current eight go down the DADD chain)
+        if (w == 0) {
+            const double *src = wt_sm + cb;
+            double acc = 0.0, x[8], nx[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) nx[q] = (q < len) ? src[q] : 0.0;
+            for (int j = 0; j < maxlen; j += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = (j + 8 + q < len) ? src[j + 8 + q] : 0.0; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (j + q < len) acc = acc + x[q];
+            }
+            s_sum[lane] = acc;
+        }
+        __syncthreads();
+        for (int k = w; k < nc; k += nw) {
+            if (ncr[k] == 0 || s_sum[k] == 0.0) continue;
+            double s = s_sum[k];
+            for (int i = off[k] + lane; i < off[k + 1]; i += 32) wt_sm[i] = wt_sm[i] / s;
+        }
+        __syncthreads();
+        if (w == 0) {
+            double acc = 0.0;
+            if (act && s_sum[lane] == 0.0) len = 0;
+            double *src = wt_sm + cb, x[8], nx[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) nx[q] = (q < len) ? src[q] : 0.0;
+            for (int j = 0; j < maxlen; j += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = (j + 8 + q < len) ? src[j + 8 + q] : 0.0; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (j + q < len) { acc = acc + x[q]; src[j + q] = acc; }
+            }
+            if (act) { nz[lane] = (s_sum[lane] == 0.0) ? 0 : nzc[lane]; last[lane] = acc; }
+        }
+    } else {
+        // the two order-defined chains (sum, then cumulative sum of p/sum): one warp per cell, see warp_chain32
+        for (int k = w; k < nc; k += nw) {
+            if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
+            int b = off[k], e = off[k + 1];
+            double shift = neg[k] ? mn[k] : 0.0, sump = 0.0;
+            int nzz = 0;
             for (int base = b; base < e; base += 32) {
                 int i = base + lane;
-                double q = (i < e) ? cdf[i] / sump : 0.0;
-                double mine = warp_chain32(q, acc);
-                if (i < e) cdf[i] = mine;
+                double p = 0.0;
+                if (i < e) { p = cdf[i]; if (neg[k]) { p = p - shift; cdf[i] = p; } }
+                nzz += __popc(__ballot_sync(FULL_MASK, p != 0.0));
+                warp_chain32(p, sump);
             }
-        if (lane == 0) { nz[k] = (sump == 0.0) ? 0 : nzz; last[k] = acc; }
+            double acc = 0.0;
+            if (sump != 0.0)
+                for (int base = b; base < e; base += 32) {
+                    int i = base + lane;
+                    double q = (i < e) ? cdf[i] / sump : 0.0;
+                    double mine = warp_chain32(q, acc);
+                    if (i < e) cdf[i] = mine;
+                }
+            if (lane == 0) { nz[k] = (sump == 0.0) ? 0 : nzz; last[k] = acc; }
+        }
     }
     __syncthreads();
-    for (int i = tid; i < total; i += blockDim.x) {
-        int k = 0;
-        while (i >= off[k + 1]) k++;
-        if (ncr[k] > 0 && nz[k] > 0) cdf[i] = cdf[i] / last[k];
+    for (int k = w; k < nc; k += nw) {
+        if (!(ncr[k] > 0 && nz[k] > 0)) continue;
+        double l = last[k];
+        for (int i = off[k] + lane; i < off[k + 1]; i += 32) wt[i] = wt[i] / l;
     }
     __syncthreads();
     // the draws
@@ -524,7 +616,7 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C) {
             continue;
         }
         int m = off[k + 1] - off[k];
-        int ii = ss_right(cdf + off[k], m, u1);
+        int ii = ss_right(wt + off[k], m, u1);
         if (ii >= m) ii = m - 1;
         int init = members[off[k] + ii];
         int si = ss_right(P.size_cdf, P.n_sizes, u2);
