@@ -247,7 +247,6 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
-    cudaDeviceSetLimit(cudaLimitStackSize, 2048);  // pw_sum recursion
     CU(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return POC_OK;

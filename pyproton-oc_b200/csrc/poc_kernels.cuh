@@ -371,20 +371,35 @@ __global__ void __launch_bounds__(256) k_tendency_pre(DevCtx C, int mode) {
 // (left half rounded down to a multiple of 8) until a piece has <= 128 elements, sums each piece with eight strided
 // accumulators, and adds the pieces up the same tree.  The pieces are independent, so the tree is walked three
 // times: pw_split lists the pieces, eight lanes per piece sum them, pw_combine adds the sums in tree order.
+// (explicit stacks instead of recursion: the depth is log2(n / 64) + 1 <= 24)
 __device__ void pw_split(int start, int n, int2 *leaf, int &cur) {
-    if (n <= 128) { leaf[cur++] = make_int2(start, n); return; }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    pw_split(start, n2, leaf, cur);
-    pw_split(start + n2, n - n2, leaf, cur);
+    int ss[24], sn[24], sp = 0;
+    ss[0] = start; sn[0] = n; sp = 1;
+    while (sp) {
+        int s = ss[--sp], m = sn[sp];
+        while (m > 128) {                 // descend to the left, remember the right half
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            ss[sp] = s + n2; sn[sp] = m - n2; sp++;
+            m = n2;
+        }
+        leaf[cur++] = make_int2(s, m);
+    }
 }
 __device__ double pw_combine(int n, const double *sum, int &cur) {
-    if (n <= 128) return sum[cur++];
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    double l = pw_combine(n2, sum, cur);
-    double h = pw_combine(n - n2, sum, cur);
-    return l + h;
+    int fn[24], fs[24], sp = 0;          // frame: piece length, state (0 = nothing done, 1 = left done)
+    double fl[24], ret = 0.0;
+    fn[0] = n; fs[0] = 0; sp = 1;
+    while (sp) {
+        int m = fn[sp - 1];
+        if (m <= 128) { ret = sum[cur++]; sp--; continue; }
+        int n2 = m / 2;
+        n2 -= n2 % 8;
+        if (fs[sp - 1] == 0) { fs[sp - 1] = 1; fn[sp] = n2; fs[sp] = 0; sp++; }
+        else if (fs[sp - 1] == 1) { fl[sp - 1] = ret; fs[sp - 1] = 2; fn[sp] = m - n2; fs[sp] = 0; sp++; }
+        else { ret = fl[sp - 1] + ret; sp--; }
+    }
+    return ret;
 }
 // one piece (n <= 128) by the eight lanes of a group; the result is valid in every lane of the group
 __device__ __forceinline__ double pw_piece8(const double *t, const int *idx, int n, int sub) {
