@@ -161,9 +161,9 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     ctx->gx = (R >= 64) ? 32 : 64;
     // embeddedness: a chain of dependent gathers per evaluation, so large batches run one evaluation per warp
     // (about 24 resident per SM) and small ones one per block
-    // threads per evaluation: measured 32 / 64 / 128 / 256 / 512 / 1024 -> 1197+ / 1197 / 885 / 782 / 777 / 856 us per
-    // 128-replica tick and - / 371 / 276 / 242 / 224 / 219 us per single-replica tick (profiles/)
-    ctx->emb_g = (R < 8) ? 1024 : 512;
+    // threads per evaluation (one block each), measured us per tick at 1 / 128 / 512 replicas (profiles/README.md):
+    // 1024 -> 198 / - / -, 512 -> - / 688 / 2041, 256 -> - / 699 / 1914, 128 -> - / 806 / 1969, 64 -> - / 1055 / 2389
+    ctx->emb_g = (R < 8) ? 1024 : (R < 256 ? 512 : 256);
     if (const char *e = getenv("POC_EMB_G")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128 || g == 256 || g == 512 || g == 1024) ctx->emb_g = g; }  // experiments
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
     ctx->draw_threads = (R > 148) ? 256 : 1024;

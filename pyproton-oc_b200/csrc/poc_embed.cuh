@@ -125,7 +125,7 @@ __device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list
 }
 
 template <int G>
-__global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 1024 ? 2 : (G == 512 ? 3 : (G == 256 ? 6 : (G == 128 ? 10 : 16))))) k_embeddedness(DevCtx C, int parity) {
+__global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 1024 ? 2 : (G == 512 ? 4 : (G == 256 ? 8 : (G == 128 ? 16 : 16))))) k_embeddedness(DevCtx C, int parity) {
     // G == 32: eight warp-sized groups per 256-thread block; otherwise the block is the group
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GPB = (G == 32) ? 8 : 1, DCAP = EmbCfg<G>::DCAP, NW = G / 32;

@@ -275,6 +275,32 @@ def test_batched_replicas_equal_single_runs(P):
             assert np.array_equal(rep[r], wrep)
 
 
+@pytest.mark.parametrize("env", [{"POC_EMB_G": "128"}, {"POC_EMB_G": "256"}, {"POC_EMB_G": "512"}, {"POC_EMB_G": "1024"},
+                                 {"POC_DRAW_T": "256"}, {"POC_DRAW_T": "1024"}, {"POC_GROUPS": "2"}, {"POC_GRAPH": "0"}],
+                         ids=lambda e: "-".join("%s%s" % kv for kv in e.items()))
+def test_kernel_shapes_do_not_change_results(P, O, env, monkeypatch):
+    """The launch-shape knobs the library picks by batch size (threads per embeddedness evaluation, k_draw block
+    size, replica groups on streams, graph replay) are performance choices only: a 30-tick Philox run of two
+    replicas equals the oracle under each of them."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fx = U.load_fixture(U.GOLDEN + "/tick_n1000_s11_oc200_t3.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    keys, ticks = [5, 6], 30
+    with engine_for(P, [st, st], crim_headroom=60000) as E:
+        E.set_params(P.make_params(prm))
+        for r in range(2):
+            E.upload_state(r, st)
+        E.run_ticks(3, ticks, keys)
+        got = [E.download_state(r) for r in range(2)]
+        cn, _ = E.counters()
+    assert (cn[:, 9] == 0).all()
+    for r in range(2):
+        S = O.OracleState(st)
+        S.run_ticks(O.make_params(prm), 3, ticks, keys[r], 0.0)
+        assert_state_equal(got[r], S, what="replica %d under %s" % (r, env))
+
+
 # ------------------------------------------------------------------ BASELINE config 4: synthetic 100k agents
 def test_synthetic_100k_matches_oracle(P, O):
     """The reference cannot produce this size; parity here is kernel vs CPU restatement,
