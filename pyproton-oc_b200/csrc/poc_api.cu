@@ -40,6 +40,8 @@ struct poc_ctx {
     uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
     size_t stage_bytes = 0, stage_off[24] = {};
     cudaEvent_t stage_ev = nullptr; bool stage_busy = false;
+    int cells_threads = 1024;       // k_cells block size (its count table is n_cells x threads ints of shared memory)
+    int commit_threads = 1024;      // k_commit block size, same reasoning
     int draw_threads = 1024;        // k_draw block size: one block per SM is latency-bound, several need fewer registers per block
     int32_t *st_rowptr[POC_NUM_LAYERS] = {};
     int32_t *st_col = nullptr;      // all staged layers back to back
@@ -167,6 +169,10 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     if (const char *e = getenv("POC_EMB_G")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128 || g == 256 || g == 512 || g == 1024) ctx->emb_g = g; }  // experiments
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
     ctx->draw_threads = (R > 148) ? 256 : 1024;
+    ctx->commit_threads = (R > 148) ? 512 : 1024;
+    ctx->cells_threads = 1024;   // measured: 512 threads is no faster at 512 replicas (59.6 vs 52 us)
+    if (const char *e = getenv("POC_CELLS_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->cells_threads = t; }
+    if (const char *e = getenv("POC_COMMIT_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->commit_threads = t; }
     if (const char *e = getenv("POC_DRAW_T")) { int t = atoi(e); if (t == 256 || t == 384 || t == 512 || t == 1024) ctx->draw_threads = t; }
     ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : ctx->gx;
     int emb_slots = R * ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1);
@@ -536,7 +542,7 @@ int poc_end_tick(poc_ctx *ctx) {
 static int launch_cells(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int yearly, int begin = 0) {
     int nc = 1;
     for (auto &hp : ctx->h_params) nc = std::max(nc, (int)hp.n_cells);
-    { Timed t(ctx, TM_CELLS, s); k_cells<<<D.Rg, 1024, (size_t)nc * 1024 * sizeof(int), s>>>(D, yearly, begin); }
+    { Timed t(ctx, TM_CELLS, s); k_cells<<<D.Rg, ctx->cells_threads, (size_t)nc * ctx->cells_threads * sizeof(int), s>>>(D, yearly, begin); }
     CU(cudaGetLastError());
     return POC_OK;
 }
@@ -612,7 +618,7 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);
     if (rc) return rc;
-    { Timed t(ctx, TM_COMMIT, s); k_commit<<<D.Rg, 1024, 0, s>>>(D); }
+    { Timed t(ctx, TM_COMMIT, s); k_commit<<<D.Rg, ctx->commit_threads, 0, s>>>(D); }
     { Timed t(ctx, TM_ARREST, s); k_recruit_arrest<<<D.Rg, 256, 0, s>>>(D, end_tick); }
     // the reporter row of the tick is written after the end-of-tick bookkeeping (model.py:286-287)
     if (report) { Timed t(ctx, TM_OTHER, s); k_report<<<D.Rg, 512, 0, s>>>(D, end_tick == 2 ? 1 : 0); }

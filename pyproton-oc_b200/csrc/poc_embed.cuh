@@ -17,7 +17,7 @@
 #define EMB_SCALE 17179869184.0 /* 2^34 */
 #define DIST_INF 0x7ff0000000000000ull
 #define RCAP 4096  /* ball size up to which ranks fit the 12-bit fields of a staged edge */
-#define ECAP 16384 /* staged induced entries per evaluation (per-group scratch) */
+#define ECAP 65536 /* staged induced entries per evaluation (per-block global scratch, 256 KB) */
 #define MAX_RADIUS 16
 
 template <int G> struct EmbCfg;

@@ -805,7 +805,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     }
 }
 
-__global__ void __launch_bounds__(256) k_search(DevCtx C, int parity) {
+__global__ void __launch_bounds__(256, 8) k_search(DevCtx C, int parity) {
     int tick = C.ti[C.grp].tick, epoch = C.ti[C.grp].epoch;
     extern __shared__ unsigned smem_u[];
     int r = C.r0 + blockIdx.y;
@@ -1237,7 +1237,7 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
 
 // end_tick: 0 = arrests only; 1 = also the prisoner countdown of model.py:279-283 (k_end_tick fused);
 // 2 = also advance the replica group's device-side tick state once the last block of the launch is through
-__global__ void __launch_bounds__(256) k_recruit_arrest(DevCtx C, int end_tick) {
+__global__ void __launch_bounds__(256, 4) k_recruit_arrest(DevCtx C, int end_tick) {
     int tick = C.ti[C.grp].tick;
     int r = C.r0 + blockIdx.x;
     if (warp_id() == 0) recruit_arrest_warp(C, r, tick);
@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(256) k_recruit_arrest(DevCtx C, int end_tick) 
 // model.py:1687-1735, the columns the hot path feeds.  One block per replica.
 // mode 0/1: write the row (1: the tick state has already moved on); 2: write the row, then the last block moves the
 // replica group's tick state on; 3: only move the tick state on
-__global__ void __launch_bounds__(512) k_report(DevCtx C, int mode) {
+__global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     int t = C.ti[C.grp].rep - (mode == 1 ? 1 : 0);
     if (mode >= 2) {
         __shared__ int s_last;
