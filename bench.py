@@ -183,7 +183,7 @@ def main():
 
     def upload_all():
         for r in range(R):
-            E.upload_state(r, st_pin)
+            E.upload_state(r, st_pin, wait=False)     # queued; E.sync() / the run's own synchronisation wait for them
             E.set_crime_multiplier(mult, r)
 
     def barrier():

@@ -152,6 +152,9 @@ int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr
                      const int32_t *co_off_or_null);
 /* merge the eight non-criminal layers into the packed multiplex CSR the kernels traverse */
 int poc_build_graph(poc_ctx *ctx, int replica);
+/* the same without waiting: the uploads of the next replica queue up behind this one.  Caller-owned page-locked
+ * buffers must stay valid until poc_sync(), which also reports invalid input found by the deferred checks. */
+int poc_build_graph_async(poc_ctx *ctx, int replica);
 int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *cols);
 int poc_layer_entries(poc_ctx *ctx, int replica, int layer, int64_t *out);
 int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, int32_t *col, int32_t *co_off_or_null);

@@ -38,6 +38,8 @@ struct poc_ctx {
     // staging
     StageCols stage{};
     uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
+    uint8_t *stage_host2[2] = {nullptr, nullptr};          // upload mirrors, used alternately
+    cudaEvent_t stage_ev2[2] = {nullptr, nullptr}; bool stage_busy2[2] = {false, false}; int stage_next = 0;
     size_t stage_bytes = 0, stage_off[24] = {};
     cudaEvent_t stage_ev = nullptr; bool stage_busy = false;
     int cells_threads = 1024;       // k_cells block size (its count table is n_cells x threads ints of shared memory)
@@ -219,6 +221,10 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
         ctx->stage_bytes = o;
         DA(ctx->stage_dev, o);
         cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
+        for (int b = 0; b < 2; b++) {
+            cudaEventCreateWithFlags(&ctx->stage_ev2[b], cudaEventDisableTiming);
+            if (cudaHostAlloc((void **)&ctx->stage_host2[b], o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
+        }
         if (cudaHostAlloc((void **)&ctx->stage_host, o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
         k = 0;
 #define PT(f, T) s.f = (T *)(ctx->stage_dev + ctx->stage_off[k++]);
@@ -265,6 +271,7 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+    for (int b = 0; b < 2; b++) { if (ctx->stage_host2[b]) cudaFreeHost(ctx->stage_host2[b]); if (ctx->stage_ev2[b]) cudaEventDestroy(ctx->stage_ev2[b]); }
     for (auto &evx : ctx->ev) cudaEventDestroy(evx);
     for (auto &m : ctx->marker) cudaEventDestroy(m);
     for (int g = 0; g < ctx->ngroups; g++) cudaStreamDestroy(ctx->gstream[g]);
@@ -275,10 +282,10 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     return POC_OK;
 }
 
+static int read_err(poc_ctx *ctx, const char *what);
 int poc_sync(poc_ctx *ctx) {
     CHECK_CTX();
-    CU(cudaStreamSynchronize(ctx->stream));
-    return POC_OK;
+    return read_err(ctx, "poc_sync");  // also reports invalid input of uploads finished with poc_build_graph_async
 }
 
 int poc_set_timing(poc_ctx *ctx, int on) { CHECK_CTX(); ctx->timing = on != 0; return POC_OK; }
@@ -355,18 +362,20 @@ int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *c)
     if (!c || replica < 0 || replica >= ctx->d.R || n < 0 || n > ctx->d.Ncap) return fail(ctx, POC_ERR_ARG, "poc_upload_agents: bad argument");
     StageCols &s = ctx->stage;
     cudaStream_t st = ctx->stream;
-    // the columns are gathered in the pinned mirror of the staging block and go up in one copy; the mirror is free
-    // again once the previous upload's copy has completed
-    if (ctx->stage_busy) { CU(cudaEventSynchronize(ctx->stage_ev)); ctx->stage_busy = false; }
+    // the columns are gathered in a pinned mirror of the staging block and go up in one copy; two mirrors alternate,
+    // so the host packs the next replica while the device still consumes the previous one
+    int mb = ctx->stage_next; ctx->stage_next ^= 1;
+    if (ctx->stage_busy2[mb]) { CU(cudaEventSynchronize(ctx->stage_ev2[mb])); ctx->stage_busy2[mb] = false; }
+    uint8_t *mirror = ctx->stage_host2[mb];
     {
         size_t k = 0;
 #define UP(f, T) { if (!c->f && n) return fail(ctx, POC_ERR_ARG, "poc_upload_agents: column " #f " is NULL"); \
-                   if (n) memcpy(ctx->stage_host + ctx->stage_off[k], c->f, sizeof(T) * (size_t)n); k++; }
+                   if (n) memcpy(mirror + ctx->stage_off[k], c->f, sizeof(T) * (size_t)n); k++; }
         POC_STAGE_COLS(UP)
 #undef UP
     }
-    CU(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, ctx->stage_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(ctx->stage_ev, st)); ctx->stage_busy = true;
+    CU(cudaMemcpyAsync(ctx->stage_dev, mirror, ctx->stage_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ctx->stage_ev2[mb], st)); ctx->stage_busy2[mb] = true;
     CU(cudaMemcpyAsync(ctx->d.n_agents + replica, &n, sizeof(int), cudaMemcpyHostToDevice, st));
     ctx->h_nagents[replica] = n;
     if (n) k_pack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica, n, s, ctx->d_err);
@@ -409,7 +418,7 @@ int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr
     return POC_OK;  // asynchronous: the caller's buffers must stay valid until poc_build_graph returns
 }
 
-int poc_build_graph(poc_ctx *ctx, int replica) {
+static int build_graph(poc_ctx *ctx, int replica, bool wait) {
     CHECK_CTX();
     if (replica < 0 || replica >= ctx->d.R || ctx->st_replica != replica) return fail(ctx, POC_ERR_STATE, "poc_build_graph: upload the layers of this replica first");
     int all = (1 << POC_NUM_LAYERS) - 1;
@@ -436,8 +445,11 @@ int poc_build_graph(poc_ctx *ctx, int replica) {
     } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
     CU(cudaGetLastError());
     ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;
-    return read_err(ctx, "poc_build_graph");
+    return wait ? read_err(ctx, "poc_build_graph") : POC_OK;
 }
+
+int poc_build_graph(poc_ctx *ctx, int replica) { return build_graph(ctx, replica, true); }
+int poc_build_graph_async(poc_ctx *ctx, int replica) { return build_graph(ctx, replica, false); }
 
 int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *c) {
     CHECK_CTX();
@@ -577,8 +589,8 @@ int poc_crime_multiplier(poc_ctx *ctx, double *out) {
 int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
     CHECK_CTX();
     if (replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_set_crime_multiplier: bad replica");
+    // pageable source: staged before the call returns, no synchronisation needed
     CU(cudaMemcpyAsync(ctx->d.crime_mult + replica, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     return POC_OK;
 }
 

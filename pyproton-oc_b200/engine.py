@@ -58,6 +58,7 @@ class CrimeEngine:
         self.R, self.max_agents = n_replicas, max_agents
         self.n_agents = [0] * n_replicas
         self.device = device
+        self._keepalive = []   # host arrays of uploads queued with wait=False, released at sync()
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -82,6 +83,7 @@ class CrimeEngine:
 
     def sync(self):
         self._ck(self.L.poc_sync(self.h))
+        self._keepalive.clear()
 
     @staticmethod
     def capacity_for(states: Sequence[Dict[str, np.ndarray]], headroom_criminal: int = 0):
@@ -95,7 +97,8 @@ class CrimeEngine:
     def set_params(self, p: Params, replica: int = -1):
         self._ck(self.L.poc_set_params(self.h, replica, C.byref(p)))
 
-    def upload_state(self, replica: int, st: Dict[str, np.ndarray]):
+    def upload_state(self, replica: int, st: Dict[str, np.ndarray], wait: bool = True):
+        """wait=False queues the upload without synchronising (input errors then surface at sync())."""
         n = int(len(st["alive"]))
         cols, keep = AgentCols(), []
         for f, key in STATE_KEYS.items():
@@ -110,7 +113,11 @@ class CrimeEngine:
             keep += [rp, col, co]  # the uploads are asynchronous until poc_build_graph returns
             self._ck(self.L.poc_upload_layer(self.h, replica, l, rp.ctypes.data, col.ctypes.data if len(col) else None,
                                              co.ctypes.data if (co is not None and len(co)) else None))
-        self._ck(self.L.poc_build_graph(self.h, replica))
+        if wait:
+            self._ck(self.L.poc_build_graph(self.h, replica))
+        else:
+            self._ck(self.L.poc_build_graph_async(self.h, replica))
+            self._keepalive.append(keep)
 
     def download_agents(self, replica: int = 0) -> Dict[str, np.ndarray]:
         n = self.n_agents[replica]

@@ -89,7 +89,8 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
         with CrimeEngine(len(batch), n, stat, crim, device=device) as E:
             for r, (m, st) in enumerate(zip(models, states)):
                 E.set_params(m._params(), replica=r)
-                E.upload_state(r, st)
+                E.upload_state(r, st, wait=False)
+            E.sync()   # input errors of the queued uploads surface here
             rep = E.run_ticks(1, T, [m._philox_key for m in models], reporters=True)
             cn, _ = E.counters()
             if cn[:, 9].any():
