@@ -190,6 +190,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.u_rowptr, (size_t)R * (N + 1)); DA(d.u_ent, (size_t)R * d.ucap);
     DA(d.c_rowptr, (size_t)R * (N + 1)); DA(d.c_ent, (size_t)R * d.ccap);
     DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
+    DA(d.c_par, R);
     DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN);
@@ -202,6 +203,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.emb_list, 2 * RN); DA(d.n_emb, 2 * R); DA(d.emb_stamp, RN); DA(d.emb_val, RN);
     DA(d.group_off, (size_t)R * (d.Ccap + 1)); DA(d.group_mem, RM);
     DA(d.pairs, (size_t)R * d.Pcap); DA(d.pair_cnt, (size_t)R * d.Pcap); DA(d.n_pairs, R);
+    DA(d.pair_new_ex, (size_t)R * (d.Pcap + 1)); DA(d.ins_row, (size_t)R * d.Pcap);
+    DA(d.ins_rowid, (size_t)R * d.Pcap); DA(d.ins_before, (size_t)R * (d.Pcap + 1));
     DA(d.arrested, RM); DA(d.n_arrested, R); DA(d.aw, RM); DA(d.ap, RM); DA(d.acdf, RM);
     DA(d.rp_u_init, RC); DA(d.rp_u_size, RC); DA(d.rp_fac_pick, RC);
     DA(d.rp_u_arrest, RM); DA(d.rp_u_sentence, RM); DA(d.rp_arrest_idx, RM);
@@ -477,12 +480,17 @@ static int fetch_graph(poc_ctx *ctx, int replica, std::vector<int32_t> &urp, std
     int n = ctx->h_nagents[replica];
     DevCtx &d = ctx->d;
     urp.resize(n + 1); crp.resize(n + 1);
+    int par = 0;
+    CU(cudaMemcpyAsync(&par, d.c_par + replica, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int32_t *c_rowptr = par ? d.c_rowptr_tmp : d.c_rowptr;
+    const int2 *c_ent = par ? d.c_ent_tmp : d.c_ent;
     CU(cudaMemcpyAsync(urp.data(), d.u_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(crp.data(), d.c_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(crp.data(), c_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     uent.resize(urp[n]); cent.resize(crp[n]);
     if (urp[n]) CU(cudaMemcpyAsync(uent.data(), d.u_ent + (size_t)replica * d.ucap, sizeof(uint32_t) * urp[n], cudaMemcpyDeviceToHost, ctx->stream));
-    if (crp[n]) CU(cudaMemcpyAsync(cent.data(), d.c_ent + (size_t)replica * d.ccap, sizeof(int2) * crp[n], cudaMemcpyDeviceToHost, ctx->stream));
+    if (crp[n]) CU(cudaMemcpyAsync(cent.data(), c_ent + (size_t)replica * d.ccap, sizeof(int2) * crp[n], cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return POC_OK;
 }

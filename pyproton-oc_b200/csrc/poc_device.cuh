@@ -73,6 +73,11 @@ struct DevCtx {
     int32_t *u_rowptr; uint32_t *u_ent;
     int32_t *c_rowptr; int2 *c_ent;
     int32_t *c_rowptr_tmp; int2 *c_ent_tmp; int32_t *c_addlen;
+    int *c_par;                     // [R] which criminal CSR is current: 0 = c_rowptr/c_ent, 1 = the _tmp pair (k_commit
+                                    // writes the other one and flips this, so nothing is copied back)
+    int32_t *pair_new_ex;           // [R][Pcap+1] exclusive count of new links before each unique pair
+    int32_t *ins_row;               // [R][Pcap] index of the first unique pair of every row that receives pairs
+    int32_t *ins_rowid, *ins_before;  // [R][Pcap], [R][Pcap+1] that row's id / new links in the receiving rows before it
     // parameters / scalars
     poc_params *params;             // [R]
     double *crime_mult;             // [R]
@@ -208,7 +213,9 @@ struct Graph {
 __device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
     Graph g;
     g.u_rowptr = C.u_rowptr + (size_t)r * (C.Ncap + 1); g.u_ent = C.u_ent + (size_t)r * C.ucap;
-    g.c_rowptr = C.c_rowptr + (size_t)r * (C.Ncap + 1); g.c_ent = C.c_ent + (size_t)r * C.ccap;
+    int par = C.c_par[r];
+    g.c_rowptr = (par ? C.c_rowptr_tmp : C.c_rowptr) + (size_t)r * (C.Ncap + 1);
+    g.c_ent = (par ? C.c_ent_tmp : C.c_ent) + (size_t)r * C.ccap;
     return g;
 }
 

@@ -103,7 +103,7 @@ __global__ void k_pack_criminal(DevCtx C, int r, int n, const int32_t *rowptr, c
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a > n) return;
     RP(C.c_rowptr, r, C.Ncap + 1)[a] = rowptr[a];
-    if (a == n) return;
+    if (a == n) { C.c_par[r] = 0; return; }   // an upload always lands in the first of the two criminal CSR buffers
     int2 *ent = RP(C.c_ent, r, C.ccap);
     int prev = -1;
     for (int e = rowptr[a]; e < rowptr[a + 1]; e++) {
@@ -900,9 +900,12 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     __syncthreads();
     int np = s_np;
     if (np > C.Pcap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 12); return; }
-    int32_t *rp_new = RP(C.c_rowptr_tmp, r, C.Ncap + 1);
-    int2 *ent_new = RP(C.c_ent_tmp, r, C.ccap);
-    int32_t *addlen = RP(C.c_addlen, r, C.Ncap);
+    // the criminal CSR is double-buffered: read the current one (g), write the other, flip C.c_par[r] at the end
+    int par = C.c_par[r];
+    int32_t *rp_new = (par ? C.c_rowptr : C.c_rowptr_tmp) + (size_t)r * (C.Ncap + 1);
+    int2 *ent_new = (par ? C.c_ent : C.c_ent_tmp) + (size_t)r * C.ccap;
+    int32_t *pnew = RP(C.pair_new_ex, r, C.Pcap + 1), *ins = RP(C.ins_row, r, C.Pcap);
+    int32_t *ins_start = RP(C.c_addlen, r, C.Ncap);   // first old entry of every receiving row (at most n of them)
     if (np == 0) { if (tid == 0) C.n_pairs[r] = 0; return; }  // no multi-member group: criminal layer unchanged
     // ---- bitonic sort of the ordered pairs
     int np2 = 1;
@@ -940,68 +943,96 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     }
     int nu = carry;
     if (tid == 0) C.n_pairs[r] = nu;
-    // ---- resolve each unique pair against the old rows
-    for (int a = tid; a < n; a += blockDim.x) addlen[a] = 0;
-    __syncthreads();
+    // ---- resolve each unique pair against the old rows: final count, and whether the link is new
     for (int i = tid; i < nu; i += blockDim.x) {
         int a = (int)(pairs[i] >> 32), b = (int)(pairs[i] & 0xffffffffu);
         int cab = crim_find(g, a, b), cba = crim_find(g, b, a);
         int old = (cab >= 0 && cba >= 0) ? cab : 0;  // CANON: a half-present link is re-created with 0
-        pcnt[i] = old + pcnt[i];
-        atomicOr(&addlen[a], 0x40000000);          // row a has pairs: it must be merged, not just moved
-        if (cab < 0) atomicAdd(&addlen[a], 1);
+        pcnt[i] = (old + pcnt[i]) | (cab < 0 ? 0x40000000 : 0);
     }
     __syncthreads();
-    // ---- new row pointers
-    if (tid == 0) carry = 0;
+    // ---- rows that receive pairs (the unique pairs are sorted by row), and the number of new links before each pair
+    __shared__ int s_nins;
+    if (tid == 0) { carry = 0; s_nins = 0; }
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int a = base + tid, v = 0, tot;
-        if (a < n) v = (g.c_rowptr[a + 1] - g.c_rowptr[a]) + (addlen[a] & 0x3fffffff);
-        int ex = block_exscan(v, ws, &tot);
-        if (a < n) rp_new[a] = carry + ex;
+    for (int base = 0; base < nu; base += blockDim.x) {
+        int i = base + tid;
+        bool valid = i < nu;
+        int isnew = (valid && (pcnt[i] & 0x40000000)) ? 1 : 0;
+        bool head = valid && (i == 0 || (int)(pairs[i - 1] >> 32) != (int)(pairs[i] >> 32));
+        int tot, ex = block_exscan(isnew, ws, &tot);
+        if (valid) pnew[i] = carry + ex;
+        int toth, exh = block_exscan(head ? 1 : 0, ws, &toth);
+        if (head) { ins[s_nins + exh] = i; ins_start[s_nins + exh] = g.c_rowptr[(int)(pairs[i] >> 32)]; }
         __syncthreads();
-        if (tid == 0) carry += tot;
+        if (tid == 0) { carry += tot; s_nins += toth; }
         __syncthreads();
     }
-    if (tid == 0) { rp_new[n] = carry; if (carry > C.ccap) atomicExch(&cn[CN_ERROR], 13); }
+    int nins = s_nins, tot_add = carry;
+    if (tid == 0) pnew[nu] = tot_add;
+    int e_old = g.c_rowptr[n], tot_new = e_old + tot_add;
+    if (tot_new > C.ccap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 13); return; }
     __syncthreads();
-    if (carry > C.ccap) return;
-    // ---- merge old rows with the new pairs
+    // The receiving rows (first old entry, row id, new links before the row) are what every row and every entry
+    // is located against below: they go to shared memory when there are at most 1024 of them.
+    __shared__ int sm_start[1024], sm_row[1024], sm_before[1025];
+    int32_t *ins_rowid = RP(C.ins_rowid, r, C.Pcap), *ins_before = RP(C.ins_before, r, C.Pcap + 1);
+    for (int k = tid; k <= nins; k += blockDim.x) {
+        int before = (k < nins) ? pnew[ins[k]] : tot_add;
+        int row = (k < nins) ? (int)(pairs[ins[k]] >> 32) : n;
+        ins_before[k] = before;
+        if (k < nins) ins_rowid[k] = row;
+        if (nins <= 1024) { sm_before[k] = before; if (k < nins) { sm_row[k] = row; sm_start[k] = ins_start[k]; } }
+    }
+    __syncthreads();
+    const int *q_start = (nins <= 1024) ? sm_start : ins_start, *q_row = (nins <= 1024) ? sm_row : ins_rowid;
+    const int *q_before = (nins <= 1024) ? sm_before : ins_before;
+    // ---- new row pointers: a row moves right by the number of new links in the receiving rows before it
+    for (int a = tid; a <= n; a += blockDim.x) {
+        int lo = 0, hi = nins;   // receiving rows with id < a
+        while (lo < hi) { int m = (lo + hi) >> 1; if (q_row[m] < a) lo = m + 1; else hi = m; }
+        rp_new[a] = g.c_rowptr[a] + q_before[lo];
+    }
+    // ---- entries of rows without pairs move as they are: one thread per old entry
+#pragma unroll 4
+    for (int e = tid; e < e_old; e += blockDim.x) {
+        int lo = 0, hi = nins;   // receiving rows whose first old entry is <= e
+        while (lo < hi) { int m = (lo + hi) >> 1; if (q_start[m] <= e) lo = m + 1; else hi = m; }
+        if (lo > 0 && e < g.c_rowptr[q_row[lo - 1] + 1]) continue;     // inside a receiving row: merged below
+        ent_new[e + q_before[lo]] = g.c_ent[e];
+    }
+    // ---- receiving rows: one warp per row.  An old entry moves right by the new links of this row that sort
+    // before it (and takes the new count if a pair names it); a new link goes behind the old entries that sort
+    // before it and the new links before it.
     uint32_t *uent_rw = RP(C.u_ent, r, C.ucap);
-    for (int a = tid; a < n; a += blockDim.x) {
-        int ob = g.c_rowptr[a], oe = g.c_rowptr[a + 1], out = rp_new[a];
-        if (!(addlen[a] & 0x40000000)) {  // no pair starts at a: the row only moves
-            for (int i = ob; i < oe; i++) ent_new[out++] = g.c_ent[i];
-            continue;
-        }
-        int pb = 0, pe = nu;  // lower_bound of (a,*) in the unique pair list
-        { int lo = 0, hi = nu; unsigned long long key = (unsigned long long)(unsigned)a << 32;
-          while (lo < hi) { int m = (lo + hi) >> 1; if (pairs[m] < key) lo = m + 1; else hi = m; } pb = lo; }
-        pe = pb;
-        while (pe < nu && (int)(pairs[pe] >> 32) == a) pe++;
-        int i = ob, j = pb;
-        while (i < oe || j < pe) {
-            if (j >= pe) { ent_new[out++] = g.c_ent[i++]; continue; }
-            int b = (int)(pairs[j] & 0xffffffffu);
-            if (i < oe && g.c_ent[i].x < b) { ent_new[out++] = g.c_ent[i++]; continue; }
-            unsigned smask;
-            if (i < oe && g.c_ent[i].x == b) { smask = CE_SMASK(g.c_ent[i].y); i++; }
-            else {  // new link: copy the static mask of the pair and flag the static entry
-                int idx = static_find_idx(g, a, b);
-                smask = 0;
-                if (idx >= 0) { smask = ENT_MASK(uent_rw[idx]); atomicOr(&uent_rw[idx], ENT_CRIM); }
+    int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    for (int k = w; k < nins; k += nw) {
+        int pb = ins[k], pe = (k + 1 < nins) ? ins[k + 1] : nu;
+        int a = q_row[k], ob = g.c_rowptr[a], oe = g.c_rowptr[a + 1], nb = ob + q_before[k];
+        for (int i = ob + lane; i < oe; i += 32) {
+            int2 ce = g.c_ent[i];
+            int shift = 0;
+            for (int j = pb; j < pe; j++) {
+                int b = (int)(pairs[j] & 0xffffffffu), pc = pcnt[j];
+                if (b < ce.x) shift += (pc & 0x40000000) ? 1 : 0;
+                else if (b == ce.x) ce.y = (pc & 0x3fffffff) | (int)(CE_SMASK(ce.y) << 24);
             }
-            ent_new[out++] = make_int2(b, pcnt[j] | (int)(smask << 24)); j++;
+            ent_new[nb + (i - ob) + shift] = ce;
+        }
+        for (int j = pb + lane; j < pe; j += 32) {
+            int pc = pcnt[j];
+            if (!(pc & 0x40000000)) continue;
+            int b = (int)(pairs[j] & 0xffffffffu);
+            int lo = ob, hi = oe;   // old entries that sort before b
+            while (lo < hi) { int m = (lo + hi) >> 1; if (g.c_ent[m].x < b) lo = m + 1; else hi = m; }
+            int idx = static_find_idx(g, a, b);  // new link: copy the static mask of the pair and flag the static entry
+            unsigned smask = 0;
+            if (idx >= 0) { smask = ENT_MASK(uent_rw[idx]); atomicOr(&uent_rw[idx], ENT_CRIM); }
+            ent_new[nb + (lo - ob) + (pnew[j] - pnew[pb])] = make_int2(b, (pc & 0x3fffffff) | (int)(smask << 24));
         }
     }
     __syncthreads();
-    // ---- publish
-    int32_t *rp_cur = RP(C.c_rowptr, r, C.Ncap + 1);
-    int2 *ent_cur = RP(C.c_ent, r, C.ccap);
-    int tot_new = rp_new[n];
-    for (int a = tid; a <= n; a += blockDim.x) rp_cur[a] = rp_new[a];
-    for (int e = tid; e < tot_new; e += blockDim.x) ent_cur[e] = ent_new[e];
+    if (tid == 0) C.c_par[r] = par ^ 1;   // publish: the other buffer is the criminal layer from here on
 }
 
 // ============================================================================ A9-A11 recruitment and arrests
@@ -1207,7 +1238,7 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
     // A11 get_caught
     double *sentence = RP(C.sentence, r, C.Ncap);
     uint32_t *uent = RP(C.u_ent, r, C.ucap);
-    int2 *cent_rw = RP(C.c_ent, r, C.ccap);
+    int2 *cent_rw = const_cast<int2 *>(g.c_ent);
     for (int i = 0; i < nfound; i++) {
         int a = gmem[found[i]];
         found[i] = a;  // report slots
@@ -1280,7 +1311,7 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     int r = C.r0 + blockIdx.x, n = C.n_agents[r], tid = threadIdx.x;
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap), *nct = RP(C.ncrimes_tick, r, C.Ncap);
-    const int32_t *crp = RP(C.c_rowptr, r, C.Ncap + 1);
+    const int32_t *crp = graph_of(C, r).c_rowptr;
     const double *tend = RP(C.tendency, r, C.Ncap);
     enum { I_OC = 0, I_PRIS, I_LINK, I_SUMCR, I_OCOC, I_ALIVE, I_AGE, I_AGE2, I_EDU, I_EDU2, I_CR2, I_EMPL, I_FAC, I_STUD, NI };
     long long vi[NI];
