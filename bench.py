@@ -309,14 +309,14 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
                          # (profiles/r01_05_*: 42.8 MB for a launch of 5,760 evaluations), scaled to this run's
                          # evaluations per launch
-                         "traffic": (42.8e6 / 5760.0) * (stats["emb_requests"] / max(tm_n[roof_class], 1)) if roof_class == "embeddedness" else None,
-                         "traffic_source": "ncu capture profiles/r01_05_ncu_full_k_embeddedness_raw.csv, per evaluation x evaluations per launch",
+                         "traffic": (298.3e6 / 12957.0) * (stats["emb_requests"] / max(tm_n[roof_class], 1)) if roof_class == "embeddedness" else None,
+                         "traffic_source": "ncu capture profiles/r01_06_ncu_full_k_embeddedness_512_raw.csv (dram read + write of one launch / its evaluations = 23 KB per evaluation) x evaluations per launch",
                          "avg_launch_ms": roof_launch_ms, "launches": tm_n[roof_class],
                          "algorithmic_bytes_per_launch": alg[roof_class] / max(tm_n[roof_class], 1),
                          "units_per_launch": (stats["emb_requests"] if roof_class == "embeddedness" else stats["search_crimes"]) / max(tm_n[roof_class], 1),
                          "bytes_per_unit": alg[roof_class] / max(stats["emb_requests"] if roof_class == "embeddedness" else stats["search_crimes"], 1),
                          "peak_source": "MEASURED_PEAKS.json (copy bandwidth, of measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "instruction-issue bound (sm__issue_active 57 %), DRAM traffic below the algorithmic bytes (L2 reuse across the balls of a replica); see DESIGN.md section 5 and profiles/README.md"},
+                         "note": "instruction-issue bound (sm__issue_active 74 %), DRAM traffic below the algorithmic bytes (L2 reuse across the balls of a replica); see DESIGN.md section 5 and profiles/README.md"},
             "work": stats,
         }
         if not args.no_cpu:
