@@ -508,19 +508,41 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         C.n_emb[r] = 0; C.n_emb[C.R + r] = 0;
         C.n_arrested[r] = 0;
     }
-    // stage weights cell-ordered, and per-cell min / any-negative (one warp per cell, round robin)
-    // the cell-ordered weights live in shared memory when the population fits (every pass below is then on chip and
-    // the serial chains cost one LDS + DADD per element); larger populations work in the global cdf array
-    int total = off[nc];
-    const bool fit = total <= smem_doubles;
-    double *wt = fit ? wt_sm : cdf;
-#pragma unroll 4
-    for (int i = tid; i < total; i += blockDim.x) wt[i] = tend[members[i]];  // 4 independent gathers in flight
+    // The cell-ordered weights live in shared memory when the population fits (every pass below is then on chip);
+    // larger populations work in the global cdf array.  In shared memory every cell starts at a multiple of eight
+    // and is padded with zeros to a multiple of eight, so the serial chains below run without per-element
+    // predicates (acc + 0.0 == acc: the weights are >= 0 once the min-shift is applied).
+    __shared__ int poff[POC_MAX_CELLS + 1];
+    if (tid == 0) {
+        int s = 0;
+        for (int k = 0; k < nc; k++) { poff[k] = s; s += (off[k + 1] - off[k] + 7) & ~7; }
+        poff[nc] = s;
+    }
     __syncthreads();
-    for (int k = w; k < nc; k += nw) {
+    int total = off[nc], ptotal = poff[nc];
+    const bool fit = ptotal <= smem_doubles;
+    unsigned char *cellof8 = (unsigned char *)(wt_sm + smem_doubles);   // cell of every block of eight positions
+    const int *woff = fit ? poff : off;
+    double *wt = fit ? wt_sm : cdf;
+    if (fit) {
+        for (int k = w; k < nc; k += nw)
+            for (int q = (poff[k] >> 3) + lane; q < (poff[k + 1] >> 3); q += 32) cellof8[q] = (unsigned char)k;
+        __syncthreads();
+#pragma unroll 4
+        for (int q = tid; q < ptotal; q += blockDim.x) {  // independent gathers in flight
+            int k = cellof8[q >> 3], i = q - poff[k];
+            wt_sm[q] = (i < off[k + 1] - off[k]) ? tend[members[off[k] + i]] : 0.0;
+        }
+    } else {
+#pragma unroll 4
+        for (int i = tid; i < total; i += blockDim.x) cdf[i] = tend[members[i]];
+    }
+    __syncthreads();
+    for (int k = w; k < nc; k += nw) {   // per-cell min / any-negative
         double m = INFINITY;
         bool ng = false;
-        for (int i = off[k] + lane; i < off[k + 1]; i += 32) { double v = wt[i]; m = fmin(m, v); ng |= (v < 0.0); }
+        int len = off[k + 1] - off[k];
+        for (int i = lane; i < len; i += 32) { double v = wt[woff[k] + i]; m = fmin(m, v); ng |= (v < 0.0); }
         for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL_MASK, m, o));
         ng = __any_sync(FULL_MASK, ng);
         if (lane == 0) { mn[k] = m; neg[k] = ng; }
@@ -528,56 +550,64 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
     __syncthreads();
     if (fit) {
         // The two order-defined chains (sum, then cumulative sum of p/sum) are serial within a cell and independent
-        // across cells: lane k of warp 0 walks cell k in shared memory; shift, count, divisions stay parallel.
+        // across cells: lane k of warp 0 walks cell k in shared memory (one LDS + one DADD per element, the next
+        // eight values in flight); shift, non-zero count and the divisions stay parallel.
         for (int k = w; k < nc; k += nw) {
             if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
-            int cnt = 0;
-            for (int base = off[k]; base < off[k + 1]; base += 32) {
+            int cnt = 0, len = off[k + 1] - off[k];
+            double *row = wt_sm + poff[k];
+            for (int base = 0; base < len; base += 32) {
                 int i = base + lane;
-                double p = 0.0;
-                if (i < off[k + 1]) { p = wt_sm[i]; if (neg[k]) { p = p - mn[k]; wt_sm[i] = p; } }
-                cnt += __popc(__ballot_sync(FULL_MASK, p != 0.0));
+                double x = 0.0;
+                if (i < len) { x = row[i]; if (neg[k]) { x = x - mn[k]; row[i] = x; } }
+                cnt += __popc(__ballot_sync(FULL_MASK, x != 0.0));
             }
             if (lane == 0) nzc[k] = cnt;
         }
         __syncthreads();
         bool act = lane < nc && ncr[lane] > 0;
-        int cb = act ? off[lane] : 0, len = act ? off[lane + 1] - off[lane] : 0, maxlen = len;
+        int len8 = act ? poff[lane + 1] - poff[lane] : 0, maxlen = len8;
         for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL_MASK, maxlen, o));
-        // (the next eight values are fetched from shared memory while the current eight go down the DADD chain)
+        double *src = wt_sm + (act ? poff[lane] : 0);
         if (w == 0) {
-            const double *src = wt_sm + cb;
             double acc = 0.0, x[8], nx[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) nx[q] = (q < len) ? src[q] : 0.0;
+            for (int q = 0; q < 8; q++) nx[q] = (len8 > 0) ? src[q] : 0.0;
             for (int j = 0; j < maxlen; j += 8) {
+                bool more = j + 8 < len8;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = (j + 8 + q < len) ? src[j + 8 + q] : 0.0; }
+                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = more ? src[j + 8 + q] : 0.0; }
 #pragma unroll
-                for (int q = 0; q < 8; q++) if (j + q < len) acc = acc + x[q];
+                for (int q = 0; q < 8; q++) acc = acc + x[q];
             }
             s_sum[lane] = acc;
         }
         __syncthreads();
-        for (int k = w; k < nc; k += nw) {
-            if (ncr[k] == 0 || s_sum[k] == 0.0) continue;
-            double s = s_sum[k];
-            for (int i = off[k] + lane; i < off[k + 1]; i += 32) wt_sm[i] = wt_sm[i] / s;
+        for (int q = tid; q < ptotal; q += blockDim.x) {
+            int k = cellof8[q >> 3];
+            if (ncr[k] > 0 && s_sum[k] != 0.0) wt_sm[q] = wt_sm[q] / s_sum[k];
         }
         __syncthreads();
         if (w == 0) {
-            double acc = 0.0;
-            if (act && s_sum[lane] == 0.0) len = 0;
-            double *src = wt_sm + cb, x[8], nx[8];
+            double acc = 0.0, x[8], nx[8];
+            if (act && s_sum[lane] == 0.0) len8 = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) nx[q] = (q < len) ? src[q] : 0.0;
+            for (int q = 0; q < 8; q++) nx[q] = (len8 > 0) ? src[q] : 0.0;
             for (int j = 0; j < maxlen; j += 8) {
+                bool more = j + 8 < len8;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = (j + 8 + q < len) ? src[j + 8 + q] : 0.0; }
+                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = more ? src[j + 8 + q] : 0.0; }
+                if (j < len8) {
 #pragma unroll
-                for (int q = 0; q < 8; q++) if (j + q < len) { acc = acc + x[q]; src[j + q] = acc; }
+                    for (int q = 0; q < 8; q++) { acc = acc + x[q]; src[j + q] = acc; }
+                }
             }
             if (act) { nz[lane] = (s_sum[lane] == 0.0) ? 0 : nzc[lane]; last[lane] = acc; }
+        }
+        __syncthreads();
+        for (int q = tid; q < ptotal; q += blockDim.x) {
+            int k = cellof8[q >> 3];
+            if (ncr[k] > 0 && nz[k] > 0) wt_sm[q] = wt_sm[q] / last[k];
         }
     } else {
         // the two order-defined chains (sum, then cumulative sum of p/sum): one warp per cell, see warp_chain32
@@ -603,12 +633,12 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
                 }
             if (lane == 0) { nz[k] = (sump == 0.0) ? 0 : nzz; last[k] = acc; }
         }
-    }
-    __syncthreads();
-    for (int k = w; k < nc; k += nw) {
-        if (!(ncr[k] > 0 && nz[k] > 0)) continue;
-        double l = last[k];
-        for (int i = off[k] + lane; i < off[k + 1]; i += 32) wt[i] = wt[i] / l;
+        __syncthreads();
+        for (int k = w; k < nc; k += nw) {
+            if (!(ncr[k] > 0 && nz[k] > 0)) continue;
+            double l = last[k];
+            for (int i = off[k] + lane; i < off[k + 1]; i += 32) cdf[i] = cdf[i] / l;
+        }
     }
     __syncthreads();
     // the draws
@@ -631,7 +661,7 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
             continue;
         }
         int m = off[k + 1] - off[k];
-        int ii = ss_right(wt + off[k], m, u1);
+        int ii = ss_right(wt + woff[k], m, u1);
         if (ii >= m) ii = m - 1;
         int init = members[off[k] + ii];
         int si = ss_right(P.size_cdf, P.n_sizes, u2);
