@@ -528,10 +528,19 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         for (int k = w; k < nc; k += nw)
             for (int q = (poff[k] >> 3) + lane; q < (poff[k + 1] >> 3); q += 32) cellof8[q] = (unsigned char)k;
         __syncthreads();
-#pragma unroll 4
-        for (int q = tid; q < ptotal; q += blockDim.x) {  // independent gathers in flight
-            int k = cellof8[q >> 3], i = q - poff[k];
-            wt_sm[q] = (i < off[k + 1] - off[k]) ? tend[members[off[k] + i]] : 0.0;
+        for (int q0 = tid; q0 < ptotal; q0 += 8 * blockDim.x) {  // eight independent gathers in flight per thread
+            int id[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int q = q0 + u * blockDim.x;
+                id[u] = -1;
+                if (q < ptotal) { int k = cellof8[q >> 3], i = q - poff[k]; if (i < off[k + 1] - off[k]) id[u] = members[off[k] + i]; }
+            }
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (id[u] >= 0) ? tend[id[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) { int q = q0 + u * blockDim.x; if (q < ptotal) wt_sm[q] = v[u]; }
         }
     } else {
 #pragma unroll 4
@@ -552,17 +561,18 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         // The two order-defined chains (sum, then cumulative sum of p/sum) are serial within a cell and independent
         // across cells: lane k of warp 0 walks cell k in shared memory (one LDS + one DADD per element, the next
         // eight values in flight); shift, non-zero count and the divisions stay parallel.
-        for (int k = w; k < nc; k += nw) {
-            if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
-            int cnt = 0, len = off[k + 1] - off[k];
-            double *row = wt_sm + poff[k];
-            for (int base = 0; base < len; base += 32) {
-                int i = base + lane;
-                double x = 0.0;
-                if (i < len) { x = row[i]; if (neg[k]) { x = x - mn[k]; row[i] = x; } }
-                cnt += __popc(__ballot_sync(FULL_MASK, x != 0.0));
+        if (tid < nc) { nzc[tid] = 0; if (ncr[tid] == 0) { nz[tid] = 1; last[tid] = 1.0; } }
+        __syncthreads();
+        for (int q0 = 0; q0 < ptotal; q0 += blockDim.x) {     // block-uniform trip count (ballot below)
+            int q = q0 + tid, k = -1;
+            double x = 0.0;
+            if (q < ptotal) {
+                k = cellof8[q >> 3];
+                if (ncr[k] > 0) { x = wt_sm[q]; if (neg[k] && q - poff[k] < off[k + 1] - off[k]) { x = x - mn[k]; wt_sm[q] = x; } }
             }
-            if (lane == 0) nzc[k] = cnt;
+            // eight consecutive positions belong to one cell: one shared-memory add per group of eight lanes
+            unsigned nzb = (__ballot_sync(FULL_MASK, x != 0.0) >> (lane & 24)) & 0xffu;
+            if ((lane & 7) == 0 && nzb) atomicAdd(&nzc[k], __popc(nzb));
         }
         __syncthreads();
         bool act = lane < nc && ncr[lane] > 0;
@@ -570,15 +580,19 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL_MASK, maxlen, o));
         double *src = wt_sm + (act ? poff[lane] : 0);
         if (w == 0) {
-            double acc = 0.0, x[8], nx[8];
+            double acc = 0.0, xa[8], xb[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) nx[q] = (len8 > 0) ? src[q] : 0.0;
-            for (int j = 0; j < maxlen; j += 8) {
-                bool more = j + 8 < len8;
+            for (int q = 0; q < 8; q++) xa[q] = (len8 > 0) ? src[q] : 0.0;
+            for (int j = 0; j < maxlen; j += 16) {     // two halves in flight: one is summed while the other loads
+                bool pb = j + 8 < len8, pa = j + 16 < len8;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = more ? src[j + 8 + q] : 0.0; }
+                for (int q = 0; q < 8; q++) xb[q] = pb ? src[j + 8 + q] : 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) acc = acc + x[q];
+                for (int q = 0; q < 8; q++) acc = acc + xa[q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) xa[q] = pa ? src[j + 16 + q] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc = acc + xb[q];
             }
             s_sum[lane] = acc;
         }
@@ -589,18 +603,20 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         }
         __syncthreads();
         if (w == 0) {
-            double acc = 0.0, x[8], nx[8];
+            double acc = 0.0, xa[8], xb[8];
             if (act && s_sum[lane] == 0.0) len8 = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) nx[q] = (len8 > 0) ? src[q] : 0.0;
-            for (int j = 0; j < maxlen; j += 8) {
-                bool more = j + 8 < len8;
+            for (int q = 0; q < 8; q++) xa[q] = (len8 > 0) ? src[q] : 0.0;
+            for (int j = 0; j < maxlen; j += 16) {
+                bool sa = j < len8, pb = j + 8 < len8, pa = j + 16 < len8;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { x[q] = nx[q]; nx[q] = more ? src[j + 8 + q] : 0.0; }
-                if (j < len8) {
+                for (int q = 0; q < 8; q++) xb[q] = pb ? src[j + 8 + q] : 0.0;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) { acc = acc + x[q]; src[j + q] = acc; }
-                }
+                for (int q = 0; q < 8; q++) { acc = acc + xa[q]; if (sa) src[j + q] = acc; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) xa[q] = pa ? src[j + 16 + q] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { acc = acc + xb[q]; if (pb) src[j + 8 + q] = acc; }
             }
             if (act) { nz[lane] = (s_sum[lane] == 0.0) ? 0 : nzc[lane]; last[lane] = acc; }
         }
