@@ -41,7 +41,6 @@ struct poc_ctx {
     uint8_t *stage_host2[2] = {nullptr, nullptr};          // upload mirrors, used alternately
     cudaEvent_t stage_ev2[2] = {nullptr, nullptr}; bool stage_busy2[2] = {false, false}; int stage_next = 0;
     size_t stage_bytes = 0, stage_off[24] = {};
-    cudaEvent_t stage_ev = nullptr; bool stage_busy = false;
     int cells_threads = 1024;       // k_cells block size (its count table is n_cells x threads ints of shared memory)
     int commit_threads = 1024;      // k_commit block size, same reasoning
     int draw_threads = 1024;        // k_draw block size: one block per SM is latency-bound, several need fewer registers per block
@@ -223,7 +222,6 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
 #undef SZ
         ctx->stage_bytes = o;
         DA(ctx->stage_dev, o);
-        cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
         for (int b = 0; b < 2; b++) {
             cudaEventCreateWithFlags(&ctx->stage_ev2[b], cudaEventDisableTiming);
             if (cudaHostAlloc((void **)&ctx->stage_host2[b], o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
@@ -273,7 +271,6 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
-    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
     for (int b = 0; b < 2; b++) { if (ctx->stage_host2[b]) cudaFreeHost(ctx->stage_host2[b]); if (ctx->stage_ev2[b]) cudaEventDestroy(ctx->stage_ev2[b]); }
     for (auto &evx : ctx->ev) cudaEventDestroy(evx);
     for (auto &m : ctx->marker) cudaEventDestroy(m);

@@ -898,7 +898,6 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     int32_t *goff = RP(C.group_off, r, C.Ccap + 1), *gmem = RP(C.group_mem, r, C.Mcap);
     unsigned long long *pairs = RP(C.pairs, r, C.Pcap);
     int32_t *pcnt = RP(C.pair_cnt, r, C.Pcap);
-    const uint32_t *attr = RP(C.attr, r, C.Ncap);
     const double *tend = RP(C.tendency, r, C.Ncap);
     int32_t *ncrimes = RP(C.ncrimes, r, C.Ncap), *ncrimes_tick = RP(C.ncrimes_tick, r, C.Ncap);
     Graph g = graph_of(C, r);
@@ -1346,13 +1345,9 @@ __global__ void __launch_bounds__(256, 4) k_recruit_arrest(DevCtx C, int end_tic
 // replica group's tick state on; 3: only move the tick state on
 __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     int t = C.ti[C.grp].rep - (mode == 1 ? 1 : 0);
-    if (mode >= 2) {
-        __shared__ int s_last;
-        if (mode == 3) {
-            if (threadIdx.x == 0) { TickInfo &ti = C.ti[C.grp]; if (atomicAdd(&ti.pad, 1) == (int)gridDim.x - 1) { ti.pad = 0; ti.tick++; ti.epoch++; ti.rep++; } }
-            return;
-        }
-        (void)s_last;
+    if (mode == 3) {
+        if (threadIdx.x == 0) { TickInfo &ti = C.ti[C.grp]; if (atomicAdd(&ti.pad, 1) == (int)gridDim.x - 1) { ti.pad = 0; ti.tick++; ti.epoch++; ti.rep++; } }
+        return;
     }
     int r = C.r0 + blockIdx.x, n = C.n_agents[r], tid = threadIdx.x;
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
