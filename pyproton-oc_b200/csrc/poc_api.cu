@@ -42,6 +42,7 @@ struct poc_ctx {
     cudaEvent_t stage_ev2[2] = {nullptr, nullptr}; bool stage_busy2[2] = {false, false}; int stage_next = 0;
     size_t stage_bytes = 0, stage_off[24] = {};
     int cells_threads = 1024;       // k_cells block size (its count table is n_cells x threads ints of shared memory)
+    int search_threads = 256;       // k_search block size (one block per crime)
     int commit_threads = 1024;      // k_commit block size, same reasoning
     int draw_threads = 1024;        // k_draw block size: one block per SM is latency-bound, several need fewer registers per block
     int32_t *st_rowptr[POC_NUM_LAYERS] = {};
@@ -171,6 +172,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
     ctx->draw_threads = (R > 148) ? 512 : 1024;   // measured at 512 replicas: 256 / 512 / 1024 threads -> 177 / 143 / 213 us
     ctx->commit_threads = (R > 148) ? 512 : 1024;
+    ctx->search_threads = (R < 8) ? 512 : (R < 256 ? 256 : 128);   // measured us per tick at 1 / 128 / 512 replicas: 128 threads - / 650 / 1723, 256: 175 / 641 / 1753, 512: 173 / 672 / 1916
+    if (const char *e = getenv("POC_SEARCH_T")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512) ctx->search_threads = t; }
     ctx->cells_threads = 1024;   // measured: 512 threads is no faster at 512 replicas (59.6 vs 52 us)
     if (const char *e = getenv("POC_CELLS_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->cells_threads = t; }
     if (const char *e = getenv("POC_COMMIT_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->commit_threads = t; }
@@ -614,7 +617,7 @@ static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
     int rounds = max_radius(ctx);
     dim3 grid(ctx->gx, D.Rg);
     for (int rd = 0; rd <= rounds; rd++) {
-        { Timed t(ctx, TM_SEARCH, s); k_search<<<grid, 256, ctx->smem_search, s>>>(D, rd & 1); }
+        { Timed t(ctx, TM_SEARCH, s); k_search<<<grid, ctx->search_threads, ctx->smem_search, s>>>(D, rd & 1); }
         if (rd < rounds) { Timed t(ctx, TM_EMB, s); launch_emb(ctx, D, s, rd & 1); }
     }
     CU(cudaGetLastError());

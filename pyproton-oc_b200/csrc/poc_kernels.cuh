@@ -708,8 +708,8 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
                              unsigned long long &ncand) {
     __shared__ int s_count, lvl_off[MAX_RADIUS + 3];
     __shared__ int s_st[6];  // nacc, target, mrem, facneeded, pickidx, stop
-    __shared__ double wkey[8];
-    __shared__ int wslot[8], widx[8];
+    __shared__ double wkey[32];
+    __shared__ int wslot[32], widx[32];
     int n = C.n_agents[r], nwords = (n + 31) >> 5, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     const poc_params &P = C.params[r];
     Graph g = graph_of(C, r);
@@ -851,7 +851,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     }
 }
 
-__global__ void __launch_bounds__(256, 8) k_search(DevCtx C, int parity) {
+__global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     int tick = C.ti[C.grp].tick, epoch = C.ti[C.grp].epoch;
     extern __shared__ unsigned smem_u[];
     int r = C.r0 + blockIdx.y;
