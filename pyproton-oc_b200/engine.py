@@ -119,14 +119,24 @@ class CrimeEngine:
             self._ck(self.L.poc_build_graph_async(self.h, replica))
             self._keepalive.append(keep)
 
-    def download_agents(self, replica: int = 0) -> Dict[str, np.ndarray]:
+    def download_agents(self, replica: int = 0, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """Agent columns of one replica.  `out` (a dict from agent_buffers()) is filled in place when given: writing
+        into already-touched host memory is about five times faster than into freshly allocated arrays."""
         n = self.n_agents[replica]
-        out, cols = {}, AgentCols()
+        if out is None:
+            out = self.agent_buffers(n)
+        cols = AgentCols()
         for f, key in STATE_KEYS.items():
-            out[key] = np.empty(n, dtype=_DTYPES[f])
-            setattr(cols, f, out[key].ctypes.data)
+            arr = out[key]
+            if arr.dtype != _DTYPES[f] or len(arr) < n or not arr.flags.c_contiguous:
+                raise ValueError("download_agents: out[%r] must be a contiguous %s array of at least %d" % (key, _DTYPES[f], n))
+            setattr(cols, f, arr.ctypes.data)
         self._ck(self.L.poc_download_agents(self.h, replica, C.byref(cols)))
         return out
+
+    @staticmethod
+    def agent_buffers(n: int) -> Dict[str, np.ndarray]:
+        return {key: np.zeros(n, dtype=_DTYPES[f]) for f, key in STATE_KEYS.items()}
 
     def download_layer(self, replica: int, layer: int):
         n = self.n_agents[replica]
@@ -222,10 +232,17 @@ class CrimeEngine:
                     "arrested": bufs["arrested"][:na].copy()}
         return res, recs
 
-    def run_ticks(self, tick0: int, n_ticks: int, philox_keys: Sequence[int], reporters: bool = True):
+    def run_ticks(self, tick0: int, n_ticks: int, philox_keys: Sequence[int], reporters: bool = True,
+                  out: Optional[np.ndarray] = None):
+        """n_ticks ticks of the hot path for every replica, no host synchronisation inside.  reporters=True returns
+        the [R, n_ticks, len(REPORTER_NAMES)] rows (into `out` when given: a float64 array of that shape)."""
         keys = np.ascontiguousarray(philox_keys, dtype=np.uint64)
         assert len(keys) == self.R
-        rep = np.zeros((self.R, n_ticks, N_REPORTERS), np.float64) if reporters else None
+        rep = None
+        if reporters:
+            rep = out if out is not None else np.zeros((self.R, n_ticks, N_REPORTERS), np.float64)
+            if rep.shape != (self.R, n_ticks, N_REPORTERS) or rep.dtype != np.float64 or not rep.flags.c_contiguous:
+                raise ValueError("run_ticks: out must be a contiguous float64 array of shape (R, n_ticks, %d)" % N_REPORTERS)
         self._ck(self.L.poc_run_ticks(self.h, tick0, n_ticks, keys.ctypes.data,
                                       rep.ctypes.data if rep is not None else None))
         return rep

@@ -21,3 +21,20 @@ pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
 t0 = time.perf_counter(); cols = [E.download_agents(r) for r in range(a.replicas)]; print("download agents: %.1f ms" % (1e3 * (time.perf_counter() - t0)))
 for k, v in st.items():
     print(k, v.dtype, v.shape, end="; ")
+
+# split of download_agents: the C call alone vs the Python wrapper (allocation of the 21 output columns)
+import ctypes as C
+from pyproton_oc_b200.engine import AgentCols, STATE_KEYS, _DTYPES
+n = E.n_agents[0]
+out = {key: np.empty(n, dtype=_DTYPES[f]) for f, key in STATE_KEYS.items()}
+cols = AgentCols()
+for f, key in STATE_KEYS.items():
+    setattr(cols, f, out[key].ctypes.data)
+t0 = time.perf_counter()
+for r in range(a.replicas):
+    E.L.poc_download_agents(E.h, r, C.byref(cols))
+print("\nC call only, reused output arrays: %.1f ms" % (1e3 * (time.perf_counter() - t0)))
+t0 = time.perf_counter()
+for r in range(a.replicas):
+    o2 = {key: np.empty(n, dtype=_DTYPES[f]) for f, key in STATE_KEYS.items()}
+print("allocating the output arrays: %.1f ms" % (1e3 * (time.perf_counter() - t0)))
