@@ -134,9 +134,10 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
     int gid = threadIdx.x / G, gt = threadIdx.x % G, lane = threadIdx.x & 31, w = gt >> 5;
     // shared memory: [invw 256 f64] then per group [dist DCAP u64][EmbShared][bitmap wcap][wprefix wcap]
     double *invw = (double *)smem_raw;
-    size_t per_group = (size_t)DCAP * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * (((size_t)wcap * 4 + 7) & ~(size_t)7);
+    size_t per_group = ((size_t)DCAP * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * (((size_t)wcap * 4 + 7) & ~(size_t)7) + 15) & ~(size_t)15;
     unsigned char *gbase = smem_raw + 256 * 8 + (size_t)gid * per_group;
     unsigned long long *s_dist = (unsigned long long *)gbase;
+    int4 *rowtab = (int4 *)gbase + w * 32;   // staging pass only: 32 rows x {entry address bases, split, rank} per warp
     EmbShared *S = (EmbShared *)(gbase + (size_t)DCAP * 8);
     unsigned *bitmap = (unsigned *)((unsigned char *)S + ((sizeof(EmbShared) + 7) & ~(size_t)7));
     int *wprefix = (int *)((unsigned char *)bitmap + (((size_t)wcap * 4 + 7) & ~(size_t)7));
@@ -210,12 +211,21 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                 // flattened index f of node t: multiplex entry (b0 - excl) + f while f < excl + len0, else criminal
                 // entry (b1 - excl - len0) + f
                 int adr0 = b0 - excl, split = excl + len0, adr1 = b1 - split;
+                // The non-empty rows of the batch go, compacted, into a per-warp table (in the distance array's shared
+                // memory, which is idle until the relaxation).  A window of 32 flattened positions then finds its rows
+                // from one OR-reduction of the row-start bits and a popcount instead of a shuffle binary search.
+                unsigned nem = __ballot_sync(FULL_MASK, len > 0);
+                if (len > 0) rowtab[__popc(nem & ((1u << lane) - 1))] = make_int4(adr0, split, adr1, ru);
+                __syncwarp();
+                int rows_before = 0;
                 for (int fb = 0; fb < tot; fb += 32) {
-                    int f = fb + lane, t = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) { int e = __shfl_sync(FULL_MASK, excl, t + s); if (e <= f) t += s; }
-                    int ta0 = __shfl_sync(FULL_MASK, adr0, t), tsp = __shfl_sync(FULL_MASK, split, t);
-                    int ta1 = __shfl_sync(FULL_MASK, adr1, t), tru = __shfl_sync(FULL_MASK, ru, t);
+                    int f = fb + lane;
+                    unsigned d = (unsigned)(excl - fb);
+                    unsigned starts = __reduce_or_sync(FULL_MASK, (len > 0 && d < 32u) ? (1u << d) : 0u);
+                    int k = rows_before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+                    rows_before += __popc(starts);
+                    int4 rt = rowtab[f < tot ? k : 0];
+                    int ta0 = rt.x, tsp = rt.y, ta1 = rt.z, tru = rt.w;
                     bool ok = false;
                     int v = 0, wgt = 0;
                     if (f < tot) {
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                         }
                     }
                 }
+                __syncwarp();   // the next batch overwrites the row table
             }
             gsync<G>();
             if (S->over) { staged = false; ib = (gt == 0) ? 4ull * total + 8ull : 0ull; }
@@ -360,6 +371,6 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
 static inline size_t emb_smem_bytes(int G, int Ncap) {
     size_t wcap = (size_t)(Ncap + 31) / 32;
     size_t dcap = (G == 32) ? EmbCfg<32>::DCAP : (G >= 256 ? EmbCfg<256>::DCAP : EmbCfg<128>::DCAP);
-    size_t per_group = dcap * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * ((wcap * 4 + 7) & ~(size_t)7);
+    size_t per_group = (dcap * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * ((wcap * 4 + 7) & ~(size_t)7) + 15) & ~(size_t)15;
     return 256 * 8 + (size_t)((G == 32) ? 8 : 1) * per_group;
 }
