@@ -262,7 +262,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
         for (int i = gt; i < total; i += G) dist[i] = DIST_INF;
         for (int i = gt; i < 2 * (RCAP >> 5); i += G) S->chg[i] = 0u;
         gsync<G>();
-        if (gt == 0) { int rs = RANK(self); dist[rs] = 0ull; S->flag_more = 1; if (rs < RCAP) S->chg[rs >> 5] = 1u << (rs & 31); }
+        if (gt == 0) { int rs = RANK(self); dist[rs] = 0ull; S->flag_more = staged ? 0 : 1; if (rs < RCAP) S->chg[rs >> 5] = 1u << (rs & 31); }
         gsync<G>();
         int rounds = 0;
         if (staged) {
@@ -270,10 +270,9 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
             // bitmaps (moved last round / this round) gate the relaxations.
             int nedge = S->ne, cw = (total + 31) >> 5;
             unsigned *chg0 = S->chg, *chg1 = S->chg + (RCAP >> 5);
-            while (S->flag_more) {
-                gsync<G>();
-                if (gt == 0) S->flag_more = 0;
-                gsync<G>();
+            // two barriers per round: a round that moved anything writes its number to flag_more, and everybody goes
+            // on while flag_more has reached the round just finished (a faster thread can only have raised it)
+            for (int round = 1;; round++) {
                 bool changed = false;
                 for (int e = gt; e < nedge; e += G) {
                     unsigned ed = edgebuf[e];
@@ -294,11 +293,14 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                         atomicOr(&chg1[ru >> 5], 1u << (ru & 31)); changed = true;
                     }
                 }
-                if (changed) S->flag_more = 1;
+                if (changed) S->flag_more = round;
                 gsync<G>();
                 for (int i = gt; i < cw; i += G) chg0[i] = 0u;  // becomes next round's "this round" map
                 unsigned *tmp = chg0; chg0 = chg1; chg1 = tmp;
-                if (++rounds > total + 2) break;
+                bool more = S->flag_more >= round;
+                rounds = round;
+                gsync<G>();
+                if (!more || round > total + 2) break;
             }
         } else {
             // very large ball: relax straight from the rows in global memory, one warp per node per round
