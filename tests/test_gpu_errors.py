@@ -80,3 +80,28 @@ def test_criminal_capacity_overflow_is_reported():
         # the state is still readable
         after = E.download_state(0)
         assert len(after["co_off"]) <= crim
+
+
+def test_queued_uploads_report_errors_at_sync_and_result_buffers_are_checked():
+    """upload_state(wait=False) returns before the device-side validation ran: the error surfaces at sync() and the
+    ctx stays usable.  Caller-provided result buffers are validated on the host."""
+    import pyproton_oc_b200 as P
+    st = U.micro_net_state()
+    bad = dict(st)
+    bad["col_7"] = st["col_7"].copy()
+    bad["col_7"][0] = 99
+    with _engine(P, st) as E:
+        E.set_params(P.make_params({}))
+        E.upload_state(0, bad, wait=False)
+        with pytest.raises(P.PocError, match="invalid input"):
+            E.sync()
+        E.upload_state(0, st, wait=False)
+        E.sync()
+        got = E.download_agents(0, out=E.agent_buffers(len(st["alive"])))
+        assert np.array_equal(got["age"], st["age"])
+        with pytest.raises(ValueError):
+            E.download_agents(0, out={k: v[:3] for k, v in E.agent_buffers(len(st["alive"])).items()})
+        with pytest.raises(ValueError):
+            E.run_ticks(1, 2, [1], out=np.zeros((1, 3, len(P.REPORTER_NAMES))))
+        rep = np.zeros((1, 2, len(P.REPORTER_NAMES)))
+        assert E.run_ticks(1, 2, [1], out=rep) is rep and rep[0, 1, 0] >= rep[0, 0, 0]

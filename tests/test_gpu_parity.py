@@ -334,8 +334,10 @@ def test_synthetic_100k_matches_oracle(P, O):
 
 # ------------------------------------------------------------------ BASELINE configs 2 and 3 at full length
 @pytest.mark.parametrize("name,overrides", [
+    ("tick_n100_s42_t1", {}),                                                               # config 1 (100 agents, from tick 1)
     ("state_n3000_s42_baseline", {}),                                                       # config 2
     ("state_n10000_s42_sample0", {"intervention": "facilitators", "number_arrests_per_year": 20}),   # config 3, run "0"
+    ("state_n10000_s42_sample1", {"intervention": "baseline", "number_arrests_per_year": 24}),       # config 3, run "1"
     ("state_n10000_s42_sample2", {"intervention": "students", "number_arrests_per_year": 28}),       # config 3, run "2"
 ])
 def test_full_length_runs_match_oracle(P, O, name, overrides):
