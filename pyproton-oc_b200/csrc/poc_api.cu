@@ -163,6 +163,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     // and 20-50 evaluations per tick, so 32-64 blocks per replica let every block take at most one or two items
     // (blocks without work exit at once); 6 blocks of 256 threads are resident per SM
     ctx->gx = (R >= 64) ? 32 : 64;
+    // a small batch of large populations has hundreds of evaluations per replica and tick: enough blocks for every SM
+    if (N > 30000 && R * ctx->gx < 2 * 148) ctx->gx = (2 * 148 + R - 1) / R;
     // embeddedness: a chain of dependent gathers per evaluation, so large batches run one evaluation per warp
     // (about 24 resident per SM) and small ones one per block
     // threads per evaluation (one block each), measured us per tick at 1 / 128 / 512 replicas (profiles/README.md):
@@ -213,7 +215,8 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     DA(d.rp_hdr, (size_t)R * 8); DA(d.rp_u_arrest_count, R); DA(d.philox_key, R);
     DA(d.scr_list, (size_t)d.scr_slots * (N + 1)); DA(d.scr_key, (size_t)R * ctx->gx * (N + 1));
     DA(d.scr_dist, (size_t)emb_slots * (N + 1));
-    DA(d.scr_edges, (size_t)emb_slots * ECAP);
+    d.ecap = (N <= 30000) ? 65536 : 262144;
+    DA(d.scr_edges, (size_t)emb_slots * d.ecap);
     DA(d.reporters, (size_t)R * d.Tcap * POC_N_REPORTERS);
     // staging
     // the 21 staging columns share one device block (and one pinned host mirror for downloads), 8-byte columns first

@@ -61,6 +61,7 @@ struct TickInfo { int tick, epoch, rep, pad; };
 
 struct DevCtx {
     int R, Ncap, Ccap, Mcap, Pcap;  // replicas, agent / crime / member / pair capacities per replica
+    int ecap;                       // staged-edge capacity per embeddedness block (entries)
     int r0, Rg, grp;                // the replica range [r0, r0 + Rg) this launch serves (one range per stream)
     TickInfo *ti;                   // [8] tick state per replica group
     long long ucap, ccap;           // static / criminal entry capacity per replica
@@ -120,7 +121,7 @@ struct DevCtx {
     int32_t *scr_list;              // [slots][Ncap+1]
     double *scr_key;                // [slots][Ncap+1]
     unsigned long long *scr_dist;   // [slots][Ncap+1]
-    unsigned *scr_edges;            // [slots][ECAP] staged induced entries of one embeddedness evaluation
+    unsigned *scr_edges;            // [slots][ecap] staged induced entries of one embeddedness evaluation
     int scr_slots;
     double *reporters;              // [R][Tcap][POC_N_REPORTERS]
     int Tcap;

@@ -17,7 +17,8 @@
 #define EMB_SCALE 17179869184.0 /* 2^34 */
 #define DIST_INF 0x7ff0000000000000ull
 #define RCAP 4096  /* ball size up to which ranks fit the 12-bit fields of a staged edge */
-#define ECAP 65536 /* staged induced entries per evaluation (per-block global scratch, 256 KB) */
+/* staged induced entries per evaluation live in per-block global scratch of C.ecap entries: 64 k (256 KB) up to 30,000
+ * agents, 256 k above (the 300-member OC clique of the 100,000-agent configuration alone is 90 k entries) */
 #define MAX_RADIUS 16
 
 template <int G> struct EmbCfg;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
     int slot = (r * gridDim.x + blockIdx.x) * GPB + gid;
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
-    unsigned *edgebuf = C.scr_edges + (size_t)slot * ECAP;
+    unsigned *edgebuf = C.scr_edges + (size_t)slot * C.ecap;
     const poc_params &P = C.params[r];
     Graph g = graph_of(C, r);
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
                         basep = __shfl_sync(FULL_MASK, basep, 0);
                         if (ok) {
                             int pos = basep + __popc(m & ((1u << lane) - 1));
-                            if (pos < ECAP) edgebuf[pos] = (unsigned)tru | ((unsigned)RANK(v) << 12) | ((unsigned)wgt << 24);
+                            if (pos < C.ecap) edgebuf[pos] = (unsigned)tru | ((unsigned)RANK(v) << 12) | ((unsigned)wgt << 24);
                             else S->over = 1;
                         }
                     }

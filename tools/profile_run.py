@@ -18,13 +18,20 @@ def main():
     ap.add_argument("--warm-ticks", type=int, default=0, help="ticks run before the measured ones (state ages)")
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--repeat", type=int, default=1, help="repeat upload+run and report the fastest")
+    ap.add_argument("--synthetic", type=int, default=0, help="use a synthetic population of this many agents (config 4) instead of the bench workload")
     args = ap.parse_args()
     import bench
     import pyproton_oc_b200 as pkg
     name, st, prm, tick0, mult = bench.load_workload()
+    if args.synthetic:
+        import util as U
+        from pyproton_oc_b200 import synth
+        tpl = U.pre_state(U.load_fixture(U.GOLDEN + "/state_n10000_s42_baseline.npz"))
+        st = synth.synthetic_state(args.synthetic, seed=42, template=tpl, num_oc_persons=30)
+        name, prm, tick0, mult = "synthetic_n%d_s42" % args.synthetic, {}, 1, 0.0
     if args.tick0 is not None:
         tick0 = args.tick0
-    n, stat, crim = pkg.CrimeEngine.capacity_for([st], 160000)
+    n, stat, crim = pkg.CrimeEngine.capacity_for([st], 16 * len(st["alive"]))
     E = pkg.CrimeEngine(args.replicas, n, stat, crim)
     E.set_params(pkg.make_params(prm))
     keys = [r * 7919 + 17 for r in range(args.replicas)]
