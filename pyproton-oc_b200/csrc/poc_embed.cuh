@@ -23,7 +23,7 @@
 
 template <int G> struct EmbCfg;
 template <> struct EmbCfg<256> { static constexpr int DCAP = 2048; };  // distances in shared memory up to this ball size
-template <> struct EmbCfg<1024> { static constexpr int DCAP = 2048; };
+template <> struct EmbCfg<1024> { static constexpr int DCAP = 4096; };  // = RCAP: every staged ball keeps its distances in shared memory
 template <> struct EmbCfg<512> { static constexpr int DCAP = 2048; };
 template <> struct EmbCfg<128> { static constexpr int DCAP = 1024; };
 template <> struct EmbCfg<64> { static constexpr int DCAP = 1024; };
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
 
 static inline size_t emb_smem_bytes(int G, int Ncap) {
     size_t wcap = (size_t)(Ncap + 31) / 32;
-    size_t dcap = (G == 32) ? EmbCfg<32>::DCAP : (G >= 256 ? EmbCfg<256>::DCAP : EmbCfg<128>::DCAP);
+    size_t dcap = (G == 32) ? EmbCfg<32>::DCAP : (G == 1024 ? EmbCfg<1024>::DCAP : (G >= 256 ? EmbCfg<256>::DCAP : EmbCfg<128>::DCAP));
     size_t per_group = (dcap * 8 + ((sizeof(EmbShared) + 7) & ~(size_t)7) + 2 * ((wcap * 4 + 7) & ~(size_t)7) + 15) & ~(size_t)15;
     return 256 * 8 + (size_t)((G == 32) ? 8 : 1) * per_group;
 }
