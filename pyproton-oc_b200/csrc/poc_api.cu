@@ -635,9 +635,10 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
         // weights of one replica in shared memory when they fit (k_draw falls back to the global cdf array otherwise):
         // cells padded to multiples of eight doubles, plus one byte per eight positions
         int nd = max_n(ctx) + 8 * POC_MAX_CELLS;
-        if ((size_t)nd * sizeof(double) + nd / 8 + 16 > 160 * 1024) nd = 0;
+        size_t draw_smem = (size_t)nd * sizeof(double) + nd / 8 + 16;
+        if (draw_smem > 160 * 1024) { nd = 16384; draw_smem = (size_t)nd * sizeof(double) + 16; }   // window mode
         Timed t(ctx, TM_DRAW, s);
-        k_draw<<<D.Rg, ctx->draw_threads, nd ? (size_t)nd * sizeof(double) + nd / 8 + 16 : 0, s>>>(D, nd);
+        k_draw<<<D.Rg, ctx->draw_threads, draw_smem, s>>>(D, nd);
     }
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);

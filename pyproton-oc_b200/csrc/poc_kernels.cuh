@@ -551,7 +551,14 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
         double m = INFINITY;
         bool ng = false;
         int len = off[k + 1] - off[k];
-        for (int i = lane; i < len; i += 32) { double v = wt[woff[k] + i]; m = fmin(m, v); ng |= (v < 0.0); }
+        const double *row = wt + woff[k];
+        for (int base = 0; base < len; base += 256) {   // eight independent loads in flight per lane
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { int i = base + u * 32 + lane; v[u] = (i < len) ? row[i] : INFINITY; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { m = fmin(m, v[u]); ng |= (v[u] < 0.0); }
+        }
         for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL_MASK, m, o));
         ng = __any_sync(FULL_MASK, ng);
         if (lane == 0) { mn[k] = m; neg[k] = ng; }
@@ -626,34 +633,91 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
             if (ncr[k] > 0 && nz[k] > 0) wt_sm[q] = wt_sm[q] / last[k];
         }
     } else {
-        // the two order-defined chains (sum, then cumulative sum of p/sum): one warp per cell, see warp_chain32
-        for (int k = w; k < nc; k += nw) {
-            if (ncr[k] == 0) { if (lane == 0) { nz[k] = 1; last[k] = 1.0; } continue; }
-            int b = off[k], e = off[k + 1];
-            double shift = neg[k] ? mn[k] : 0.0, sump = 0.0;
-            int nzz = 0;
-            for (int base = b; base < e; base += 32) {
-                int i = base + lane;
-                double p = 0.0;
-                if (i < e) { p = cdf[i]; if (neg[k]) { p = p - shift; cdf[i] = p; } }
-                nzz += __popc(__ballot_sync(FULL_MASK, p != 0.0));
-                warp_chain32(p, sump);
-            }
-            double acc = 0.0;
-            if (sump != 0.0)
-                for (int base = b; base < e; base += 32) {
-                    int i = base + lane;
-                    double q = (i < e) ? cdf[i] / sump : 0.0;
-                    double mine = warp_chain32(q, acc);
-                    if (i < e) cdf[i] = mine;
+        // Population too large for shared memory: the weights stay in the global cdf array and the two chains run
+        // over a shared-memory window of W elements per cell (all threads fill the window with coalesced loads, lane
+        // k of warp 0 walks cell k's part, the accumulators carry over from window to window).
+        if (tid < nc) { nzc[tid] = 0; if (ncr[tid] == 0) { nz[tid] = 1; last[tid] = 1.0; } }
+        __syncthreads();
+        for (int k = w; k < nc; k += nw) {   // min-shift and non-zero count, warp per cell
+            if (ncr[k] == 0) continue;
+            int len = off[k + 1] - off[k], cnt = 0;
+            double *row = cdf + off[k];
+            for (int base = 0; base < len; base += 128) {
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { int i = base + u * 32 + lane; x[u] = (i < len) ? row[i] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int i = base + u * 32 + lane;
+                    if (neg[k] && i < len) { x[u] = x[u] - mn[k]; row[i] = x[u]; }
+                    cnt += __popc(__ballot_sync(FULL_MASK, x[u] != 0.0));
                 }
-            if (lane == 0) { nz[k] = (sump == 0.0) ? 0 : nzz; last[k] = acc; }
+            }
+            if (lane == 0) nzc[k] = cnt;
         }
         __syncthreads();
-        for (int k = w; k < nc; k += nw) {
+        const int W = min(1024, (smem_doubles / max(nc, 1) - 1) & ~7);   // window per cell, a multiple of eight
+        const int WS = W + 1;                                             // row stride: odd, so the lanes of the chain warp hit different banks
+        bool act = lane < nc && ncr[lane] > 0;
+        int len = act ? off[lane + 1] - off[lane] : 0, maxlen = len;
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL_MASK, maxlen, o));
+        double *src = wt_sm + lane * WS;
+        for (int pass = 0; pass < 2; pass++) {
+            double acc = 0.0;
+            if (pass == 1 && act && s_sum[lane] == 0.0) len = 0;
+            for (int win = 0; win < maxlen; win += W) {
+                // fill: cell k's elements [win, win + W), zero behind its end (rounded up to the chain's step of 16)
+                for (int k = 0; k < nc; k++) {
+                    if (ncr[k] == 0 || (pass == 1 && s_sum[k] == 0.0)) continue;
+                    int lk = off[k + 1] - off[k] - win;
+                    if (lk <= 0) continue;
+                    int fill = min(W, (lk + 15) & ~15);
+                    double s = (pass == 1) ? s_sum[k] : 1.0;
+                    for (int j = tid; j < fill; j += blockDim.x) {
+                        double x = (j < lk) ? cdf[off[k] + win + j] : 0.0;
+                        wt_sm[k * WS + j] = (pass == 1) ? x / s : x;
+                    }
+                }
+                __syncthreads();
+                if (w == 0) {
+                    int n8 = min(W, (max(len - win, 0) + 7) & ~7);   // this lane's part of the window, padded
+                    int wmax = n8;
+                    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL_MASK, wmax, o));
+                    double xa[8], xb[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) xa[q] = (n8 > 0) ? src[q] : 0.0;
+                    for (int j = 0; j < wmax; j += 16) {
+                        bool sa = j < n8, pb = j + 8 < n8, pa = j + 16 < n8;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) xb[q] = pb ? src[j + 8 + q] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { acc = acc + xa[q]; if (pass == 1 && sa) src[j + q] = acc; }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) xa[q] = pa ? src[j + 16 + q] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { acc = acc + xb[q]; if (pass == 1 && pb) src[j + 8 + q] = acc; }
+                    }
+                }
+                __syncthreads();
+                if (pass == 1) {   // write the cumulative sums of this window back
+                    for (int k = 0; k < nc; k++) {
+                        if (ncr[k] == 0 || s_sum[k] == 0.0) continue;
+                        int lk = min(W, off[k + 1] - off[k] - win);
+                        for (int j = tid; j < lk; j += blockDim.x) cdf[off[k] + win + j] = wt_sm[k * WS + j];
+                    }
+                    __syncthreads();
+                }
+            }
+            if (w == 0) {
+                if (pass == 0) s_sum[lane] = acc;
+                else if (act) { nz[lane] = (s_sum[lane] == 0.0) ? 0 : nzc[lane]; last[lane] = acc; }
+            }
+            __syncthreads();
+        }
+        for (int k = 0; k < nc; k++) {
             if (!(ncr[k] > 0 && nz[k] > 0)) continue;
             double l = last[k];
-            for (int i = off[k] + lane; i < off[k + 1]; i += 32) cdf[i] = cdf[i] / l;
+            for (int i = off[k] + tid; i < off[k + 1]; i += blockDim.x) cdf[i] = cdf[i] / l;
         }
     }
     __syncthreads();
