@@ -247,7 +247,10 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     ctx->ev.resize(EV_POOL); ctx->ev_class.assign(EV_POOL, 0);
     for (auto &evx : ctx->ev) cudaEventCreate(&evx);
     for (auto &m : ctx->marker) cudaEventCreate(&m);
-    ctx->ngroups = 1;  // measured: replica groups on separate streams gain < 12 % even fully independent (profiles/)
+    // replica groups on separate streams: the one-block-per-replica kernels of one group overlap the traversal kernels
+    // of the other.  Measured (profiles/README.md): 512 replicas 851 -> 787 ms per 480-tick run with 2 groups (4: 799),
+    // 128 replicas 641 -> 626 us per tick: two groups from 256 replicas on
+    ctx->ngroups = (R >= 256) ? 2 : 1;
     if (const char *e = getenv("POC_GROUPS")) ctx->ngroups = std::max(1, std::min(8, std::min(R, atoi(e))));
     for (int g = 0; g < ctx->ngroups; g++) cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking);
     for (auto &e : ctx->gev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -747,7 +750,7 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
         d.reporters = p; d.Tcap = n_ticks;
     }
     int n = max_n(ctx);
-    int G = ctx->ngroups;
+    int G = ctx->timing ? 1 : ctx->ngroups;   // per-kernel timing wants the kernels alone on the GPU
     bool report = reporters_out != nullptr;
     for (int g = 0; g < G; g++) { rc = set_tick(ctx, g, tick0, ctx->epoch + 1, 0, ctx->stream); if (rc) return rc; }
     ctx->epoch += n_ticks;

@@ -302,6 +302,34 @@ def test_kernel_shapes_do_not_change_results(P, O, env, monkeypatch):
         assert_state_equal(got[r], S, what="replica %d under %s" % (r, env))
 
 
+def test_large_batch_defaults_equal_single_runs(P):
+    """A batch of 256 replicas takes the large-batch launch shapes (two replica groups on separate streams, 256 threads per
+    embeddedness evaluation, smaller one-block-per-replica kernels): every replica still equals its own single run."""
+    fx = U.load_fixture(U.GOLDEN + "/tick_n1000_s11_oc200_t3.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    R, ticks = 256, 16
+    keys = [1000 + 7 * r for r in range(R)]
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 60000)
+    with P.CrimeEngine(R, n, stat, crim) as E:
+        E.set_params(P.make_params(prm))
+        for r in range(R):
+            E.upload_state(r, st, wait=False)
+        rep = E.run_ticks(3, ticks, keys)
+        got = {r: E.download_state(r) for r in (0, 127, 128, 255)}
+        cn, _ = E.counters()
+    assert (cn[:, 9] == 0).all()
+    for r, g in got.items():
+        with P.CrimeEngine(1, n, stat, crim) as E1:
+            E1.set_params(P.make_params(prm))
+            E1.upload_state(0, st)
+            rep1 = E1.run_ticks(3, ticks, [keys[r]])
+            want = E1.download_state(0)
+        for k in COLS:
+            assert np.array_equal(g[k], want[k]), (r, k)
+        assert np.array_equal(g["col_6"], want["col_6"]) and np.array_equal(g["co_off"], want["co_off"]), r
+        assert np.array_equal(rep[r], rep1[0]), r
+
+
 # ------------------------------------------------------------------ BASELINE config 4: synthetic 100k agents
 def test_synthetic_100k_matches_oracle(P, O):
     """The reference cannot produce this size; parity here is kernel vs CPU restatement,
