@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--replicas", type=int, default=512, help="independent runs per GPU in one batch")
+    ap.add_argument("--replicas", type=int, default=1024, help="independent runs per GPU in one batch")
     ap.add_argument("--ticks", type=int, default=480)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -250,7 +250,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     // replica groups on separate streams: the one-block-per-replica kernels of one group overlap the traversal kernels
     // of the other.  Measured (profiles/README.md): 512 replicas 851 -> 787 ms per 480-tick run with 2 groups (4: 799),
     // 128 replicas 641 -> 626 us per tick: two groups from 256 replicas on
-    ctx->ngroups = (R >= 256) ? 2 : 1;
+    ctx->ngroups = (R >= 1024) ? 4 : (R >= 256) ? 2 : 1;   // 1,024 replicas: 2 groups 1,409 ms per 480 ticks, 4 groups 1,362
     if (const char *e = getenv("POC_GROUPS")) ctx->ngroups = std::max(1, std::min(8, std::min(R, atoi(e))));
     for (int g = 0; g < ctx->ngroups; g++) cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking);
     for (auto &e : ctx->gev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
