@@ -131,7 +131,7 @@ def reference_arm(args):
                              "sample": "oracle/hotpath.c (C restatement; the Python reference cannot travel), one run "
                                        "per process on %d host cores, %d steps" % (procs, args.steps)},
             "e2e": {"value": value, "unit": "agent-ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -141,7 +141,28 @@ def state_bytes(st):
 
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: anything a library prints there while the bench runs (NCCL's
+    version banner, for one) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -323,7 +344,7 @@ def main():
         }
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(st, prm, tick0, T, mult, n_agents)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
