@@ -178,6 +178,11 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay_or
  * reporters_out: [n_replicas][n_ticks][POC_N_REPORTERS] doubles, copied back at the end (may be NULL). */
 #define POC_N_REPORTERS 40 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
 int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *philox_keys, double *reporters_out);
+/* the same, but the reporter rows stay on the device (for a collective over NVLink, run_modes.py:221-232 gathers the
+ * outputs of the runs): *rows_dev points at [n_replicas][*ticks_per_replica][POC_N_REPORTERS] doubles owned by the ctx and
+ * valid until the next run; rows 0..n_ticks-1 of every replica are this run's.  Returns after the run has completed. */
+int poc_run_ticks_device(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *philox_keys, double **rows_dev,
+                         int *ticks_per_replica);
 /* ProtonOC.calculate_fast_reporters, model.py:1687-1735, for the current device state: one row of POC_N_REPORTERS
  * doubles per replica (columns: engine.REPORTER_NAMES). */
 int poc_report(poc_ctx *ctx, double *out /* [n_replicas][POC_N_REPORTERS] */);

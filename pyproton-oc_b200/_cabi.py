@@ -107,6 +107,7 @@ SYMBOLS = {
     "poc_commit_crimes": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "poc_run_ticks": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "poc_report": (C.c_int, [_P, _P]),
+    "poc_run_ticks_device": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "poc_rings": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
     "poc_social_proximity": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "poc_embeddedness": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

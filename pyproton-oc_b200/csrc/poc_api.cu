@@ -738,20 +738,18 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay, c
     return POC_OK;
 }
 
-int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, double *reporters_out) {
-    CHECK_CTX();
+static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, double *reporters_out, bool report) {
     DevCtx &d = ctx->d;
     if (n_ticks < 0) return fail(ctx, POC_ERR_ARG, "poc_run_ticks: n_ticks < 0");
     int rc = upload_replay(ctx, nullptr, keys);
     if (rc) return rc;
-    if (reporters_out && n_ticks > d.Tcap) {
+    if (report && n_ticks > d.Tcap) {
         double *p = nullptr;
         DA(p, (size_t)d.R * n_ticks * POC_N_REPORTERS);
         d.reporters = p; d.Tcap = n_ticks;
     }
     int n = max_n(ctx);
     int G = ctx->timing ? 1 : ctx->ngroups;   // per-kernel timing wants the kernels alone on the GPU
-    bool report = reporters_out != nullptr;
     for (int g = 0; g < G; g++) { rc = set_tick(ctx, g, tick0, ctx->epoch + 1, 0, ctx->stream); if (rc) return rc; }
     ctx->epoch += n_ticks;
     // one tick of every replica group; each group's pipeline on its own stream, forked from / joined to the
@@ -828,6 +826,21 @@ int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, do
                                sizeof(double) * (size_t)n_ticks * POC_N_REPORTERS, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
+    return POC_OK;
+}
+
+int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, double *reporters_out) {
+    CHECK_CTX();
+    return run_ticks_impl(ctx, tick0, n_ticks, keys, reporters_out, reporters_out != nullptr);
+}
+
+int poc_run_ticks_device(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *keys, double **rows_dev, int *ticks_per_replica) {
+    CHECK_CTX();
+    if (!rows_dev || !ticks_per_replica) return fail(ctx, POC_ERR_ARG, "poc_run_ticks_device: NULL output");
+    int rc = run_ticks_impl(ctx, tick0, n_ticks, keys, nullptr, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    *rows_dev = ctx->d.reporters; *ticks_per_replica = ctx->d.Tcap;
     return POC_OK;
 }
 

@@ -247,6 +247,21 @@ class CrimeEngine:
                                       rep.ctypes.data if rep is not None else None))
         return rep
 
+    def run_ticks_device(self, tick0: int, n_ticks: int, philox_keys: Sequence[int]):
+        """run_ticks with the reporter rows left on the device: returns a torch tensor [R, n_ticks, len(REPORTER_NAMES)]
+        that aliases ctx memory (valid until the next run) — what the multi-GPU ensemble hands to the NCCL gather."""
+        import torch
+        keys = np.ascontiguousarray(philox_keys, dtype=np.uint64)
+        assert len(keys) == self.R
+        ptr, tcap = C.c_void_p(), C.c_int(0)
+        self._ck(self.L.poc_run_ticks_device(self.h, tick0, n_ticks, keys.ctypes.data, C.byref(ptr), C.byref(tcap)))
+
+        class _Rows:   # the CUDA array interface is how torch adopts foreign device memory without a copy
+            __cuda_array_interface__ = {"shape": (self.R, tcap.value, N_REPORTERS), "typestr": "<f8", "data": (ptr.value, False),
+                                        "version": 3, "strides": None}
+        t = torch.as_tensor(_Rows(), device=torch.device("cuda", self.device))
+        return t[:, :n_ticks, :]
+
     def report(self) -> np.ndarray:
         """calculate_fast_reporters for the current device state: [R, len(REPORTER_NAMES)]."""
         out = np.zeros((self.R, N_REPORTERS), np.float64)
