@@ -261,3 +261,25 @@ def test_whole_run_distribution_vs_reference(P):
     # against the full reference the out-of-scope phases show up as drift; keep it bounded and on record
     drift = abs(mine["number_crimes"][:, -1].mean() - fx["ref_number_crimes"][:, -1].mean()) / fx["ref_number_crimes"][:, -1].mean()
     assert drift < 0.06
+
+
+def test_reporter_rows_on_the_device_equal_the_downloaded_rows(P):
+    """poc_run_ticks_device leaves the reporter rows in ctx memory (what the multi-GPU gather reads): same numbers as
+    the host copy of poc_run_ticks."""
+    import torch
+    fx = U.load_fixture(U.GOLDEN + "/tick_n1000_s42_t12.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    n, stat, crim = P.CrimeEngine.capacity_for([st, st], 40000)
+    outs = []
+    for mode in ("host", "device"):
+        with P.CrimeEngine(2, n, stat, crim) as E:
+            E.set_params(P.make_params(prm))
+            for r in range(2):
+                E.upload_state(r, st)
+            if mode == "host":
+                outs.append(E.run_ticks(12, 10, [3, 4]))
+            else:
+                rows = E.run_ticks_device(12, 10, [3, 4])
+                assert rows.is_cuda and tuple(rows.shape) == (2, 10, len(P.REPORTER_NAMES))
+                outs.append(rows.cpu().numpy().copy())
+    assert np.array_equal(outs[0], outs[1])
