@@ -5,11 +5,14 @@ import ctypes as C
 import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
 
 import util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -182,3 +185,23 @@ def test_person_api_builds_the_same_state_as_the_fixture_helper():
     assert np.array_equal(got["co_off"], want["co_off"])
     # the reference's parent link is one-directional offspring + reverse parent (entities.py:206-215)
     assert ag[5].neighbors["offspring"] == {ag[0]} and ag[0].neighbors["parent"] == {ag[5]}
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: one JSON line on stdout (library chatter goes to stderr), with the reference-arm keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ticks", "12"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "agent-ticks/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "agent-ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works and prints
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--ticks", "12"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
