@@ -172,6 +172,12 @@ def main(argv):
     # many OC members at 1000 agents so OC-initiated crimes and embeddedness dominate
     run_case("n1000_s11_oc200", 1000, 11, [3, 15, 40],
              overrides={"num_oc_persons": 300, "num_oc_families": 8}, only=only)
+    # late in a run: twenty simulated years of the reference's own demography, arrests and co-offending behind it
+    # (one-sided clears, a dense criminal layer, negative tendencies)
+    run_case("n1000_s5_late", 1000, 5, [240, 252], tend_ticks=[240], only=only)
+    # ... and the same with a large OC population, where arrests, recruitment and embeddedness have been busy for ten years
+    run_case("n1000_s13_oc150_late", 1000, 13, [120, 121], tend_ticks=[120],
+             overrides={"num_oc_persons": 150, "num_oc_families": 8}, only=only)
 
 
 if __name__ == "__main__":
