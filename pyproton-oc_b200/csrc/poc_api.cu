@@ -135,6 +135,8 @@ const char *poc_last_error(poc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err
 int poc_sizeof_params(void) { return (int)sizeof(poc_params); }
 int poc_sizeof_tick_out(void) { return (int)sizeof(poc_tick_out); }
 
+static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_static_entries, int64_t max_criminal_entries);
+
 int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_static_entries,
                    int64_t max_criminal_entries, poc_ctx **out) {
     if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 23) || max_static_entries < 0 || max_criminal_entries < 0)
@@ -146,8 +148,19 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     poc_ctx *ctx = new poc_ctx();
     ctx->device = device;
     cudaSetDevice(device);
+    int rc = ctx_init(ctx, n_replicas, max_agents, max_static_entries, max_criminal_entries);
+    if (rc) {   // release whatever was created; the message survives in the library-wide slot
+        if (!ctx->err.empty()) g_err = ctx->err;
+        poc_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return POC_OK;
+}
+
+static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_static_entries, int64_t max_criminal_entries) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return fail(nullptr, POC_ERR_CUDA, cudaGetErrorString(e));
     DevCtx &d = ctx->d;
     int R = n_replicas, N = max_agents;
     d.R = R; d.Ncap = N; d.r0 = 0; d.Rg = R;
@@ -186,7 +199,7 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     size_t wcap = (size_t)(N + 31) / 32;
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
     ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
-    if (ctx->smem_emb + 2 * 1024 > 220 * 1024) { delete ctx; return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps"); }
+    if (ctx->smem_emb + 2 * 1024 > 220 * 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
     size_t RN = (size_t)R * N;
     DA(d.n_agents, R);
     DA(d.attr, RN); DA(d.birth, RN); DA(d.ncrimes, RN); DA(d.ncrimes_tick, RN); DA(d.father, RN); DA(d.new_recruit, RN);
@@ -230,9 +243,9 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
         DA(ctx->stage_dev, o);
         for (int b = 0; b < 2; b++) {
             cudaEventCreateWithFlags(&ctx->stage_ev2[b], cudaEventDisableTiming);
-            if (cudaHostAlloc((void **)&ctx->stage_host2[b], o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
+            if (cudaHostAlloc((void **)&ctx->stage_host2[b], o, cudaHostAllocDefault) != cudaSuccess) return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed");
         }
-        if (cudaHostAlloc((void **)&ctx->stage_host, o, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed"); }
+        if (cudaHostAlloc((void **)&ctx->stage_host, o, cudaHostAllocDefault) != cudaSuccess) return fail(nullptr, POC_ERR_CUDA, "cudaHostAlloc failed");
         k = 0;
 #define PT(f, T) s.f = (T *)(ctx->stage_dev + ctx->stage_off[k++]);
         POC_STAGE_COLS(PT)
@@ -270,23 +283,24 @@ int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_stati
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     CU(cudaStreamSynchronize(ctx->stream));
-    *out = ctx;
     return POC_OK;
 }
 
 int poc_ctx_destroy(poc_ctx *ctx) {
     if (!ctx) return POC_ERR_ARG;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     for (int b = 0; b < 2; b++) { if (ctx->stage_host2[b]) cudaFreeHost(ctx->stage_host2[b]); if (ctx->stage_ev2[b]) cudaEventDestroy(ctx->stage_ev2[b]); }
-    for (auto &evx : ctx->ev) cudaEventDestroy(evx);
-    for (auto &m : ctx->marker) cudaEventDestroy(m);
-    for (int g = 0; g < ctx->ngroups; g++) cudaStreamDestroy(ctx->gstream[g]);
-    for (auto &e : ctx->gev) cudaEventDestroy(e);
-    for (auto &e : ctx->gstag) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    // (a ctx whose creation failed half-way comes through here too: every handle may still be null)
+    for (auto &evx : ctx->ev) if (evx) cudaEventDestroy(evx);
+    for (auto &m : ctx->marker) if (m) cudaEventDestroy(m);
+    for (int g = 0; g < 8; g++) if (ctx->gstream[g]) cudaStreamDestroy(ctx->gstream[g]);
+    for (auto &e : ctx->gev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->gstag) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();   // leave no stale error behind for the next ctx of this thread
     delete ctx;
     return POC_OK;
 }

@@ -105,3 +105,14 @@ def test_queued_uploads_report_errors_at_sync_and_result_buffers_are_checked():
             E.run_ticks(1, 2, [1], out=np.zeros((1, 3, len(P.REPORTER_NAMES))))
         rep = np.zeros((1, 2, len(P.REPORTER_NAMES)))
         assert E.run_ticks(1, 2, [1], out=rep) is rep and rep[0, 1, 0] >= rep[0, 0, 0]
+
+
+def test_failed_ctx_creation_releases_everything_and_keeps_its_message():
+    import pyproton_oc_b200 as P
+    st = U.micro_net_state()
+    with pytest.raises(P.PocError, match="shared-memory"):
+        P.CrimeEngine(1, 2_000_000, 10, 10)          # fails half-way through poc_ctx_create
+    with _engine(P, st) as E:                          # the next ctx of this process is unaffected
+        E.set_params(P.make_params({}))
+        E.upload_state(0, st)
+        assert E.rings([0], 2, True)[0].tolist() == [6]
