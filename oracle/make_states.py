@@ -49,6 +49,8 @@ def main(argv):
     cases = [c + (0,) for c in cases]
     # the 10k state a quarter into the second year (friendship layer grown to ~8.9 per agent): bench workload
     cases.append(("state_n10000_s42_t13", 10000, 42, None, 12))
+    # four years in: arrests, recruitment, deaths and births of the reference itself behind the exported state
+    cases.append(("state_n10000_s42_t49", 10000, 42, None, 48))
     for name, n, seed, ov, steps in cases:
         if only and not name.startswith(only):
             continue

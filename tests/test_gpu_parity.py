@@ -367,6 +367,7 @@ def test_synthetic_100k_matches_oracle(P, O):
     ("state_n10000_s42_sample0", {"intervention": "facilitators", "number_arrests_per_year": 20}),   # config 3, run "0"
     ("state_n10000_s42_sample1", {"intervention": "baseline", "number_arrests_per_year": 24}),       # config 3, run "1"
     ("state_n10000_s42_sample2", {"intervention": "students", "number_arrests_per_year": 28}),       # config 3, run "2"
+    ("state_n10000_s42_t49", {}),                                         # 10k agents, four reference years in (from tick 49)
 ])
 def test_full_length_runs_match_oracle(P, O, name, overrides):
     """480 ticks of the hot path from the reference's own setup state: final state, criminal layer and the
@@ -380,11 +381,12 @@ def test_full_length_runs_match_oracle(P, O, name, overrides):
     m.choose_intervention_setting()
     prm = {k: getattr(m, k) for k in P.HOT_PATH_DEFAULTS}
     ticks, key = 480, 20261020
+    tick0 = int(fx["tick"]) if "tick" in fx and not name.startswith("tick_") else 1
     S = O.OracleState(st)
     OP = O.make_params(prm)
-    mult, crimes, oc_series = 0.0, 0, []
+    mult, crimes, oc_series = float(fx["crime_multiplier"]) if tick0 > 1 else 0.0, 0, []
     for t in range(ticks):
-        mult, tot = S.run_ticks(OP, 1 + t, 1, key, mult)
+        mult, tot = S.run_ticks(OP, tick0 + t, 1, key, mult)
         crimes += int(tot[0])
         if t % 60 == 59:
             c = S.cols()
@@ -392,7 +394,9 @@ def test_full_length_runs_match_oracle(P, O, name, overrides):
     with engine_for(P, [st], crim_headroom=400000) as E:
         E.set_params(P.make_params(prm))
         E.upload_state(0, st)
-        rep = E.run_ticks(1, ticks, [key])
+        if tick0 > 1:
+            E.set_crime_multiplier(float(fx["crime_multiplier"]))
+        rep = E.run_ticks(tick0, ticks, [key])
         after = E.download_state(0)
         cn, _ = E.counters()
     assert cn[0, 9] == 0
