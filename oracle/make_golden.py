@@ -95,6 +95,19 @@ def pack_tick(model, h: dict) -> dict:
     out["emb_accumulated"] = np.array([v for _, v, _ in rec["emb"]], dtype=np.float64)
     out["emb_fresh"] = np.array([v for _, _, v in rec["emb"]], dtype=np.float64)
     out["arrested"] = np.array([slot_of[u] for u in rec["arrested"]], dtype=np.int32)
+    # meta-edge direction winners on pairs with asymmetric multiplicities: (evaluation index, slot a, slot b, multiplicity)
+    out["emb_over"] = np.array([(j, slot_of[a], slot_of[b], m) for j, a, b, m in rec.get("emb_over", [])],
+                               dtype=np.int32).reshape(-1, 4)
+    return out
+
+
+def pack_report(model, h: dict) -> dict:
+    """State at the end of a reference step() and the reporter values it collected from it (model.py:286-287)."""
+    out = _pack_state("pre_", h["end"])
+    out.update(_params(model))
+    for k, v in h["end_reporters"].items():
+        out["rep_" + k] = np.float64(v)
+    out["tick"] = np.int32(model.tick)
     return out
 
 
@@ -121,7 +134,7 @@ def save(name: str, d: dict):
 
 
 def run_case(prefix, n_agents, seed, ticks_to_record, overrides=None, tend_ticks=(), pre_setup=None, post_setup=None,
-             only=None):
+             only=None, rep_ticks=()):
     names = ["tick_%s_t%d" % (prefix, t) for t in ticks_to_record] + ["tend_%s_t%d" % (prefix, t) for t in tend_ticks]
     if only and not any(n.startswith(only) for n in names):
         return
@@ -147,37 +160,63 @@ def run_case(prefix, n_agents, seed, ticks_to_record, overrides=None, tend_ticks
         if tick in ticks_to_record:
             h = H.step_with_recording(model)
             save("tick_%s_t%d" % (prefix, tick), pack_tick(model, h))
+            if tick in rep_ticks:
+                save("rep_%s_t%d" % (prefix, tick), pack_report(model, h))
         else:
             model.step()
 
 
 def main(argv):
+    """argv[1]: only fixtures whose name starts with this prefix; `case:<prefix>` selects one run_case by its prefix
+    (so that the cases can be generated by parallel processes)."""
     only = argv[1] if len(argv) > 1 else None
+    case = None
+    if only and only.startswith("case:"):
+        case, only = only[5:], None
+
+    def rc(prefix, *a, **kw):
+        if case is None or prefix == case:
+            run_case(prefix, *a, only=only, **kw)
+
     # config 1 of BASELINE.json: 100 agents, seed 42
-    run_case("n100_s42", 100, 42, [1, 12, 60], tend_ticks=[1, 12], only=only)
+    rc("n100_s42", 100, 42, [1, 12, 60], tend_ticks=[1, 12], rep_ticks=[12, 60])
     # 1000 agents: early ticks, yearly tick, and a later tick with OC growth
-    run_case("n1000_s42", 1000, 42, [1, 5, 12, 13, 120], tend_ticks=[1, 12, 120], only=only)
+    rc("n1000_s42", 1000, 42, [1, 5, 12, 13, 120], tend_ticks=[1, 12, 120], rep_ticks=[13, 120])
     # 3000 agents (config 2): embeddedness evaluations appear
-    run_case("n3000_s42", 3000, 42, [1, 24, 30], tend_ticks=[1], only=only)
+    rc("n3000_s42", 3000, 42, [1, 24, 30], tend_ticks=[1], rep_ticks=[24])
     # facilitator repression active every tick from 13 (model.py:1326-1336)
-    run_case("n1000_s7_facilitators", 1000, 7, [13, 20], overrides={"intervention": "facilitators"}, only=only)
+    rc("n1000_s7_facilitators", 1000, 7, [13, 20], overrides={"intervention": "facilitators"})
     # OC-boss repression (model.py:1293-1302), more OC members so the regime is exercised
-    run_case("n1000_s7_disruptive_strong", 1000, 7, [14, 25],
-             overrides={"intervention": "disruptive-strong", "num_oc_persons": 200, "num_oc_families": 30}, only=only)
+    rc("n1000_s7_disruptive_strong", 1000, 7, [14, 25],
+       overrides={"intervention": "disruptive-strong", "num_oc_persons": 200, "num_oc_families": 30}, rep_ticks=[25])
 
     # the reference's own test_big_crimes_from_small_fish setting (test_protonoc.py:103-114)
     def big_post(model):
         model.num_co_offenders_dist = [[5, 0.5], [6, 0.5], [10, 0.5]]
-    run_case("n500_s3_radius6", 500, 3, [2, 7], overrides={"max_accomplice_radius": 6}, post_setup=big_post, only=only)
+    rc("n500_s3_radius6", 500, 3, [2, 7], overrides={"max_accomplice_radius": 6}, post_setup=big_post)
     # many OC members at 1000 agents so OC-initiated crimes and embeddedness dominate
-    run_case("n1000_s11_oc200", 1000, 11, [3, 15, 40],
-             overrides={"num_oc_persons": 300, "num_oc_families": 8}, only=only)
+    rc("n1000_s11_oc200", 1000, 11, [3, 15, 40], overrides={"num_oc_persons": 300, "num_oc_families": 8})
     # late in a run: twenty simulated years of the reference's own demography, arrests and co-offending behind it
     # (one-sided clears, a dense criminal layer, negative tendencies)
-    run_case("n1000_s5_late", 1000, 5, [240, 252], tend_ticks=[240], only=only)
+    rc("n1000_s5_late", 1000, 5, [240, 252], tend_ticks=[240], rep_ticks=[252])
     # ... and the same with a large OC population, where arrests, recruitment and embeddedness have been busy for ten years
-    run_case("n1000_s13_oc150_late", 1000, 13, [120, 121], tend_ticks=[120],
-             overrides={"num_oc_persons": 150, "num_oc_families": 8}, only=only)
+    rc("n1000_s13_oc150_late", 1000, 13, [120, 121], tend_ticks=[120],
+       overrides={"num_oc_persons": 150, "num_oc_families": 8})
+
+    # ---- round 2: the OC-initiated branch (the crimes that recruit, entities.py:465-467) and full-size states
+    # group sizes skewed to large groups so that most crimes search for accomplices; 300 of 1,000 agents in OC families
+    def skew_post(model):
+        model.num_co_offenders_dist = [[1, 0.15], [2, 0.3], [3, 0.25], [4, 0.15], [5, 0.1], [6, 0.05]]
+    rc("n1000_s17_oc300_big", 1000, 17, list(range(2, 14)), overrides={"num_oc_persons": 300, "num_oc_families": 8},
+       post_setup=skew_post)
+    rc("n3000_s19_oc300_big", 3000, 19, [2, 3, 4, 5], overrides={"num_oc_persons": 300, "num_oc_families": 24},
+       post_setup=skew_post)
+    # BASELINE config 3/5 size: 10,000 agents, baseline parameters, a quarter into the second year (= the bench workload
+    # state_n10000_s42_t13) and the tick after it; tendency at setup and at the first yearly pass
+    rc("n10000_s42", 10000, 42, [13, 14], tend_ticks=[1, 12], rep_ticks=[13])
+    # samples/sample_json.json run "0": 80 OC members in 16 families, facilitator repression
+    rc("n10000_s42_sample0", 10000, 42, [1, 2, 13],
+       overrides={"intervention": "facilitators", "num_oc_persons": 80, "number_arrests_per_year": 20, "num_oc_families": 16})
 
 
 if __name__ == "__main__":

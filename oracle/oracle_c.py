@@ -137,6 +137,8 @@ def lib():
         L.orc_embeddedness_ex.restype = C.c_double
         L.orc_embeddedness_ex.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reset_embeddedness.argtypes = [C.c_void_p]
+        L.orc_embeddedness_accumulated.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_preload_embeddedness.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_candidate_weight.restype = C.c_double
         L.orc_candidate_weight.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.orc_find_accomplices.restype = C.c_int32
@@ -297,6 +299,22 @@ class OracleState:
         v = float(self.L.orc_embeddedness_ex(self.h, a, radius, ball.ctypes.data, dist.ctypes.data, C.byref(nb),
                                              C.byref(nasym)))
         return v, ball[:nb.value].copy(), dist[:nb.value].copy(), int(nasym.value)
+
+    def embeddedness_accumulated(self, slots, radius: int = 2, over=None) -> np.ndarray:
+        """H1 exact mode: the evaluations `slots`, in this order, on the accumulating meta graph (model.py:1515-1536).
+        over: int32 [m, 4] rows (evaluation index, a, b, multiplicity in use), see hotpath.c."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        ov = np.zeros((0, 4), np.int32) if over is None else np.ascontiguousarray(over, dtype=np.int32).reshape(-1, 4)
+        ov = np.ascontiguousarray(ov[np.argsort(ov[:, 0], kind="stable")])
+        out = np.zeros(len(slots), np.float64)
+        self.L.orc_embeddedness_accumulated(self.h, len(slots), slots.ctypes.data, radius, len(ov), ov.ctypes.data, out.ctypes.data)
+        return out
+
+    def preload_embeddedness(self, slots, vals):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        assert len(slots) == len(vals)
+        self.L.orc_preload_embeddedness(self.h, len(slots), slots.ctypes.data, vals.ctypes.data)
 
     def reset_embeddedness(self):
         self.L.orc_reset_embeddedness(self.h)

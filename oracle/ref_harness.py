@@ -257,7 +257,7 @@ def record_commit_crimes(model) -> dict:
     ref_model, ref_entities, ref_extra = load_reference()
     import networkx as nx
     Person = ref_entities.Person
-    rec: dict = {"crimes": [], "emb": [], "arrested": []}
+    rec: dict = {"crimes": [], "emb": [], "arrested": [], "emb_over": []}
     rng = RecordingRNG(model.random)
     real_rng = model.random
     model.random = rng
@@ -267,7 +267,35 @@ def record_commit_crimes(model) -> dict:
     orig_atd = Person.agents_at_distance
     orig_cw = Person.candidates_weight
     orig_caught = Person.get_caught
+    orig_uml = model.update_meta_links
     cur: dict = {}
+    fresh_flag = {"on": False}
+
+    def update_meta_links(agents):
+        """model.py:1515-1536 unchanged; afterwards note, for every directed entry a->b inside the ball whose stored
+        meta-edge weight is NOT 1/w(a->b), that the other direction's multiplicity won (nx.Graph.add_edge keeps the
+        direction the set iteration visited last): the one place where the reference's own value depends on
+        CPython set order.  Recorded as (evaluation index, a, b, multiplicity in use)."""
+        orig_uml(agents)
+        if fresh_flag["on"]:
+            return
+        j = len(rec["emb"])
+        G = model.meta_graph
+        for a in agents:
+            for b in a.agents_in_radius(1):
+                if b is a or b not in agents:
+                    continue
+                w = 0
+                for net in Person.network_names:
+                    if b in a.neighbors.get(net):
+                        if net == "criminal":
+                            if b in a.num_co_offenses:
+                                w += a.num_co_offenses[b]
+                        else:
+                            w += 1
+                stored = G[a.unique_id][b.unique_id]["weight"]
+                if stored != 1 / w:
+                    rec["emb_over"].append((j, a.unique_id, b.unique_id, int(round(1 / stored))))
 
     def find_accomplices(self, n):
         cur.clear()
@@ -304,7 +332,11 @@ def record_commit_crimes(model) -> dict:
     def oc_embeddedness(self):
         miss = self.cached_oc_embeddedness is None
         if miss:
-            fresh = fresh_embeddedness(self, nx, orig_emb)
+            fresh_flag["on"] = True
+            try:
+                fresh = fresh_embeddedness(self, nx, orig_emb)
+            finally:
+                fresh_flag["on"] = False
         v = orig_emb(self)
         if miss:
             rec["emb"].append((self.unique_id, float(v), fresh))
@@ -319,6 +351,7 @@ def record_commit_crimes(model) -> dict:
     Person.agents_at_distance = agents_at_distance
     Person.candidates_weight = candidates_weight
     Person.get_caught = get_caught
+    model.update_meta_links = update_meta_links
     try:
         model.reset_oc_embeddedness()
         model.commit_crimes()
@@ -328,6 +361,7 @@ def record_commit_crimes(model) -> dict:
         Person.agents_at_distance = orig_atd
         Person.candidates_weight = orig_cw
         Person.get_caught = orig_caught
+        del model.update_meta_links
         model.random = real_rng
     rec["rng_log"] = rng.log
     return rec
@@ -362,7 +396,26 @@ def step_with_recording(model) -> dict:
     finally:
         model.reset_oc_embeddedness = orig_reset
         model.commit_crimes = orig_commit
+    holder["end"] = export_state(model)          # the state calculate_fast_reporters (model.py:286) has just summarised
+    holder["end_reporters"] = fast_reporters(model)
     return holder
+
+
+FAST_REPORTERS = ["number_crimes_committed_of_persons", "current_oc_members", "current_num_persons",
+                  "criminal_tendency_mean", "criminal_tencency_sd", "age_mean", "age_sd", "education_level_mean",
+                  "education_level_sd", "num_crime_committed_mean", "num_crime_committed_sd",
+                  "crimes_committed_by_oc_this_tick", "current_prisoners", "employed", "facilitators",
+                  "tot_friendship_link", "tot_household_link", "tot_partner_link", "tot_offspring_link",
+                  "tot_criminal_link", "tot_school_link", "tot_professional_link", "tot_sibling_link",
+                  "tot_parent_link", "number_students", "number_crimes", "crime_size_fails", "facilitator_crimes",
+                  "facilitator_fails", "big_crime_from_small_fish", "number_offspring_recruited_this_tick",
+                  "number_protected_recruited_this_tick", "people_jailed", "number_law_interventions_this_tick",
+                  "crime_multiplier", "tick"]
+
+
+def fast_reporters(model) -> Dict[str, float]:
+    """The values ProtonOC.calculate_fast_reporters (model.py:1687-1735) and the hot-path counters hold right now."""
+    return {k: float(getattr(model, k)) for k in FAST_REPORTERS}
 
 
 def replay_from_record(rec: dict, slot_of: Dict[int, int]) -> dict:

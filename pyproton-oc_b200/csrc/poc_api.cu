@@ -34,7 +34,9 @@ struct poc_ctx {
     int gx = 4;            // blocks per replica of the search grid (and of the block-per-evaluation embeddedness grid)
     int emb_g = 256;       // threads per embeddedness evaluation: 256 (block) for small batches, 32 (warp) for large ones
     int emb_gx = 4;        // blocks per replica of the embeddedness grid
-    size_t smem_search = 0, smem_emb = 0;
+    size_t smem_search = 0, smem_emb = 0, smem_emb2 = 0;
+    int emb_blocks = 8;    // resident blocks per SM the second formulation is compiled / sized for
+    int emb_v = 2;         // embeddedness formulation: 2 = poc_embed2.cuh (level-ordered stage-and-relax), 1 = poc_embed.cuh
     // staging
     StageCols stage{};
     uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
@@ -200,6 +202,21 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
     ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
     if (ctx->smem_emb + 2 * 1024 > 220 * 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
+    if (const char *e = getenv("POC_EMB_V")) ctx->emb_v = (atoi(e) == 1) ? 1 : 2;
+    if (ctx->emb_g == 32) ctx->emb_v = 1;   // the warp-per-evaluation variant exists in the first formulation only
+    {
+        // second formulation: the block's dynamic shared memory is whatever its share of the SM allows (227 KB per SM,
+        // 1 KB reserved per block) at the residency its block size permits; the kernel splits it into distances + staged entries
+        int g = ctx->emb_g, blocks = (g == 1024) ? 2 : (g == 512) ? 4 : (g == 256) ? 8 : 12;
+        if (g == 64) { g = ctx->emb_g = 128; ctx->smem_emb = emb_smem_bytes(128, N); }
+        if (const char *e = getenv("POC_EMB_BLOCKS")) blocks = std::max(1, std::min(16, atoi(e)));
+        size_t fixed = emb2_fixed_bytes(g, N);
+        size_t share = ((size_t)227 * 1024 / blocks - 1024) & ~(size_t)15;
+        while (blocks > 1 && share < fixed + 8 * 1024) { blocks--; share = ((size_t)227 * 1024 / blocks - 1024) & ~(size_t)15; }
+        if (share < fixed + 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
+        ctx->smem_emb2 = share;
+        ctx->emb_blocks = blocks;
+    }
     size_t RN = (size_t)R * N;
     DA(d.n_agents, R);
     DA(d.attr, RN); DA(d.birth, RN); DA(d.ncrimes, RN); DA(d.ncrimes_tick, RN); DA(d.father, RN); DA(d.new_recruit, RN);
@@ -231,6 +248,15 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     d.ecap = (N <= 30000) ? 65536 : 262144;
     DA(d.scr_edges, (size_t)emb_slots * d.ecap);
     DA(d.reporters, (size_t)R * d.Tcap * POC_N_REPORTERS);
+    {
+        double *iw = nullptr, h[256];
+        DA(iw, 256);
+        h[0] = 0.0;
+        for (int i = 1; i < 256; i++) h[i] = 1.0 / (double)i;
+        CU(cudaMemcpyAsync(iw, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        d.invw = iw;
+    }
     // staging
     // the 21 staging columns share one device block (and one pinned host mirror for downloads), 8-byte columns first
     StageCols &s = ctx->stage;
@@ -280,6 +306,9 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     cudaFuncSetAttribute(k_embeddedness<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(1024, N));
     cudaFuncSetAttribute(k_embeddedness<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(128, N));
     cudaFuncSetAttribute(k_embeddedness<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(256, N));
+#define EMB2_ATTR(G, MB) cudaFuncSetAttribute(k_emb2<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb2)
+    EMB2_ATTR(128, 12); EMB2_ATTR(256, 8); EMB2_ATTR(256, 6); EMB2_ATTR(256, 5); EMB2_ATTR(512, 4); EMB2_ATTR(512, 3); EMB2_ATTR(1024, 2); EMB2_ATTR(1024, 1);
+#undef EMB2_ATTR
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -624,6 +653,16 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
 
 static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity) {
     dim3 grid(ctx->emb_gx, D.Rg);
+    if (ctx->emb_v == 2) {
+        int sm = (int)ctx->smem_emb2, mb = ctx->emb_blocks;
+        if (ctx->emb_g == 128) k_emb2<128, 12><<<grid, 128, sm, s>>>(D, parity, sm);
+        else if (ctx->emb_g == 512) { if (mb >= 4) k_emb2<512, 4><<<grid, 512, sm, s>>>(D, parity, sm); else k_emb2<512, 3><<<grid, 512, sm, s>>>(D, parity, sm); }
+        else if (ctx->emb_g == 1024) { if (mb >= 2) k_emb2<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm); else k_emb2<1024, 1><<<grid, 1024, sm, s>>>(D, parity, sm); }
+        else if (mb >= 8) k_emb2<256, 8><<<grid, 256, sm, s>>>(D, parity, sm);
+        else if (mb >= 6) k_emb2<256, 6><<<grid, 256, sm, s>>>(D, parity, sm);
+        else k_emb2<256, 5><<<grid, 256, sm, s>>>(D, parity, sm);
+        return;
+    }
     if (ctx->emb_g == 32) k_embeddedness<32><<<grid, 256, ctx->smem_emb, s>>>(D, parity);
     else if (ctx->emb_g == 64) k_embeddedness<64><<<grid, 64, ctx->smem_emb, s>>>(D, parity);
     else if (ctx->emb_g == 128) k_embeddedness<128><<<grid, 128, ctx->smem_emb, s>>>(D, parity);

@@ -122,6 +122,7 @@ struct DevCtx {
     double *scr_key;                // [slots][Ncap+1]
     unsigned long long *scr_dist;   // [slots][Ncap+1]
     unsigned *scr_edges;            // [slots][ecap] staged induced entries of one embeddedness evaluation
+    const double *invw;             // [256] 1.0 / i (meta-edge weight of multiplicity i, model.py:1536)
     int scr_slots;
     double *reporters;              // [R][Tcap][POC_N_REPORTERS]
     int Tcap;

@@ -67,16 +67,16 @@ template <int G> __device__ __forceinline__ int group_exscan(int v, int *ws, int
 
 // Frontier BFS for one group (same algorithm as bfs_levels in poc_device.cuh, group-relative).
 template <int G>
-__device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list, int depth, EmbShared *S,
+__device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list, int depth, EmbShared *, int &s_count, int *s_lvl_off,
                          unsigned long long &edges, unsigned long long &rowbytes) {
     int gt = threadIdx.x % G, lane = threadIdx.x & 31, w = gt >> 5;
     constexpr int NW = G / 32;
     for (int i = gt; i < nwords; i += G) bitmap[i] = 0u;
     gsync<G>();
-    if (gt == 0) { int v = list[0]; bitmap[v >> 5] = 1u << (v & 31); S->count = 1; S->lvl_off[0] = 0; S->lvl_off[1] = 1; }
+    if (gt == 0) { int v = list[0]; bitmap[v >> 5] = 1u << (v & 31); s_count = 1; s_lvl_off[0] = 0; s_lvl_off[1] = 1; }
     gsync<G>();
     for (int lvl = 1; lvl <= depth; lvl++) {
-        int fb = S->lvl_off[lvl - 1], fe = S->lvl_off[lvl];
+        int fb = s_lvl_off[lvl - 1], fe = s_lvl_off[lvl];
         for (int f0 = fb; f0 < fe; f0 += 32 * NW) {
             int fi = f0 + lane * NW + w;
             int b0 = 0, len0 = 0, b1 = 0, len1 = 0;
@@ -112,17 +112,17 @@ __device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list
                 unsigned m = __ballot_sync(FULL_MASK, isnew);
                 if (m) {
                     int pos = 0;
-                    if (lane == 0) pos = atomicAdd(&S->count, __popc(m));
+                    if (lane == 0) pos = atomicAdd(&s_count, __popc(m));
                     pos = __shfl_sync(FULL_MASK, pos, 0);
                     if (isnew) list[pos + __popc(m & ((1u << lane) - 1))] = v;
                 }
             }
         }
         gsync<G>();
-        if (gt == 0) S->lvl_off[lvl + 1] = S->count;
+        if (gt == 0) s_lvl_off[lvl + 1] = s_count;
         gsync<G>();
     }
-    return S->lvl_off[depth + 1];
+    return s_lvl_off[depth + 1];
 }
 
 template <int G>
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
         gsync<G>();
         bfsbytes = 0;
         unsigned long long ib = 0;  // algorithmic bytes of this evaluation
-        int total = bfs_group<G>(g, nwords, bitmap, list, R, S, edges, bfsbytes);
+        int total = bfs_group<G>(g, nwords, bitmap, list, R, S, S->count, S->lvl_off, edges, bfsbytes);
         nreq++;
         bool anyoc = false;
         for (int i = 1 + gt; i < total; i += G) anyoc |= (attr[list[i]] & F_OC) != 0;

@@ -6,6 +6,7 @@
 
 #define RP(ptr, r, stride) ((ptr) + (size_t)(r) * (size_t)(stride))
 #include "poc_embed.cuh"
+#include "poc_embed2.cuh"
 
 // ============================================================================ state I/O
 struct StageCols {
