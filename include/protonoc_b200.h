@@ -150,6 +150,16 @@ int poc_upload_agents(poc_ctx *ctx, int replica, int n, const poc_agent_cols *co
  * reported, when poc_build_graph (which synchronises) returns. */
 int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr, const int32_t *col,
                      const int32_t *co_off_or_null);
+/* Packed state: one contiguous host block per state (header, the agent columns, nine {rowptr, col} pairs, co-offence
+ * counts) built once with poc_pack_state and uploaded with ONE copy per replica by poc_upload_packed -- how an
+ * ensemble driver (run_modes.py:221-232) hands hundreds of initial states to one ctx.  poc_packed_size: bytes needed
+ * for n agents with n_entries[l] directed entries in layer l.  poc_upload_packed is asynchronous (the block must stay
+ * valid until poc_sync, which also reports what the device-side input checks found); pinned memory makes the copy
+ * overlap the unpacking of the previous replica. */
+int64_t poc_packed_size(int n, const int64_t *n_entries /* [POC_NUM_LAYERS] */);
+int poc_pack_state(int n, const poc_agent_cols *cols, const int32_t *const *rowptr, const int32_t *const *col,
+                   const int32_t *co_off_or_null, void *block, int64_t block_bytes);
+int poc_upload_packed(poc_ctx *ctx, int replica, const void *block, int64_t block_bytes);
 /* merge the eight non-criminal layers into the packed multiplex CSR the kernels traverse */
 int poc_build_graph(poc_ctx *ctx, int replica);
 /* the same without waiting: the uploads of the next replica queue up behind this one.  Caller-owned page-locked
@@ -196,6 +206,16 @@ int poc_rings(poc_ctx *ctx, int replica, int n_src, const int32_t *src, int d, i
 int poc_social_proximity(poc_ctx *ctx, int replica, int n_pairs, const int32_t *a, const int32_t *b, double *out);
 /* Person.oc_embeddedness, entities.py:526-558 (own-ball meta graph) */
 int poc_embeddedness(poc_ctx *ctx, int replica, int n, const int32_t *agents, double *out);
+/* Person.oc_embeddedness exactly as the reference computes it inside one commit_crimes (test hook): the
+ * evaluations `agents`, IN THIS ORDER, on the tick-global meta graph that every evaluation adds its ball to
+ * (model.py:709-718, 1515-1536; entities.py:545-558).  over: [n_over][4] rows (evaluation index, a, b, multiplicity):
+ * after that evaluation the meta edge {a,b} carries 1/multiplicity (the direction nx.Graph.add_edge saw last on a pair
+ * whose two directed multiplicities differ); NULL / 0 = none.  The values also become the per-tick cache
+ * (entities.py:531) of the NEXT poc_commit_crimes on this ctx, so a replayed tick ranks candidates with them. */
+int poc_embeddedness_accumulated(poc_ctx *ctx, int replica, int n, const int32_t *agents, int n_over, const int32_t *over,
+                                 double *out);
+/* test hook: hand the next poc_commit_crimes its per-tick oc_embeddedness cache (entities.py:531) directly */
+int poc_preload_embeddedness(poc_ctx *ctx, int replica, int n, const int32_t *agents, const double *values);
 /* Person.candidates_weight, entities.py:457-467 */
 int poc_candidate_weights(poc_ctx *ctx, int replica, int n_pairs, const int32_t *self, const int32_t *cand, double *out);
 /* Person.find_accomplices, entities.py:413-455: n independent searches on the current state.
@@ -203,6 +223,31 @@ int poc_candidate_weights(poc_ctx *ctx, int replica, int n_pairs, const int32_t 
 int poc_find_accomplices(poc_ctx *ctx, int replica, int n, const int32_t *initiator, const int32_t *k,
                          const int32_t *fac_pick_or_null, const double *u_fac_or_null, int32_t *groups,
                          int32_t *group_len, int32_t *d_fails);
+
+/* ---- the phases of ProtonOC.step that write the multiplex network, on the device ------------------
+ * make_baby (model.py:1553-1573, entities.py:605-613, 628-650), make_friends (model.py:610-626, entities.py:246-254),
+ * make_people_die (model.py:1575-1602, entities.py:615-626, 652-661) with a batch semantics (every agent of a phase
+ * decides on the state the phase started from).  Off by default: poc_run_ticks is the crime path. */
+typedef struct poc_demography {
+    double mort[2][128];      /* yearly death probability by [male][age] (initial_mortality_rates.csv); past the table 1 */
+    double fert[3][64];       /* yearly fertility by [min(number_of_children, 2)][age] (initial_fertility_rates.csv) */
+    double poisson_cdf[32];   /* CDF of Poisson(3): new friends an agent asks for (model.py:619) */
+    double prop_q[1024];      /* quantiles of lognormal(nat_propensity_m, nat_propensity_sigma): a newborn's propensity */
+    int32_t mort_max_age;     /* last age of the mortality table */
+    int32_t n_prop;           /* quantiles in use (<= 1024) */
+} poc_demography;
+enum { POC_PHASE_BABY = 1, POC_PHASE_FRIENDS = 2, POC_PHASE_DIE = 4 };
+int poc_set_demography(poc_ctx *ctx, const poc_demography *d);
+/* which of the phases poc_run_ticks runs after commit_crimes every tick, in the order of model.py:273-284 (default 0).
+ * max_agents / max_static_entries of the ctx must leave room for the newborns and their links. */
+int poc_set_phases(poc_ctx *ctx, int phase_mask);
+/* one phase for all replicas on the current state (stage hook for the parity tests) */
+int poc_run_phase(poc_ctx *ctx, int phase, int tick, const uint64_t *philox_keys);
+/* Person.number_of_children (entities.py:75): defaults to the number of offspring links at upload */
+int poc_upload_children(poc_ctx *ctx, int replica, const int32_t *n_children);
+int poc_download_children(poc_ctx *ctx, int replica, int32_t *n_children);
+/* agent slots of a replica (grows with births) */
+int poc_n_agents(poc_ctx *ctx, int replica, int32_t *out);
 
 int poc_sizeof_params(void);
 int poc_sizeof_tick_out(void);

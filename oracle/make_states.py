@@ -37,7 +37,24 @@ def export_setup(name, n_agents, seed, overrides=None, steps=0):
         path, os.path.getsize(path) / 1024, time.time() - t, int(st["oc_member"].sum()), int(st["facilitator"].sum())))
 
 
+def export_sweep_pool(variant: str, seeds):
+    """Config 5 (override-mode ensemble): the reference's own setup states at 10,000 agents for the three
+    samples/sample_json.json variants x a pool of seeds -- what bench.py --sweep draws its 1,024 replicas from."""
+    with open(os.path.join("/root/reference", "samples", "sample_json.json")) as f:
+        sj = json.load(f)
+    ov = dict(sj[variant])
+    n = ov.pop("initial_agents")
+    for seed in seeds:
+        export_setup("pool_n%d_s%d_sample%s" % (n, seed, variant), n, seed, ov, 0)
+
+
 def main(argv):
+    if len(argv) > 1 and argv[1] == "distdemog":
+        export_distribution_demog()
+        return
+    if len(argv) > 2 and argv[1] == "pool":   # python -m oracle.make_states pool <variant> <seed> [<seed> ...]
+        export_sweep_pool(argv[2], [int(x) for x in argv[3:]])
+        return
     only = argv[1] if len(argv) > 1 else None
     cases = [("state_n3000_s42_baseline", 3000, 42, None), ("state_n10000_s42_baseline", 10000, 42, None)]
     with open(os.path.join(H.REFERENCE_ROOT, "samples", "sample_json.json")) as f:
@@ -64,6 +81,47 @@ def main(argv):
 OUT_OF_SCOPE_PHASES = ["wedding", "retire_persons", "make_baby", "remove_excess_friends",
                        "remove_excess_professional_links", "make_friends", "make_people_die",
                        "graduate_and_enter_jobmarket", "let_migrants_in", "return_kids"]
+
+
+DEMOG_KEEP = ["make_baby", "make_friends", "make_people_die"]
+DEMOG_COLS = ["number_crimes", "current_oc_members", "people_jailed", "tot_criminal_link", "tot_friendship_link",
+              "tot_household_link", "tot_sibling_link", "tot_offspring_link", "tot_parent_link", "number_deceased",
+              "number_born", "current_num_persons", "facilitators", "criminal_tendency_mean", "age_mean"]
+
+
+def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42, n_runs=30, ticks=48):
+    """Whole-run distribution fixture for the SURVEY.md 8(f) rows built on the device: the reference continued from ONE
+    setup state with `n_runs` RNG streams, with its own make_baby / make_friends / make_people_die and the crime path
+    active and every other phase of step() replaced by a no-op (`refdemog_*`).  Per tick: DEMOG_COLS."""
+    ref_model, _, _ = H.load_reference()
+    d = {}
+    rows_all = []
+    for j in range(n_runs):
+        model = ref_model.ProtonOC(seed=seed)
+        model.setup(n_agents)
+        if not d:
+            st = H.export_state(model)
+            d.update({"pre_" + k: v for k, v in st.items()})
+            for k in PARAM_KEYS:
+                d["param_" + k] = np.float64(getattr(model, k))
+            d["tick"] = np.int32(model.tick)
+            d["crime_multiplier"] = np.float64(model.crime_multiplier)
+        model.random = np.random.default_rng(1000 + j)
+        for ph in OUT_OF_SCOPE_PHASES:
+            if ph not in DEMOG_KEEP:
+                setattr(model, ph, lambda *a, **k: None)
+        rows = []
+        for _ in range(ticks):
+            model.step()
+            rows.append([float(getattr(model, c)) for c in DEMOG_COLS])
+        rows_all.append(np.array(rows, dtype=np.float64))
+        print("refdemog run", j, rows_all[-1][-1][:12])
+    arr = np.array(rows_all)
+    for i, col in enumerate(DEMOG_COLS):
+        d["refdemog_" + col] = arr[:, :, i]
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path)
 
 
 def export_distribution(name="dist_n1000_s42", n_agents=1000, seed=42, n_runs=40, ticks=36):

@@ -101,6 +101,32 @@ class TickOut(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Demog(C.Structure):
+    """Mirror of orc_demog (hotpath.c)."""
+    _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
+                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32)]
+
+
+def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None) -> Demog:
+    """mortality: (female[120], male[120]) yearly probabilities; fertility: [3][64]; defaults = the Palermo tables."""
+    from pyproton_oc_b200 import tables
+    fem, mal = mortality if mortality is not None else (tables.MORTALITY_FEMALE, tables.MORTALITY_MALE)
+    fert = fertility if fertility is not None else tables.FERTILITY
+    d = Demog()
+    for a in range(128):
+        d.mort[0][a] = float(fem[a]) if a < len(fem) else 1.0
+        d.mort[1][a] = float(mal[a]) if a < len(mal) else 1.0
+    for k in range(3):
+        for a in range(64):
+            d.fert[k][a] = float(fert[k][a])
+    for i, v in enumerate(tables.poisson_cdf(3.0, 32)):
+        d.poisson_cdf[i] = v
+    for i, v in enumerate(tables.lognormal_quantiles(nat_propensity_m, nat_propensity_sigma, 1024)):
+        d.prop_q[i] = v
+    d.mort_max_age, d.n_prop = len(fem) - 1, 1024
+    return d
+
+
 _lib = None
 
 
@@ -152,6 +178,20 @@ def lib():
         L.orc_run_ticks.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int32, C.c_int32, C.c_uint64,
                                     C.POINTER(C.c_double), C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_reserve.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_n_agents.restype = C.c_int32
+        L.orc_n_agents.argtypes = [C.c_void_p]
+        L.orc_get_children.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_children.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_demog_counters.argtypes = [C.c_void_p, C.c_void_p]
+        for fn in ("orc_make_baby", "orc_make_friends", "orc_make_people_die"):
+            getattr(L, fn).restype = C.c_int32
+            getattr(L, fn).argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_uint64]
+        L.orc_run_ticks_phases.restype = C.c_int32
+        L.orc_run_ticks_phases.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_uint64, C.POINTER(C.c_double), C.c_void_p]
+        L.orc_sizeof_demog.restype = C.c_int32
+        assert L.orc_sizeof_demog() == C.sizeof(Demog), (L.orc_sizeof_demog(), C.sizeof(Demog))
         L.orc_sizeof_params.restype = C.c_int32
         L.orc_sizeof_tick_out.restype = C.c_int32
         assert L.orc_sizeof_params() == C.sizeof(Params), (L.orc_sizeof_params(), C.sizeof(Params))
@@ -251,8 +291,54 @@ class OracleState:
         except Exception:
             pass
 
+    # ---- demography
+    def reserve(self, cap: int):
+        self.L.orc_reserve(self.h, int(cap))
+
+    def _refresh_n(self):
+        self.n = int(self.L.orc_n_agents(self.h))
+
+    def children(self) -> np.ndarray:
+        self._refresh_n()
+        out = np.zeros(self.n, np.int32)
+        self.L.orc_get_children(self.h, out.ctypes.data)
+        return out
+
+    def set_children(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.int32)
+        assert len(a) == self.n
+        self.L.orc_set_children(self.h, a.ctypes.data)
+
+    def demog_counters(self):
+        out = np.zeros(2, np.int64)
+        self.L.orc_demog_counters(self.h, out.ctypes.data)
+        return {"number_deceased": int(out[0]), "number_born": int(out[1])}
+
+    def make_baby(self, p, dm, tick, key):
+        r = int(self.L.orc_make_baby(self.h, C.byref(p), C.byref(dm), tick, key))
+        self._refresh_n()
+        return r
+
+    def make_friends(self, p, dm, tick, key):
+        return int(self.L.orc_make_friends(self.h, C.byref(p), C.byref(dm), tick, key))
+
+    def make_people_die(self, p, dm, tick, key):
+        return int(self.L.orc_make_people_die(self.h, C.byref(p), C.byref(dm), tick, key))
+
+    def run_ticks_phases(self, p, dm, phases: int, tick0: int, n_ticks: int, philox_key: int, crime_multiplier: float = 0.0):
+        """Hot path + the demography phases in `phases` (1 make_baby, 2 make_friends, 4 make_people_die)."""
+        mult = C.c_double(crime_multiplier)
+        totals = np.zeros(6, dtype=np.int64)
+        rc = self.L.orc_run_ticks_phases(self.h, C.byref(p), C.byref(dm), phases, tick0, n_ticks, philox_key, C.byref(mult),
+                                         totals.ctypes.data)
+        if rc:
+            raise RuntimeError("oracle: slot capacity exhausted (reserve more)")
+        self._refresh_n()
+        return float(mult.value), totals
+
     # ---- read back
     def cols(self) -> Dict[str, np.ndarray]:
+        self._refresh_n()
         out, cols = {}, Cols()
         for f, key in STATE_KEYS.items():
             out[key] = np.empty(self.n, dtype=_DTYPES[f])
@@ -261,6 +347,7 @@ class OracleState:
         return out
 
     def layer(self, l: int):
+        self._refresh_n()
         e = int(self.L.orc_layer_entries(self.h, l))
         rowptr = np.empty(self.n + 1, dtype=np.int32)
         col = np.empty(max(e, 1), dtype=np.int32)

@@ -28,7 +28,21 @@ from typing import Dict, List
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PROTONOC_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference() -> str:
+    """The reference tree: $PROTONOC_REFERENCE, /root/reference (build container), or the unmodified install under
+    baseline/_ref (`pip install --no-deps --target baseline/_ref /root/reference`, done by __graft_entry__.build();
+    git-ignored, travels to the GPU box with the snapshot)."""
+    cands = [os.environ.get("PROTONOC_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "protonoc", "simulator", "model.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 _SIM = os.path.join(REFERENCE_ROOT, "protonoc", "simulator")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
 
@@ -135,6 +149,7 @@ def export_state(model, extra_agents=()) -> Dict[str, np.ndarray]:
     st["arrest_weight"] = np.array([float(a.arrest_weight) for a in agents], dtype=np.float64)
     st["father"] = np.array([slot[a.father.unique_id] if a.father is not None else -1
                              for a in agents], dtype=np.int32)
+    st["number_of_children"] = np.array([int(a.number_of_children) for a in agents], dtype=np.int32)
     for li, net in enumerate(LAYERS):
         rowptr = np.zeros(n + 1, dtype=np.int32)
         cols: List[int] = []
@@ -386,6 +401,7 @@ def step_with_recording(model) -> dict:
         holder["n_alive"] = len(model.schedule.agents)
         holder["intervention_on"] = bool(model.intervention_is_on())
         holder["rec"] = record_commit_crimes(model)
+        holder["rng_state_after"] = copy.deepcopy(model.random.bit_generator.state)
         holder["post"] = export_state(model)
         holder["post_scalars"] = model_scalars(model)
 

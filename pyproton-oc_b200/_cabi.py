@@ -22,6 +22,12 @@ class PocError(RuntimeError):
     pass
 
 
+class Demography(C.Structure):
+    """poc_demography (include/protonoc_b200.h)."""
+    _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
+                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("n_cells", C.c_int32), ("cell_male", C.c_int32 * MAX_CELLS), ("cell_age_from", C.c_int32 * MAX_CELLS),
@@ -111,6 +117,17 @@ SYMBOLS = {
     "poc_rings": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
     "poc_social_proximity": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "poc_embeddedness": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "poc_set_demography": (C.c_int, [_P, _P]),
+    "poc_set_phases": (C.c_int, [_P, C.c_int]),
+    "poc_run_phase": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "poc_upload_children": (C.c_int, [_P, C.c_int, _P]),
+    "poc_download_children": (C.c_int, [_P, C.c_int, _P]),
+    "poc_n_agents": (C.c_int, [_P, C.c_int, _P]),
+    "poc_packed_size": (C.c_int64, [C.c_int, _P]),
+    "poc_pack_state": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int64]),
+    "poc_upload_packed": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
+    "poc_embeddedness_accumulated": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "poc_preload_embeddedness": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "poc_candidate_weights": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "poc_find_accomplices": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "poc_sizeof_params": (C.c_int, []),

@@ -56,6 +56,13 @@ struct poc_ctx {
     int st_replica = -1;
     int *d_err = nullptr;
     int *d_prev_counters = nullptr;
+    // packed uploads (poc_upload_packed): two device staging blobs used alternately
+    uint8_t *blob_dev[2] = {nullptr, nullptr}; size_t blob_cap = 0;
+    cudaEvent_t blob_ev[2] = {nullptr, nullptr}; int blob_next = 0;
+    // instantiated tick graphs of poc_run_ticks, kept across calls
+    struct GraphKey { int ticks, report, n, groups, radius, Tcap, phases; const void *rows; bool operator==(const GraphKey &o) const { return ticks == o.ticks && report == o.report && n == o.n && groups == o.groups && radius == o.radius && Tcap == o.Tcap && phases == o.phases && rows == o.rows; } };
+    std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
+    std::vector<long long> graph_launches;
     int32_t *d_hook_a = nullptr, *d_hook_b = nullptr; double *d_hook_out = nullptr; long long hook_cap = 0;
     // timing
     bool timing = false;
@@ -75,6 +82,9 @@ struct poc_ctx {
     int graph_ticks = 8;
     TickInfo *d_ti = nullptr;
     bool use_graph = true;
+    int phases = 0;                 // demography phases poc_run_ticks runs per tick (poc_set_phases)
+    DevDemog *d_demog = nullptr;
+    bool demog_set = false;
 };
 
 static thread_local std::string g_err;
@@ -225,6 +235,11 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     DA(d.c_rowptr, (size_t)R * (N + 1)); DA(d.c_ent, (size_t)R * d.ccap);
     DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
     DA(d.c_par, R);
+    DA(d.u_rowptr_tmp, (size_t)R * (N + 1)); DA(d.u_ent_tmp, (size_t)R * d.ucap); DA(d.u_par, R);
+    DA(d.n_children, RN); DA(d.ncrim_dead, RN); DA(d.dm_list, RN); DA(d.dm_n, (size_t)R * 4);
+    d.DPcap = std::max(4 * N, 16384);
+    DA(d.dm_pairs, (size_t)R * d.DPcap); DA(d.dm_defer, (size_t)R * 1024);
+    DA(ctx->d_demog, 1); d.demog = ctx->d_demog;
     DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN);
@@ -311,6 +326,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
 #undef EMB2_ATTR
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_emb_acc_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_emb_acc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     CU(cudaStreamSynchronize(ctx->stream));
     return POC_OK;
 }
@@ -319,7 +336,9 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     if (!ctx) return POC_ERR_ARG;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &ge : ctx->graphs) if (ge.second) cudaGraphExecDestroy(ge.second);
     for (void *p : ctx->allocs) cudaFree(p);
+    for (int b = 0; b < 2; b++) if (ctx->blob_ev[b]) cudaEventDestroy(ctx->blob_ev[b]);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     for (int b = 0; b < 2; b++) { if (ctx->stage_host2[b]) cudaFreeHost(ctx->stage_host2[b]); if (ctx->stage_ev2[b]) cudaEventDestroy(ctx->stage_ev2[b]); }
     // (a ctx whose creation failed half-way comes through here too: every handle may still be null)
@@ -470,13 +489,13 @@ int poc_upload_layer(poc_ctx *ctx, int replica, int layer, const int32_t *rowptr
     return POC_OK;  // asynchronous: the caller's buffers must stay valid until poc_build_graph returns
 }
 
+static int build_union(poc_ctx *ctx, int replica, int n, const StageLayers &L);
 static int build_graph(poc_ctx *ctx, int replica, bool wait) {
     CHECK_CTX();
     if (replica < 0 || replica >= ctx->d.R || ctx->st_replica != replica) return fail(ctx, POC_ERR_STATE, "poc_build_graph: upload the layers of this replica first");
     int all = (1 << POC_NUM_LAYERS) - 1;
     if ((ctx->st_have & all) != all) return fail(ctx, POC_ERR_STATE, "poc_build_graph: all nine layers must be uploaded");
     int n = ctx->h_nagents[replica];
-    cudaStream_t st = ctx->stream;
     StageLayers L;
     for (int l = 0, b = 0; l < POC_NUM_LAYERS; l++) {
         if (l == POC_CRIMINAL) continue;
@@ -485,6 +504,15 @@ static int build_graph(poc_ctx *ctx, int replica, bool wait) {
         L.col[b] = ctx->st_col + ctx->st_off[idx];
         b++;
     }
+    int rc = build_union(ctx, replica, n, L);
+    if (rc) return rc;
+    ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;
+    return wait ? read_err(ctx, "poc_build_graph") : POC_OK;
+}
+
+// the eight static layers (staged per-layer CSRs on the device) -> merged multiplex rows, criminal flags, layer totals
+static int build_union(poc_ctx *ctx, int replica, int n, const StageLayers &L) {
+    cudaStream_t st = ctx->stream;
     int *lens = ctx->d.c_addlen + (size_t)replica * ctx->d.Ncap;  // scratch
     int32_t *urp = ctx->d.u_rowptr + (size_t)replica * (ctx->d.Ncap + 1);
     if (n) {
@@ -496,8 +524,92 @@ static int build_graph(poc_ctx *ctx, int replica, bool wait) {
         k_layer_totals<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
     } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
     CU(cudaGetLastError());
-    ctx->st_have = 0; ctx->st_replica = -1; ctx->st_off[0] = 0;
-    return wait ? read_err(ctx, "poc_build_graph") : POC_OK;
+    return POC_OK;
+}
+
+// ---- packed state: one contiguous host block per state (header, the 21 agent columns, nine {rowptr, col} pairs, the
+// co-offence counts), built once by the caller and uploaded with ONE copy per replica.  An ensemble uploads hundreds
+// of replicas: the ~20 copies and the host-side column gathering of the call-per-array path were the end-to-end cost.
+static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+int64_t poc_packed_size(int n, const int64_t *n_entries /* [9] */) {
+    if (n < 0 || !n_entries) return -1;
+    size_t o = 256;
+#define SZ(f, T) o += al16(sizeof(T) * (size_t)n);
+    POC_STAGE_COLS(SZ)
+#undef SZ
+    for (int l = 0; l < POC_NUM_LAYERS; l++) { if (n_entries[l] < 0) return -1; o += al16(sizeof(int32_t) * (size_t)(n + 1)) + al16(sizeof(int32_t) * (size_t)n_entries[l]); }
+    o += al16(sizeof(int32_t) * (size_t)n_entries[POC_CRIMINAL]);
+    return (int64_t)o;
+}
+
+int poc_pack_state(int n, const poc_agent_cols *c, const int32_t *const *rowptr, const int32_t *const *col, const int32_t *co, void *blob, int64_t blob_bytes) {
+    if (n < 0 || !c || !rowptr || !col || !blob) return POC_ERR_ARG;
+    int64_t ne[POC_NUM_LAYERS];
+    for (int l = 0; l < POC_NUM_LAYERS; l++) { if (!rowptr[l]) return POC_ERR_ARG; ne[l] = rowptr[l][n]; if (ne[l] < 0 || (ne[l] && !col[l])) return POC_ERR_ARG; }
+    if (poc_packed_size(n, ne) > blob_bytes) return POC_ERR_CAPACITY;
+    uint8_t *b = (uint8_t *)blob;
+    int64_t *h = (int64_t *)b;
+    memset(b, 0, 256);
+    h[0] = 0x504f4331;  // "POC1"
+    h[1] = n;
+    for (int l = 0; l < POC_NUM_LAYERS; l++) h[2 + l] = ne[l];
+    size_t o = 256;
+#define PK(f, T) { if (!c->f && n) return POC_ERR_ARG; if (n) memcpy(b + o, c->f, sizeof(T) * (size_t)n); o += al16(sizeof(T) * (size_t)n); }
+    POC_STAGE_COLS(PK)
+#undef PK
+    for (int l = 0; l < POC_NUM_LAYERS; l++) {
+        memcpy(b + o, rowptr[l], sizeof(int32_t) * (size_t)(n + 1)); o += al16(sizeof(int32_t) * (size_t)(n + 1));
+        if (ne[l]) memcpy(b + o, col[l], sizeof(int32_t) * (size_t)ne[l]);
+        o += al16(sizeof(int32_t) * (size_t)ne[l]);
+    }
+    if (ne[POC_CRIMINAL]) { if (co) memcpy(b + o, co, sizeof(int32_t) * (size_t)ne[POC_CRIMINAL]); else memset(b + o, 0, sizeof(int32_t) * (size_t)ne[POC_CRIMINAL]); }
+    return POC_OK;
+}
+
+int poc_upload_packed(poc_ctx *ctx, int replica, const void *blob, int64_t blob_bytes) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (!blob || blob_bytes < 256 || replica < 0 || replica >= d.R) return fail(ctx, POC_ERR_ARG, "poc_upload_packed: bad argument");
+    const int64_t *h = (const int64_t *)blob;
+    if (h[0] != 0x504f4331) return fail(ctx, POC_ERR_ARG, "poc_upload_packed: not a packed state");
+    int n = (int)h[1];
+    int64_t ne[POC_NUM_LAYERS], stat = 0;
+    for (int l = 0; l < POC_NUM_LAYERS; l++) { ne[l] = h[2 + l]; if (l != POC_CRIMINAL) stat += ne[l]; }
+    if (n < 0 || n > d.Ncap) return fail(ctx, POC_ERR_CAPACITY, "poc_upload_packed: more agents than max_agents");
+    if (stat > d.ucap) return fail(ctx, POC_ERR_CAPACITY, "poc_upload_packed: static layers exceed max_static_entries");
+    if (ne[POC_CRIMINAL] > d.ccap) return fail(ctx, POC_ERR_CAPACITY, "poc_upload_packed: criminal layer exceeds max_criminal_entries");
+    int64_t need = poc_packed_size(n, ne);
+    if (need < 0 || need > blob_bytes) return fail(ctx, POC_ERR_ARG, "poc_upload_packed: truncated block");
+    if (!ctx->blob_cap) {   // sized once for the ctx capacity
+        int64_t cap_ne[POC_NUM_LAYERS];
+        for (int l = 0; l < POC_NUM_LAYERS; l++) cap_ne[l] = 0;
+        cap_ne[0] = d.ucap; cap_ne[POC_CRIMINAL] = d.ccap;
+        ctx->blob_cap = (size_t)poc_packed_size(d.Ncap, cap_ne) + 16 * POC_NUM_LAYERS;
+        for (int b = 0; b < 2; b++) { DA(ctx->blob_dev[b], ctx->blob_cap); cudaEventCreateWithFlags(&ctx->blob_ev[b], cudaEventDisableTiming); }
+    }
+    cudaStream_t st = ctx->stream;
+    int bi = ctx->blob_next; ctx->blob_next ^= 1;
+    uint8_t *dev = ctx->blob_dev[bi];
+    // the stream itself orders the reuse of a staging blob behind the kernels that read it (everything is on ctx->stream)
+    CU(cudaMemcpyAsync(dev, blob, (size_t)need, cudaMemcpyHostToDevice, st));
+    StageCols sc;
+    size_t o = 256;
+#define PT(f, T) sc.f = (T *)(dev + o); o += al16(sizeof(T) * (size_t)n);
+    POC_STAGE_COLS(PT)
+#undef PT
+    StageLayers L;
+    const int32_t *crp = nullptr, *ccol = nullptr;
+    for (int l = 0, b = 0; l < POC_NUM_LAYERS; l++) {
+        const int32_t *rp = (const int32_t *)(dev + o); o += al16(sizeof(int32_t) * (size_t)(n + 1));
+        const int32_t *cl = (const int32_t *)(dev + o); o += al16(sizeof(int32_t) * (size_t)ne[l]);
+        if (l == POC_CRIMINAL) { crp = rp; ccol = cl; } else { L.rowptr[b] = rp; L.col[b] = cl; b++; }
+    }
+    const int32_t *cco = (const int32_t *)(dev + o);
+    ctx->h_nagents[replica] = n;
+    k_pack_agents<<<(std::max(n, 1) + 255) / 256, 256, 0, st>>>(d, replica, n, sc, ctx->d_err);
+    k_pack_criminal<<<(n + 256) / 256, 256, 0, st>>>(d, replica, n, crp, ccol, cco, ctx->d_err);
+    CU(cudaGetLastError());
+    return build_union(ctx, replica, n, L);   // asynchronous: poc_sync reports what the device-side input checks found
 }
 
 int poc_build_graph(poc_ctx *ctx, int replica) { return build_graph(ctx, replica, true); }
@@ -529,16 +641,19 @@ static int fetch_graph(poc_ctx *ctx, int replica, std::vector<int32_t> &urp, std
     int n = ctx->h_nagents[replica];
     DevCtx &d = ctx->d;
     urp.resize(n + 1); crp.resize(n + 1);
-    int par = 0;
+    int par = 0, upar = 0;
     CU(cudaMemcpyAsync(&par, d.c_par + replica, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&upar, d.u_par + replica, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const int32_t *c_rowptr = par ? d.c_rowptr_tmp : d.c_rowptr;
     const int2 *c_ent = par ? d.c_ent_tmp : d.c_ent;
-    CU(cudaMemcpyAsync(urp.data(), d.u_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    const int32_t *u_rowptr = upar ? d.u_rowptr_tmp : d.u_rowptr;
+    const uint32_t *u_ent = upar ? d.u_ent_tmp : d.u_ent;
+    CU(cudaMemcpyAsync(urp.data(), u_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(crp.data(), c_rowptr + (size_t)replica * (d.Ncap + 1), sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     uent.resize(urp[n]); cent.resize(crp[n]);
-    if (urp[n]) CU(cudaMemcpyAsync(uent.data(), d.u_ent + (size_t)replica * d.ucap, sizeof(uint32_t) * urp[n], cudaMemcpyDeviceToHost, ctx->stream));
+    if (urp[n]) CU(cudaMemcpyAsync(uent.data(), u_ent + (size_t)replica * d.ucap, sizeof(uint32_t) * urp[n], cudaMemcpyDeviceToHost, ctx->stream));
     if (crp[n]) CU(cudaMemcpyAsync(cent.data(), c_ent + (size_t)replica * d.ccap, sizeof(int2) * crp[n], cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return POC_OK;
@@ -550,7 +665,7 @@ int poc_layer_entries(poc_ctx *ctx, int replica, int layer, int64_t *out) {
     std::vector<int32_t> urp, crp; std::vector<uint32_t> uent; std::vector<int2> cent;
     int rc = fetch_graph(ctx, replica, urp, uent, crp, cent);
     if (rc) return rc;
-    if (layer == POC_CRIMINAL) { *out = (int64_t)cent.size(); return POC_OK; }
+    if (layer == POC_CRIMINAL) { int64_t k = 0; for (const int2 &e : cent) if (!CE_IS_DEAD(e.y)) k++; *out = k; return POC_OK; }
     uint32_t bit = 1u << layer_bit(layer);
     int64_t k = 0;
     for (uint32_t e : uent) if (ENT_MASK(e) & bit) k++;
@@ -569,7 +684,7 @@ int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, in
     for (int a = 0; a < n; a++) {
         rowptr[a] = p;
         if (layer == POC_CRIMINAL) {
-            for (int e = crp[a]; e < crp[a + 1]; e++) { if (col) col[p] = cent[e].x; if (co) co[p] = CE_CNT(cent[e].y); p++; }
+            for (int e = crp[a]; e < crp[a + 1]; e++) { if (CE_IS_DEAD(cent[e].y)) continue; if (col) col[p] = cent[e].x; if (co) co[p] = CE_CNT(cent[e].y); p++; }
         } else {
             uint32_t bit = 1u << layer_bit(layer);
             for (int e = urp[a]; e < urp[a + 1]; e++) if (ENT_MASK(uent[e]) & bit) { if (col) col[p] = ENT_COL(uent[e]); p++; }
@@ -580,7 +695,12 @@ int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, in
 }
 
 // ------------------------------------------------------------------------------------------------ hot path
-static int max_n(poc_ctx *ctx) { int m = 0; for (int v : ctx->h_nagents) m = std::max(m, v); return m; }
+static int max_n(poc_ctx *ctx) {
+    if (ctx->phases & POC_PHASE_BABY) return ctx->d.Ncap;   // births add slots on the device: size the grids for the capacity
+    int m = 0;
+    for (int v : ctx->h_nagents) m = std::max(m, v);
+    return m;
+}
 static int max_radius(poc_ctx *ctx) { int m = 1; for (auto &p : ctx->h_params) m = std::max(m, (int)p.max_accomplice_radius); return m; }
 
 static int set_tick(poc_ctx *ctx, int grp, int tick, int epoch, int rep, cudaStream_t s) {
@@ -692,9 +812,10 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
         // cells padded to multiples of eight doubles, plus one byte per eight positions
         int nd = max_n(ctx) + 8 * POC_MAX_CELLS;
         size_t draw_smem = (size_t)nd * sizeof(double) + nd / 8 + 16;
-        if (draw_smem > 160 * 1024) { nd = 16384; draw_smem = (size_t)nd * sizeof(double) + 16; }   // window mode
+        int allow_fit = 1;
+        if (draw_smem > 160 * 1024) { nd = 16384; draw_smem = (size_t)nd * sizeof(double) + 16; allow_fit = 0; }   // window mode
         Timed t(ctx, TM_DRAW, s);
-        k_draw<<<D.Rg, ctx->draw_threads, draw_smem, s>>>(D, nd);
+        k_draw<<<D.Rg, ctx->draw_threads, draw_smem, s>>>(D, nd, allow_fit);
     }
     if (after_draw) CU(cudaEventRecord(after_draw, s));
     int rc = launch_search_rounds(ctx, D, s);
@@ -704,6 +825,89 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
     // the reporter row of the tick is written after the end-of-tick bookkeeping (model.py:286-287)
     if (report) { Timed t(ctx, TM_OTHER, s); k_report<<<D.Rg, 512, 0, s>>>(D, end_tick == 2 ? 1 : 0); }
     CU(cudaGetLastError());
+    return POC_OK;
+}
+
+// the demography phases of one tick for one replica range (kernels in poc_demog.cuh); n = agent slots the grids cover
+static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask, int n) {
+    if (!mask || !n) return POC_OK;
+    if (!ctx->demog_set) return fail(ctx, POC_ERR_STATE, "demography phases requested before poc_set_demography");
+    if (mask & POC_PHASE_BABY) {
+        Timed t(ctx, TM_OTHER, s);
+        k_make_baby<<<D.Rg, 1024, 0, s>>>(D);
+        k_multiplex_insert<<<D.Rg, 1024, 0, s>>>(D);
+    }
+    if (mask & POC_PHASE_FRIENDS) {
+        Timed t(ctx, TM_OTHER, s);
+        k_make_friends<<<dim3((n + 127) / 128, D.Rg), 128, 0, s>>>(D);
+        k_apply_friends<<<dim3(8, D.Rg), 256, 0, s>>>(D);
+        k_friends_done<<<(D.Rg + 127) / 128, 128, 0, s>>>(D);
+        k_multiplex_insert<<<D.Rg, 1024, 0, s>>>(D);   // entries whose reverse slot was missing (rare; leaves at once otherwise)
+    }
+    if (mask & POC_PHASE_DIE) {
+        Timed t(ctx, TM_OTHER, s);
+        k_die_mark<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D);
+        k_die_apply<<<D.Rg, 256, 0, s>>>(D);
+    }
+    CU(cudaGetLastError());
+    return POC_OK;
+}
+
+static int refresh_counts(poc_ctx *ctx) {   // births add agent slots on the device
+    CU(cudaMemcpyAsync(ctx->h_nagents.data(), ctx->d.n_agents, sizeof(int) * ctx->d.R, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_set_demography(poc_ctx *ctx, const poc_demography *dm) {
+    CHECK_CTX();
+    static_assert(sizeof(poc_demography) == sizeof(DevDemog), "poc_demography / DevDemog out of sync");
+    if (!dm || dm->n_prop < 1 || dm->n_prop > 1024 || dm->mort_max_age < 0 || dm->mort_max_age > 127) return fail(ctx, POC_ERR_ARG, "poc_set_demography: bad argument");
+    CU(cudaMemcpyAsync(ctx->d_demog, dm, sizeof(DevDemog), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->demog_set = true;
+    return POC_OK;
+}
+
+int poc_set_phases(poc_ctx *ctx, int mask) {
+    CHECK_CTX();
+    if (mask & ~7) return fail(ctx, POC_ERR_ARG, "poc_set_phases: unknown phase");
+    if (mask && !ctx->demog_set) return fail(ctx, POC_ERR_STATE, "poc_set_phases: poc_set_demography first");
+    ctx->phases = mask;
+    return POC_OK;
+}
+
+int poc_run_phase(poc_ctx *ctx, int phase, int tick, const uint64_t *keys) {
+    CHECK_CTX();
+    if (phase != POC_PHASE_BABY && phase != POC_PHASE_FRIENDS && phase != POC_PHASE_DIE) return fail(ctx, POC_ERR_ARG, "poc_run_phase: one phase at a time");
+    if (keys) CU(cudaMemcpyAsync(ctx->d.philox_key, keys, sizeof(uint64_t) * ctx->d.R, cudaMemcpyHostToDevice, ctx->stream));
+    TickInfo t{tick, ctx->epoch, 0, 0};
+    CU(cudaMemcpyAsync(ctx->d_ti, &t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_phases(ctx, ctx->d, ctx->stream, phase, ctx->d.Ncap);
+    if (rc) return rc;
+    return refresh_counts(ctx);
+}
+
+int poc_upload_children(poc_ctx *ctx, int replica, const int32_t *nc) {
+    CHECK_CTX();
+    if (!nc || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_upload_children: bad argument");
+    CU(cudaMemcpyAsync(ctx->d.n_children + (size_t)replica * ctx->d.Ncap, nc, sizeof(int32_t) * ctx->h_nagents[replica], cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_download_children(poc_ctx *ctx, int replica, int32_t *nc) {
+    CHECK_CTX();
+    if (!nc || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_download_children: bad argument");
+    CU(cudaMemcpyAsync(nc, ctx->d.n_children + (size_t)replica * ctx->d.Ncap, sizeof(int32_t) * ctx->h_nagents[replica], cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_n_agents(poc_ctx *ctx, int replica, int32_t *out) {
+    CHECK_CTX();
+    if (!out || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_n_agents: bad argument");
+    *out = ctx->h_nagents[replica];
     return POC_OK;
 }
 
@@ -832,7 +1036,12 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
                 if (rc2) return rc2;
                 rc2 = launch_commit(ctx, D, s, true, false, (k == 0 && g + 1 < G) ? ctx->gstag[g] : nullptr, 0);
                 if (rc2) return rc2;
+                // model.py:274-278: make_baby, make_friends (retire / remove_excess_* are not built)
+                rc2 = launch_phases(ctx, D, s, ctx->phases & (POC_PHASE_BABY | POC_PHASE_FRIENDS), n);
+                if (rc2) return rc2;
                 if (n) { Timed t(ctx, TM_OTHER, s); k_end_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, 0); }
+                rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_DIE, n);   // model.py:284
+                if (rc2) return rc2;
                 // reporter row after the end-of-tick bookkeeping (model.py:286-287); it also moves the tick state on
                 { Timed t(ctx, TM_OTHER, s); k_report<<<D.Rg, 512, 0, s>>>(D, report ? 2 : 3); }
             }
@@ -847,24 +1056,38 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
         while (done < n_ticks) {
             int kk = std::min(K, n_ticks - done);   // the tail gets its own (smaller) graph
             int reps = (kk == K) ? (n_ticks - done) / K : 1;
-            cudaGraph_t graph = nullptr;
+            // instantiated graphs are kept across calls: an ensemble driver calls poc_run_ticks once per step with the
+            // same shape, and capture + instantiation of ~450 nodes costs more than replaying them once
+            int nc_max = 1;
+            for (auto &hp : ctx->h_params) nc_max = std::max(nc_max, (int)hp.n_cells);
+            // everything the captured launch shapes depend on
+            poc_ctx::GraphKey key{kk, report ? 1 : 0, n, G, max_radius(ctx) * 1024 + nc_max, d.Tcap, ctx->phases, (const void *)d.reporters};
             cudaGraphExec_t exec = nullptr;
-            long long launches_before = ctx->launches;
-            CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
-            rc = enqueue_ticks(kk);
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-            CU(cudaGraphInstantiate(&exec, graph, 0));
-            long long per_graph = ctx->launches - launches_before;
+            long long per_graph = 0;
+            for (size_t gi = 0; gi < ctx->graphs.size(); gi++)
+                if (ctx->graphs[gi].first == key) { exec = ctx->graphs[gi].second; per_graph = ctx->graph_launches[gi]; }
+            if (!exec) {
+                cudaGraph_t graph = nullptr;
+                long long launches_before = ctx->launches;
+                CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+                rc = enqueue_ticks(kk);
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+                cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+                per_graph = ctx->launches - launches_before;
+                ctx->launches = launches_before;
+                if (ctx->graphs.size() >= 16) { cudaGraphExecDestroy(ctx->graphs[0].second); ctx->graphs.erase(ctx->graphs.begin()); ctx->graph_launches.erase(ctx->graph_launches.begin()); }
+                ctx->graphs.push_back({key, exec});
+                ctx->graph_launches.push_back(per_graph);
+            }
             for (int i = 0; i < reps; i++) {
                 cudaError_t le = cudaGraphLaunch(exec, ctx->stream);
-                if (le != cudaSuccess) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return fail(ctx, POC_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le)); }
+                if (le != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
             }
-            ctx->launches = launches_before + per_graph * reps;
-            CU(cudaStreamSynchronize(ctx->stream));
-            cudaGraphExecDestroy(exec);
-            cudaGraphDestroy(graph);
+            ctx->launches += per_graph * reps;
             done += kk * reps;
         }
     } else {
@@ -872,6 +1095,7 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
         if (rc) return rc;
     }
     CU(cudaGetLastError());
+    if (ctx->phases & POC_PHASE_BABY) { rc = refresh_counts(ctx); if (rc) return rc; }
     if (reporters_out && n_ticks) {
         // device layout [R][Tcap][K] -> host [R][n_ticks][K]
         for (int r = 0; r < d.R; r++)
@@ -1022,6 +1246,66 @@ int poc_embeddedness(poc_ctx *ctx, int replica, int n, const int32_t *agents, do
     CU(cudaMemcpyAsync(all.data(), ctx->d.emb_val + (size_t)replica * ctx->d.Ncap, sizeof(double) * na, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n; i++) out[i] = all[agents[i]];
+    return POC_OK;
+}
+
+int poc_embeddedness_accumulated(poc_ctx *ctx, int replica, int n, const int32_t *agents, int n_over, const int32_t *over, double *out) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (replica < 0 || replica >= d.R || n < 0 || n > d.Ncap || (n && (!agents || !out)) || n_over < 0 || (n_over && !over))
+        return fail(ctx, POC_ERR_ARG, "poc_embeddedness_accumulated: bad argument");
+    int na = ctx->h_nagents[replica];
+    for (int i = 0; i < n; i++) if (agents[i] < 0 || agents[i] >= na) return fail(ctx, POC_ERR_ARG, "poc_embeddedness_accumulated: bad slot");
+    if (!n) return POC_OK;
+    // rows normalised to {lo, hi, evaluation, multiplicity}, sorted by (lo, hi, evaluation)
+    std::vector<int4> ov(n_over);
+    for (int i = 0; i < n_over; i++) {
+        int j = over[4 * i], a = over[4 * i + 1], b = over[4 * i + 2], m = over[4 * i + 3];
+        if (j < 0 || j >= n || a < 0 || a >= na || b < 0 || b >= na || m < 1) return fail(ctx, POC_ERR_ARG, "poc_embeddedness_accumulated: bad override row");
+        ov[i] = make_int4(std::min(a, b), std::max(a, b), j, m);
+    }
+    std::sort(ov.begin(), ov.end(), [](const int4 &x, const int4 &y) { return x.x != y.x ? x.x < y.x : (x.y != y.y ? x.y < y.y : x.z < y.z); });
+    int EW = (n + 31) / 32;
+    int32_t *d_slots = nullptr; unsigned *d_bits = nullptr; int *d_has = nullptr; int4 *d_over = nullptr; double *d_out = nullptr;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMalloc((void **)&d_slots, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_bits, sizeof(unsigned) * (size_t)std::max(na, 1) * EW);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_has, sizeof(int) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_over, sizeof(int4) * std::max(n_over, 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * (size_t)std::max(na, 1) * EW, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slots, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_over) e = cudaMemcpyAsync(d_over, ov.data(), sizeof(int4) * n_over, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        int grid = std::min(n, d.scr_slots);
+        k_emb_acc_mark<<<grid, 256, ctx->smem_search, st>>>(d, replica, n, d_slots, d_bits, EW, d_has);
+        k_emb_acc_eval<<<grid, 256, ctx->smem_search, st>>>(d, replica, n, d_slots, d_bits, EW, d_has, n_over, d_over, d_out, ctx->epoch + 1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_slots); cudaFree(d_bits); cudaFree(d_has); cudaFree(d_over); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("poc_embeddedness_accumulated: ") + cudaGetErrorString(e));
+    return POC_OK;
+}
+
+int poc_preload_embeddedness(poc_ctx *ctx, int replica, int n, const int32_t *agents, const double *values) {
+    CHECK_CTX();
+    DevCtx &d = ctx->d;
+    if (replica < 0 || replica >= d.R || n < 0 || (n && (!agents || !values))) return fail(ctx, POC_ERR_ARG, "poc_preload_embeddedness: bad argument");
+    int na = ctx->h_nagents[replica];
+    for (int i = 0; i < n; i++) if (agents[i] < 0 || agents[i] >= na) return fail(ctx, POC_ERR_ARG, "poc_preload_embeddedness: bad slot");
+    if (!n) return POC_OK;
+    int32_t *d_slots = nullptr; double *d_vals = nullptr;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMalloc((void **)&d_slots, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_vals, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slots, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_vals, values, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { k_emb_preload<<<(n + 255) / 256, 256, 0, st>>>(d, replica, n, d_slots, d_vals, ctx->epoch + 1); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_slots); cudaFree(d_vals);
+    if (e != cudaSuccess) return fail(ctx, POC_ERR_CUDA, std::string("poc_preload_embeddedness: ") + cudaGetErrorString(e));
     return POC_OK;
 }
 

@@ -1,0 +1,466 @@
+// poc_demog.cuh -- SURVEY.md 8(f): the three phases of ProtonOC.step that write the multiplex network, on the device.
+//
+//   make_baby          model.py:1553-1573 (non-constant population), entities.py:605-613, 628-650
+//   make_friends       model.py:610-626, entities.py:246-254, 674-689, extra.py:102-132
+//   make_people_die    model.py:1575-1602, entities.py:615-626, 652-661
+//
+// The reference walks the agents one after the other on one shared PCG64 stream; what runs here is the BATCH semantics
+// oracle/hotpath.c restates (every agent of a phase decides on the state the phase started from, with its own Philox
+// draws; the edits are applied together), which the kernels follow bit for bit.  Parity with the reference itself is
+// distributional (tests: KS against reference runs with exactly these phases active).
+//
+// Data: deaths clear layer masks / leave tombstones in criminal rows (entries never move); friendships set a mask bit on
+// entries that already exist (a potential friend is a relative, schoolmate or colleague: already a neighbour); births
+// need new entries, so the multiplex rows are laid out again into the second buffer (k_multiplex_insert: sort the new
+// directed entries -> merge, like k_commit does for the criminal layer).
+#pragma once
+#include "poc_device.cuh"
+
+#define DM_KEY(u, v, m) (((unsigned long long)(unsigned)(u) << 40) | ((unsigned long long)(unsigned)(v) << 8) | (unsigned long long)(m))
+#define DM_U(k) ((int)(((k) >> 40) & 0x7fffffu))
+#define DM_V(k) ((int)(((k) >> 8) & 0x7fffffu))
+#define DM_M(k) ((unsigned)((k) & 0xffu))
+#define FRIEND_CAND_MAX 64   /* CANON: the 64 lowest slots among an agent's potential friends are considered */
+
+// ---------------------------------------------------------------------------------------------- make_baby
+// one block per replica: eligible mothers draw, the births are listed in ascending slot order of the mother, every birth
+// fills its slot and queues its directed entries
+__global__ void __launch_bounds__(1024) k_make_baby(DevCtx C) {
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.x, tid = threadIdx.x, n = C.n_agents[r];
+    __shared__ int ws[33];
+    __shared__ int carry, s_np;
+    const poc_params &P = C.params[r];
+    const DevDemog &D = *C.demog;
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    int32_t *nch = RP(C.n_children, r, C.Ncap), *list = RP(C.dm_list, r, C.Ncap);
+    int *cn = RP(C.counters, r, CN_COUNT);
+    Graph g = graph_of(C, r);
+    const unsigned long long key = C.philox_key[r];
+    if (tid == 0) { carry = 0; s_np = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int a = base + tid;
+        bool born = false;
+        if (a < n) {
+            const uint32_t x = attr[a];
+            const int age = attr_age(x);
+            if ((x & F_ALIVE) && !(x & F_MALE) && age >= 14 && age <= 50) {
+                double u, u2;
+                philox_u2(key, tick, ST_BABY, a, u, u2);
+                const int nc = min(nch[a], 2);
+                const double pf = (age < 64) ? D.fert[nc][age] / (double)P.ticks_per_year : 0.0;
+                born = u < pf;
+            }
+        }
+        int tot, ex = block_exscan(born ? 1 : 0, ws, &tot);
+        if (born && carry + ex < C.Ncap) list[carry + ex] = a;
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    const int nb = carry;
+    if (tid == 0) { RP(C.dm_n, r, 4)[0] = nb; RP(C.dm_n, r, 4)[2] = 0; }
+    if (nb == 0) return;
+    if (n + nb > C.Ncap) { if (tid == 0) { atomicExch(&cn[CN_ERROR], 20); RP(C.dm_n, r, 4)[0] = 0; } return; }
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    for (int i = tid; i < nb; i += blockDim.x) {
+        const int m = list[i], b = n + i;
+        const size_t o = (size_t)r * C.Ncap + b;
+        double u0, u1;
+        philox_u2(key, tick, ST_BABYATTR, m, u0, u1);
+        int qi = (int)floor(u1 * (double)D.n_prop);
+        if (qi >= D.n_prop) qi = D.n_prop - 1;
+        const uint32_t xm = attr[m];
+        // Person.__init__ (entities.py:49-83) + init_baby: age 0, the mother's wealth level, everything else at its default
+        attr[b] = F_ALIVE | (u0 < 0.5 ? F_MALE : 0u) | ((uint32_t)attr_wealth(xm) << 24);
+        C.birth[o] = tick; C.ncrimes[o] = 0; C.ncrimes_tick[o] = 0; C.new_recruit[o] = -2;
+        C.propensity[o] = D.prop_q[qi]; C.tendency[o] = 0.0; C.sentence[o] = 0.0; C.arrest_w[o] = 0.0;
+        C.emb_stamp[o] = 0; C.ncrim_dead[o] = 0; nch[b] = 0;
+        // the mother's row as the phase found it: children so far (siblings), partner (father), household
+        int f = -1, cnt = 0;
+        const int e0 = g.u_rowptr[m], e1 = g.u_rowptr[m + 1];
+        for (int e = e0; e < e1; e++) {
+            const uint32_t ent = g.u_ent[e];
+            const unsigned mk = ENT_MASK(ent);
+            if ((mk & MB_PARTNER) && f < 0) f = ENT_COL(ent);   // CANON: the partner with the smallest slot
+            cnt += ((mk & MB_OFF) ? 2 : 0) + ((mk & MB_HH) ? 2 : 0);
+        }
+        cnt += 2 + (f >= 0 ? 2 : 0);
+        C.father[o] = f;
+        int pos = atomicAdd(&s_np, cnt);
+        if (pos + cnt <= C.DPcap) {
+            for (int e = e0; e < e1; e++) {
+                const uint32_t ent = g.u_ent[e];
+                const unsigned mk = ENT_MASK(ent);
+                const int v = ENT_COL(ent);
+                if (mk & MB_OFF) { pairs[pos++] = DM_KEY(b, v, MB_SIB); pairs[pos++] = DM_KEY(v, b, MB_SIB); }
+                if (mk & MB_HH) { pairs[pos++] = DM_KEY(b, v, MB_HH); pairs[pos++] = DM_KEY(v, b, MB_HH); }
+            }
+            pairs[pos++] = DM_KEY(m, b, MB_OFF); pairs[pos++] = DM_KEY(b, m, MB_PAR);
+            if (f >= 0) { pairs[pos++] = DM_KEY(f, b, MB_OFF); pairs[pos++] = DM_KEY(b, f, MB_PAR); }
+        }
+        nch[m] += 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_np > C.DPcap) { atomicExch(&cn[CN_ERROR], 21); RP(C.dm_n, r, 4)[0] = 0; return; }
+        RP(C.dm_n, r, 4)[2] = s_np;
+        cn[CN_BORN] += nb;
+    }
+}
+
+// The queued directed entries {u, v, layer bit} go into the multiplex rows: an entry that exists gets the bit, a new one
+// is inserted in slot order.  Everything is laid out again in the other buffer (rows keep no slack); one block per replica.
+// n_new = number of agent slots afterwards (newborn rows start empty).
+__global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
+    const int r = C.r0 + blockIdx.x, tid = threadIdx.x;
+    int *dmn = RP(C.dm_n, r, 4);
+    const int nb = dmn[0], np = dmn[2];
+    if (nb == 0 && np == 0) return;
+    __shared__ int ws[33];
+    __shared__ int carry, s_nins;
+    int *cn = RP(C.counters, r, CN_COUNT);
+    const int n_old = C.n_agents[r], n_new = n_old + nb;
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    Graph g = graph_of(C, r);
+    uint32_t *ent_old = const_cast<uint32_t *>(g.u_ent);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    long long *ltot = RP(C.layer_tot, r, 8);
+    // ---- bitonic sort by (u, v)
+    int np2 = 1;
+    while (np2 < np) np2 <<= 1;
+    if (np2 > C.DPcap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 21); return; }
+    for (int i = np + tid; i < np2; i += blockDim.x) pairs[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = pairs[i], b = pairs[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { pairs[i] = b; pairs[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // ---- one entry per (u, v): OR the layer bits of a run into its first element, compact
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < np; base += blockDim.x) {
+        const int i = base + tid;
+        const bool valid = i < np;
+        unsigned long long me = valid ? pairs[i] : 0ull;
+        const bool head = valid && (i == 0 || (pairs[i - 1] >> 8) != (me >> 8));
+        if (head) for (int j = i + 1; j < np && (pairs[j] >> 8) == (me >> 8); j++) me |= pairs[j] & 0xffull;
+        int tot, ex = block_exscan(head ? 1 : 0, ws, &tot);
+        __syncthreads();
+        if (head) pairs[carry + ex] = me;
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    const int nu = carry;
+    // ---- an entry that exists already takes the bits in place (the copy below carries it over); the rest are new
+    int32_t *isnew_ex = RP(C.pair_new_ex, r, C.Pcap + 1), *ins = RP(C.ins_row, r, C.Pcap);
+    int32_t *ins_rowid = RP(C.ins_rowid, r, C.Pcap), *ins_before = RP(C.ins_before, r, C.Pcap + 1);
+    if (nu > C.Pcap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 21); return; }
+    for (int i = tid; i < nu; i += blockDim.x) {
+        const unsigned long long k = pairs[i];
+        const int u = DM_U(k), v = DM_V(k);
+        const unsigned m = DM_M(k);
+        const int idx = (u < n_old) ? static_find_idx(g, u, v) : -1;
+        const bool ualive = (attr[u] & F_ALIVE) != 0;
+        if (idx >= 0) {
+            const unsigned old = atomicOr(&ent_old[idx], m << 24);
+            if (ualive) for (int l = 0; l < 8; l++) if (((m >> l) & 1u) && !((old >> (24 + l)) & 1u)) atomicAdd((unsigned long long *)&ltot[l], 1ull);
+        } else {
+            if (ualive) for (int l = 0; l < 8; l++) if ((m >> l) & 1u) atomicAdd((unsigned long long *)&ltot[l], 1ull);
+            pairs[i] = k | (1ull << 63);   // new entry
+        }
+    }
+    if (tid == 0) { carry = 0; s_nins = 0; }
+    __syncthreads();
+    // number of new entries before each pair; first new pair of every row that receives any
+    for (int base = 0; base < nu; base += blockDim.x) {
+        const int i = base + tid;
+        const bool valid = i < nu;
+        const int isnew = (valid && (pairs[i] >> 63)) ? 1 : 0;
+        bool head = isnew != 0;
+        for (int j = i - 1; head && j >= 0 && DM_U(pairs[j]) == DM_U(pairs[i]); j--) if (pairs[j] >> 63) head = false;
+        int tot, ex = block_exscan(isnew, ws, &tot);
+        if (valid) isnew_ex[i] = carry + ex;
+        int toth, exh = block_exscan(head ? 1 : 0, ws, &toth);
+        if (head) ins[s_nins + exh] = i;
+        __syncthreads();
+        if (tid == 0) { carry += tot; s_nins += toth; }
+        __syncthreads();
+    }
+    const int nins = s_nins, tot_add = carry;
+    if (tid == 0) isnew_ex[nu] = tot_add;
+    const int e_old = g.u_rowptr[n_old];
+    if ((long long)e_old + tot_add > C.ucap) { if (tid == 0) atomicExch(&cn[CN_ERROR], 22); return; }
+    __syncthreads();
+    // receiving rows: id, new entries in the receiving rows before it
+    for (int k = tid; k <= nins; k += blockDim.x) {
+        ins_before[k] = (k < nins) ? isnew_ex[ins[k]] : tot_add;
+        if (k < nins) ins_rowid[k] = DM_U(pairs[ins[k]]);
+    }
+    __syncthreads();
+    const int upar = C.u_par[r];
+    int32_t *rp_new = (upar ? C.u_rowptr : C.u_rowptr_tmp) + (size_t)r * (C.Ncap + 1);
+    uint32_t *ent_new = (upar ? C.u_ent : C.u_ent_tmp) + (size_t)r * C.ucap;
+    // ---- new row pointers (rows of newborns start behind the old rows)
+    for (int a = tid; a <= n_new; a += blockDim.x) {
+        int lo = 0, hi = nins;   // receiving rows with id < a
+        while (lo < hi) { int m = (lo + hi) >> 1; if (ins_rowid[m] < a) lo = m + 1; else hi = m; }
+        rp_new[a] = ((a <= n_old) ? g.u_rowptr[a] : e_old) + ins_before[lo];
+    }
+    // ---- rows without new entries move as they are; receiving rows are merged by one warp each
+    for (int a = tid; a < n_old; a += blockDim.x) {
+        int lo = 0, hi = nins;
+        while (lo < hi) { int m = (lo + hi) >> 1; if (ins_rowid[m] < a) lo = m + 1; else hi = m; }
+        if (lo < nins && ins_rowid[lo] == a) continue;
+        const int b = g.u_rowptr[a], e = g.u_rowptr[a + 1], sh = ins_before[lo];
+        for (int i = b; i < e; i++) ent_new[i + sh] = ent_old[i];
+    }
+    const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    for (int k = w; k < nins; k += nw) {
+        const int a = ins_rowid[k];
+        const int ob = (a < n_old) ? g.u_rowptr[a] : e_old, oe = (a < n_old) ? g.u_rowptr[a + 1] : e_old, nbase = ob + ins_before[k];
+        // the pairs of row a: from ins[k] to the end of the row's run
+        const int pb = ins[k];
+        int pe = pb;
+        while (pe < nu && DM_U(pairs[pe]) == a) pe++;
+        for (int i = ob + lane; i < oe; i += 32) {
+            const uint32_t en = ent_old[i];
+            int shift = 0;
+            for (int j = pb; j < pe; j++) if ((pairs[j] >> 63) && DM_V(pairs[j]) < ENT_COL(en)) shift++;
+            ent_new[nbase + (i - ob) + shift] = en;
+        }
+        for (int j = pb + lane; j < pe; j += 32) {
+            if (!(pairs[j] >> 63)) continue;
+            const unsigned long long kk = pairs[j];
+            const int v = DM_V(kk);
+            int lo = ob, hi = oe;   // old entries that sort before v
+            while (lo < hi) { int m = (lo + hi) >> 1; if (ENT_COL(ent_old[m]) < v) lo = m + 1; else hi = m; }
+            // a criminal entry towards v may exist already (the flag lives in the static entry)
+            const unsigned crim = (a < n_old && crim_find(g, a, v) >= 0) ? ENT_CRIM : 0u;
+            ent_new[nbase + (lo - ob) + (isnew_ex[j] - isnew_ex[pb])] = (uint32_t)v | crim | (DM_M(kk) << 24);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { C.u_par[r] = upar ^ 1; C.n_agents[r] = n_new; dmn[0] = 0; dmn[2] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------- make_friends
+// social_proximity's last term: does any friend of a also count c among its friends?  Both rows ascending.
+__device__ __forceinline__ bool friends_shared_rows(const Graph &g, int a, int c) {
+    int i = g.u_rowptr[a], ie = g.u_rowptr[a + 1], j = g.u_rowptr[c], je = g.u_rowptr[c + 1];
+    while (i < ie && j < je) {
+        const uint32_t x = g.u_ent[i], y = g.u_ent[j];
+        if (!(ENT_MASK(x) & MB_FRIEND)) { i++; continue; }
+        if (!(ENT_MASK(y) & MB_FRIEND)) { j++; continue; }
+        const int cx = ENT_COL(x), cy = ENT_COL(y);
+        if (cx == cy) return true;
+        if (cx < cy) i++; else j++;
+    }
+    return false;
+}
+
+// pass 1 (thread per agent, decisions on the state the phase started from): the chosen pairs are queued
+__global__ void __launch_bounds__(128) k_make_friends(DevCtx C) {
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const uint32_t xa = attr[a];
+    if (!(xa & F_ALIVE)) return;
+    const DevDemog &D = *C.demog;
+    Graph g = graph_of(C, r);
+    const unsigned long long key = C.philox_key[r];
+    int cand[FRIEND_CAND_MAX];
+    double w[FRIEND_CAND_MAX], cdf[FRIEND_CAND_MAX];
+    int m = 0;
+    const unsigned src = MB_SIB | MB_OFF | MB_PARTNER | MB_SCHOOL | MB_PROF;
+    for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1] && m < FRIEND_CAND_MAX; e++) {
+        const uint32_t ent = g.u_ent[e];
+        const unsigned mk = ENT_MASK(ent);
+        if ((mk & src) && !(mk & MB_FRIEND)) cand[m++] = ENT_COL(ent);
+    }
+    if (m == 0) return;
+    double u, u2;
+    philox_u2(key, tick, ST_FRIEND_N, a, u, u2);
+    int want = 0;
+    while (want < 31 && u >= D.poisson_cdf[want]) want++;
+    if (want > m) want = m;
+    if (want == 0) return;
+    // extra.weighted_n_of(n, candidates, social_proximity): left-to-right sum, p = w / sum, numpy's no-replacement sampler
+    int nz = 0;
+    double sump = 0.0;
+    for (int i = 0; i < m; i++) w[i] = social_proximity(xa, attr[cand[i]], friends_shared_rows(g, a, cand[i]));
+    for (int i = 0; i < m; i++) { sump = sump + w[i]; if (w[i] != 0.0) nz++; }
+    if (nz < want) want = nz;
+    if (sump == 0.0) return;
+    for (int i = 0; i < m; i++) w[i] = w[i] / sump;
+    int found[32], nf = 0, ucur = 0;
+    while (nf < want) {
+        for (int i = 0; i < nf; i++) w[found[i]] = 0.0;
+        double acc = 0.0;
+        for (int i = 0; i < m; i++) { acc = acc + w[i]; cdf[i] = acc; }
+        for (int i = 0; i < m; i++) cdf[i] = cdf[i] / acc;
+        const int need = want - nf, base = nf;
+        for (int j = 0; j < need; j++) {
+            double uu, uu2;
+            philox_u2(key, tick, ST_FRIEND, a * 64 + (ucur & 63), uu, uu2);
+            ucur++;
+            int ix = ss_right(cdf, m, uu);
+            if (ix >= m) ix = m - 1;
+            bool dup = false;
+            for (int q = base; q < nf; q++) dup |= (found[q] == ix);
+            if (!dup) found[nf++] = ix;
+        }
+        if (ucur > 4096) break;
+    }
+    if (nf == 0) return;
+    int *dmn = RP(C.dm_n, r, 4);
+    const int pos = atomicAdd(&dmn[3], nf);
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    if (pos + nf > C.DPcap) { atomicExch(&RP(C.counters, r, CN_COUNT)[CN_ERROR], 23); return; }
+    for (int i = 0; i < nf; i++) pairs[pos + i] = DM_KEY(a, cand[found[i]], MB_FRIEND);
+}
+
+// pass 2: the friendship bit on both entries of every queued pair (Person.make_friendship_link, entities.py:133-140)
+__global__ void __launch_bounds__(256) k_apply_friends(DevCtx C) {
+    const int r = C.r0 + blockIdx.y;
+    int *dmn = RP(C.dm_n, r, 4);
+    const int np = min(dmn[3], C.DPcap);
+    const unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    Graph g = graph_of(C, r);
+    uint32_t *ent = const_cast<uint32_t *>(g.u_ent);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    long long *ltot = RP(C.layer_tot, r, 8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const int a = DM_U(pairs[i]), c = DM_V(pairs[i]);
+        const int e1 = static_find_idx(g, a, c), e2 = static_find_idx(g, c, a);
+        if (e1 >= 0 && !(atomicOr(&ent[e1], MB_FRIEND << 24) & (MB_FRIEND << 24)) && (attr[a] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
+        if (e2 >= 0) { if (!(atomicOr(&ent[e2], MB_FRIEND << 24) & (MB_FRIEND << 24)) && (attr[c] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull); }
+        else {
+            // c's row has no slot for a (a one-sided link in the uploaded state: c cleared its own sets when it was
+            // arrested before the upload, entities.py:601-602): the entry is created by the insert pass that follows
+            const int q = atomicAdd(&dmn[2], 1);
+            if (q < 1024) RP(C.dm_defer, r, 1024)[q] = DM_KEY(c, a, MB_FRIEND); else atomicExch(&RP(C.counters, r, CN_COUNT)[CN_ERROR], 24);
+        }
+    }
+}
+__global__ void k_friends_done(DevCtx C) {   // after pass 2: count, reset the queue, hand deferred entries to the insert pass
+    const int r = C.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C.r0 + C.Rg) return;
+    int *dmn = RP(C.dm_n, r, 4);
+    RP(C.counters, r, CN_COUNT)[CN_FRIENDSHIPS] += dmn[3];
+    dmn[3] = 0;
+    const int nd = min(dmn[2], 1024);
+    dmn[2] = nd;
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    for (int i = 0; i < nd; i++) pairs[i] = RP(C.dm_defer, r, 1024)[i];
+}
+
+// ---------------------------------------------------------------------------------------------- make_people_die
+// pass 1 (thread per agent): who dies this tick
+__global__ void __launch_bounds__(256) k_die_mark(DevCtx C) {
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const uint32_t x = attr[a];
+    if (!(x & F_ALIVE)) return;
+    const DevDemog &D = *C.demog;
+    double u, u2;
+    philox_u2(C.philox_key[r], tick, ST_DIE, a, u, u2);
+    const int age = attr_age(x);
+    const double pm = (age <= D.mort_max_age && age < 128) ? D.mort[(x & F_MALE) ? 1 : 0][age] / (double)C.params[r].ticks_per_year : 1.0;
+    if (u < pm || age > 119) {
+        attr[a] = x | F_DYING;
+        RP(C.dm_list, r, C.Ncap)[atomicAdd(&RP(C.dm_n, r, 4)[1], 1)] = a;
+    }
+}
+
+// pass 2 (block per replica): facilitator replacement in ascending order of the dying agents, then Person.die
+__global__ void __launch_bounds__(256) k_die_apply(DevCtx C) {
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    int *dmn = RP(C.dm_n, r, 4);
+    const int nd = dmn[1];
+    if (nd == 0) return;
+    const int n = C.n_agents[r];
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    int32_t *list = RP(C.dm_list, r, C.Ncap);
+    int32_t *ncd = RP(C.ncrim_dead, r, C.Ncap);
+    long long *ltot = RP(C.layer_tot, r, 8);
+    Graph g = graph_of(C, r);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
+    int2 *cent = const_cast<int2 *>(g.c_ent);
+    if (tid == 0) {
+        // dying facilitators, ascending slot: each is replaced by a random adult who is neither facilitator nor OC member
+        // (model.py:1590-1594): uniform over the slots by rejection
+        for (int guard = 0; guard < nd; guard++) {
+            int best = -1;
+            for (int i = 0; i < nd; i++) { int a = list[i]; if ((attr[a] & F_FAC) && !(attr[a] & (1u << 30)) && (best < 0 || a < best)) best = a; }
+            if (best < 0) break;
+            attr[best] |= (1u << 30);   // handled (cleared below together with F_DYING)
+            for (int j = 0; j < 64; j++) {
+                double u, u2;
+                philox_u2(C.philox_key[r], tick, ST_FACREP, best * 64 + j, u, u2);
+                int c = (int)floor(u * (double)n);
+                if (c >= n) c = n - 1;
+                const uint32_t xc = attr[c];
+                if ((xc & F_ALIVE) && !(xc & F_FAC) && !(xc & F_OC) && attr_age(xc) > 18) { attr[c] = xc | F_FAC; break; }
+            }
+        }
+    }
+    __syncthreads();
+    // Person.die: the dying agent leaves the neighbour sets of its own out-neighbours, in all nine networks; its own
+    // sets stay.  Rows of agents that die in the same tick are left alone (batch rule).  One warp per dying agent.
+    for (int i = w; i < nd; i += nw) {
+        const int a = list[i];
+        const int b0 = g.u_rowptr[a], e0 = g.u_rowptr[a + 1], b1 = g.c_rowptr[a], e1 = g.c_rowptr[a + 1];
+        const int len0 = e0 - b0, len = len0 + (e1 - b1);
+        int own[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = lane; j < len; j += 32) {
+            int v = -1;
+            if (j < len0) {
+                const uint32_t ent = uent[b0 + j];
+                const unsigned mk = ENT_MASK(ent);
+#pragma unroll
+                for (int l = 0; l < 8; l++) own[l] += (mk >> l) & 1u;
+                if (mk) v = ENT_COL(ent);
+            } else {
+                const int2 ce = cent[b1 + (j - len0)];
+                if (!CE_IS_DEAD(ce.y)) v = ce.x;
+            }
+            if (v < 0 || v == a || (attr[v] & F_DYING)) continue;
+            const bool valive = (attr[v] & F_ALIVE) != 0;
+            const int idx = static_find_idx(g, v, a);
+            if (idx >= 0) {
+                const unsigned old = atomicAnd(&uent[idx], 0x00ffffffu);
+                if (valive) for (int l = 0; l < 8; l++) if ((old >> (24 + l)) & 1u) atomicAdd((unsigned long long *)&ltot[l], (unsigned long long)-1ll);
+            }
+            const int cidx = crim_find_idx(g, v, a);
+            if (cidx >= 0) {
+                const int oldy = atomicExch(&cent[cidx].y, CE_DEAD);
+                if (!CE_IS_DEAD(oldy)) atomicAdd(&ncd[v], 1);
+            }
+        }
+        // the dying agent's own rows no longer count towards the tot_<layer>_link reporters (scheduled agents only)
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            int s = own[l];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+            if (lane == 0 && s) atomicAdd((unsigned long long *)&ltot[l], (unsigned long long)(-(long long)s));
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nd; i += blockDim.x) { const int a = list[i]; attr[a] &= ~(F_ALIVE | F_DYING | (1u << 30)); }
+    if (tid == 0) { RP(C.counters, r, CN_COUNT)[CN_DECEASED] += nd; dmn[1] = 0; }
+}

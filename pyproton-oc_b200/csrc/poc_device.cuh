@@ -20,7 +20,8 @@
 // ---- packed attribute word ------------------------------------------------------------------------
 enum : uint32_t {
     F_ALIVE = 1u << 8, F_MALE = 1u << 9, F_OC = 1u << 10, F_FAC = 1u << 11, F_PRISONER = 1u << 12,
-    F_HASJOB = 1u << 13, F_HASSCHOOL = 1u << 14, F_TARGET = 1u << 15
+    F_HASJOB = 1u << 13, F_HASSCHOOL = 1u << 14, F_TARGET = 1u << 15,
+    F_DYING = 1u << 31   /* set by make_people_die for the length of that phase only */
 };
 __host__ __device__ __forceinline__ int attr_age(uint32_t a) { return (int)(a & 0xffu); }
 __host__ __device__ __forceinline__ int attr_job(uint32_t a) { return (int)((a >> 16) & 0xfu); }
@@ -40,15 +41,19 @@ __host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < PO
 #define ENT_COL(e) ((int)((e) & 0x007fffffu))
 #define ENT_CRIM 0x00800000u /* the same neighbour also has an entry in the criminal row */
 #define ENT_MASK(e) ((e) >> 24)
-// criminal entry .y = num_co_offenses (24 bit) | copy of the static layer mask of the same neighbour << 24
-#define CE_CNT(y) ((int)((unsigned)(y) & 0x00ffffffu))
+// criminal entry .y = num_co_offenses (23 bit) | removed flag (bit 23) | copy of the static layer mask of the same neighbour << 24
+// A removed entry (Person.die took the owner's dead neighbour out of its criminal set, entities.py:652-661) stays in the
+// row as a tombstone with count 0 and mask 0 until the row is laid out again: traversals skip it, weights see 0.
+#define CE_CNT(y) ((int)((unsigned)(y) & 0x007fffffu))
+#define CE_DEAD 0x00800000
+#define CE_IS_DEAD(y) (((unsigned)(y) & 0x00800000u) != 0u)
 #define CE_SMASK(y) ((unsigned)(y) >> 24)
 
 // counters per replica (ints), cumulative unless noted
 enum {
     CN_NUMBER_CRIMES = 0, CN_SIZE_FAILS, CN_FAC_CRIMES, CN_FAC_FAILS, CN_BIG_CRIME, CN_OFFSPRING_RECRUITED,
     CN_PROTECTED_RECRUITED, CN_PEOPLE_JAILED, CN_RECRUITED, CN_ERROR, CN_TICK_CRIMES, CN_TICK_MEMBERS,
-    CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_COUNT = 24
+    CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_DECEASED, CN_BORN, CN_FRIENDSHIPS, CN_COUNT = 24
 };
 
 // algorithmic-work counters per replica (what an ideal implementation must move once)
@@ -72,6 +77,8 @@ struct DevCtx {
     double *propensity, *tendency, *sentence, *arrest_w;
     // graph
     int32_t *u_rowptr; uint32_t *u_ent;
+    int32_t *u_rowptr_tmp; uint32_t *u_ent_tmp;   // second multiplex buffer: make_baby lays the rows out again (k_multiplex_insert)
+    int *u_par;                     // [R] which multiplex CSR is current
     int32_t *c_rowptr; int2 *c_ent;
     int32_t *c_rowptr_tmp; int2 *c_ent_tmp; int32_t *c_addlen;
     int *c_par;                     // [R] which criminal CSR is current: 0 = c_rowptr/c_ent, 1 = the _tmp pair (k_commit
@@ -123,13 +130,31 @@ struct DevCtx {
     unsigned long long *scr_dist;   // [slots][Ncap+1]
     unsigned *scr_edges;            // [slots][ecap] staged induced entries of one embeddedness evaluation
     const double *invw;             // [256] 1.0 / i (meta-edge weight of multiplicity i, model.py:1536)
+    // demography (make_baby, make_friends, make_people_die)
+    const struct DevDemog *demog;   // tables, one set for the ctx
+    int32_t *n_children;            // [R][Ncap] Person.number_of_children
+    int32_t *ncrim_dead;            // [R][Ncap] tombstones in the agent's criminal row (tot_criminal_link counts live entries)
+    int32_t *dm_list;               // [R][Ncap] mothers of the tick / agents dying in the tick
+    int32_t *dm_n;                  // [R][4] their numbers; [2] = queued multiplex insertions / friendships
+    unsigned long long *dm_pairs;   // [R][DPcap] directed entries to add: u << 40 | v << 8 | layer mask
+    unsigned long long *dm_defer;   // [R][1024] friendships whose reverse entry has no slot yet
+    int DPcap;
     int scr_slots;
     double *reporters;              // [R][Tcap][POC_N_REPORTERS]
     int Tcap;
 };
 
+struct DevDemog {
+    double mort[2][128];      // yearly death probability by [male][age]; past the table 1 (entities.py:615-626)
+    double fert[3][64];       // yearly fertility by [min(children, 2)][age] (entities.py:605-613)
+    double poisson_cdf[32];   // CDF of Poisson(3) (model.py:619)
+    double prop_q[1024];      // quantiles of the newborns' propensity lognormal (entities.py:71)
+    int mort_max_age, n_prop;
+};
+
 // ---- Philox4x32-10 (Salmon et al. SC'11) -----------------------------------------------------------
-enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4 };
+enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4, ST_DIE = 5, ST_FACREP = 6, ST_BABY = 7,
+       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10 };
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
 #pragma unroll
@@ -214,7 +239,9 @@ struct Graph {
 };
 __device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
     Graph g;
-    g.u_rowptr = C.u_rowptr + (size_t)r * (C.Ncap + 1); g.u_ent = C.u_ent + (size_t)r * C.ucap;
+    int upar = C.u_par[r];
+    g.u_rowptr = (upar ? C.u_rowptr_tmp : C.u_rowptr) + (size_t)r * (C.Ncap + 1);
+    g.u_ent = (upar ? C.u_ent_tmp : C.u_ent) + (size_t)r * C.ucap;
     int par = C.c_par[r];
     g.c_rowptr = (par ? C.c_rowptr_tmp : C.c_rowptr) + (size_t)r * (C.Ncap + 1);
     g.c_ent = (par ? C.c_ent_tmp : C.c_ent) + (size_t)r * C.ccap;
@@ -263,7 +290,7 @@ __device__ int bfs_levels(const Graph &g, int nwords, unsigned *bitmap, int *lis
                 if (f < tot) {
                     int j = f - tex;
                     if (j < tl0) { uint32_t ent = g.u_ent[tb0 + j]; if (ENT_MASK(ent)) v = ENT_COL(ent); }
-                    else v = g.c_ent[tb1 + (j - tl0)].x;
+                    else { int2 ce = g.c_ent[tb1 + (j - tl0)]; if (!CE_IS_DEAD(ce.y)) v = ce.x; }
                 }
                 bool isnew = false;
                 if (v >= 0) {
@@ -316,8 +343,13 @@ __device__ __forceinline__ double social_proximity(uint32_t self_attr, uint32_t 
 __device__ __forceinline__ int crim_find(const Graph &g, int u, int v) {  // returns count or -1
     int lo = g.c_rowptr[u], hi = g.c_rowptr[u + 1], end = hi;
     while (lo < hi) { int m = (lo + hi) >> 1; if (g.c_ent[m].x < v) lo = m + 1; else hi = m; }
-    if (lo < end) { int2 e = g.c_ent[lo]; if (e.x == v) return CE_CNT(e.y); }
+    if (lo < end) { int2 e = g.c_ent[lo]; if (e.x == v && !CE_IS_DEAD(e.y)) return CE_CNT(e.y); }
     return -1;
+}
+__device__ __forceinline__ int crim_find_idx(const Graph &g, int u, int v) {  // entry index (tombstones included) or -1
+    int lo = g.c_rowptr[u], hi = g.c_rowptr[u + 1], end = hi;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (g.c_ent[m].x < v) lo = m + 1; else hi = m; }
+    return (lo < end && g.c_ent[lo].x == v) ? lo : -1;
 }
 __device__ __forceinline__ int static_find_idx(const Graph &g, int u, int v) {  // entry index of v in u's row or -1
     int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;

@@ -101,7 +101,7 @@ __device__ int bfs_group(const Graph &g, int nwords, unsigned *bitmap, int *list
                 if (f < tot) {
                     int j = f - tex;
                     if (j < tl0) { uint32_t ent = g.u_ent[tb0 + j]; if (ENT_MASK(ent)) v = ENT_COL(ent); }
-                    else v = g.c_ent[tb1 + (j - tl0)].x;
+                    else { int2 ce = g.c_ent[tb1 + (j - tl0)]; if (!CE_IS_DEAD(ce.y)) v = ce.x; }
                 }
                 bool isnew = false;
                 if (v >= 0) {

@@ -58,8 +58,7 @@ __device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_i4(unsigned a, int4 v) { asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void smin_f64(unsigned a, double v) {   // positive doubles order like their bit patterns
-    unsigned long long old;
-    asm volatile("atom.shared.min.u64 %0, [%1], %2;" : "=l"(old) : "r"(a), "l"((unsigned long long)__double_as_longlong(v)) : "memory");
+    asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"((unsigned long long)__double_as_longlong(v)) : "memory");
 }
 #define OPAQUE(x) asm volatile("" : "+r"(x))
 
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(G, MB) k_emb2(DevCtx C, int parity, int smem_b
                         if (f < tot) {
                             const int4 rt = lds_i4(a_rowtab + 16u * k);
                             if (f < rt.y) { uint32_t ent = __ldg(&g.u_ent[rt.x + f]); if (ENT_MASK(ent)) v = ENT_COL(ent); }
-                            else v = __ldg(&g.c_ent[rt.z + f]).x;
+                            else { const int2 ce = __ldg(&g.c_ent[rt.z + f]); if (!CE_IS_DEAD(ce.y)) v = ce.x; }
                         }
                         bool isnew = false;
                         if (v >= 0) {
@@ -219,6 +218,12 @@ __global__ void __launch_bounds__(G, MB) k_emb2(DevCtx C, int parity, int smem_b
         // ---- split of the dynamic region: distances of the ball first, one region of staged entries per warp behind them
         const int dist_bytes = (total * 8 + 15) & ~15;
         bool staged = total <= RCAP && dist_bytes + NW * 256 <= dyn_bytes;
+        // a staged entry is rank(u) | rank(v) << rb | multiplicity << 2 rb: balls of up to 1,024 nodes (nearly all at 10,000
+        // agents) leave 12 bits for the multiplicity -- co-offence counts of a long-lived OC pair pass 255 late in a run --
+        // larger ones 8
+        const int rb = (total <= 1024) ? 10 : 12;
+        const unsigned rmask = (1u << rb) - 1u;
+        const int wmax = (1 << (32 - 2 * rb)) - 1;
         int rounds = 0;
         if (staged) {
             unsigned long long *dist = (unsigned long long *)(smem_raw + off_dyn);
@@ -266,18 +271,18 @@ __global__ void __launch_bounds__(G, MB) k_emb2(DevCtx C, int parity, int smem_b
                                     v = ce.x; wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
                                     bw = lds_u2(a_bp + 8u * (v >> 5));
                                     ok = wgt > 0 && ((bw.x >> (v & 31)) & 1u);  // 0: the reference divides by zero here
-                                    if (ok && wgt > 255) { S->over = 1; ok = false; }
+                                    if (ok && wgt > wmax) { S->over = 1; ok = false; }
                                 }
                             }
                             const unsigned m = __ballot_sync(FULL_MASK, ok);
                             if (ok) {
                                 const int rv = (int)bw.y + __popc(bw.x & ((1u << (v & 31)) - 1u));
                                 const int pos = wcnt + __popc(m & ltmask);
-                                const unsigned pk = (unsigned)tru | ((unsigned)rv << 12) | ((unsigned)wgt << 24);
+                                const unsigned pk = (unsigned)tru | ((unsigned)rv << rb) | ((unsigned)wgt << (2 * rb));
                                 if (pos < ecap_w) sts_u32(a_sedge + 4u * pos, pk);
                                 else if (pos - ecap_w < gcap_w) gedge[pos - ecap_w] = pk;
                                 else S->over = 1;
-                                const double wt = lds_f64(a_invw + 8u * wgt);
+                                const double wt = (wgt < 256) ? lds_f64(a_invw + 8u * wgt) : 1.0 / (double)wgt;
                                 const double du = lds_f64(a_dist + 8u * tru), dv = lds_f64(a_dist + 8u * rv);
                                 const double nv = du + wt, nu = dv + wt;   // undirected meta edge (CANON: each direction relaxes with its own weight)
                                 if (nv < dv) smin_f64(a_dist + 8u * rv, nv);
@@ -299,8 +304,8 @@ __global__ void __launch_bounds__(G, MB) k_emb2(DevCtx C, int parity, int smem_b
                     bool changed = false;
                     for (int e = lane; e < wcnt; e += 32) {
                         const unsigned pk = (e < ns) ? lds_u32(a_sedge + 4u * e) : gedge[e - ns];
-                        const int ru = pk & 0xfffu, rv = (pk >> 12) & 0xfffu;
-                        const double wt = lds_f64(a_invw + 8u * (pk >> 24));
+                        const int ru = pk & rmask, rv = (pk >> rb) & rmask, wg = pk >> (2 * rb);
+                        const double wt = (wg < 256) ? lds_f64(a_invw + 8u * wg) : 1.0 / (double)wg;
                         const double du = lds_f64(a_dist + 8u * ru), dv = lds_f64(a_dist + 8u * rv);
                         const double nv = du + wt, nu = dv + wt;
                         if (nv < dv) { smin_f64(a_dist + 8u * rv, nv); changed = true; }

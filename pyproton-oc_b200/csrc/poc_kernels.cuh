@@ -7,6 +7,8 @@
 #define RP(ptr, r, stride) ((ptr) + (size_t)(r) * (size_t)(stride))
 #include "poc_embed.cuh"
 #include "poc_embed2.cuh"
+#include "poc_embed_acc.cuh"
+#include "poc_demog.cuh"
 
 // ============================================================================ state I/O
 struct StageCols {
@@ -18,6 +20,7 @@ struct StageCols {
 
 __global__ void k_pack_agents(DevCtx C, int r, int n, StageCols S, int *err) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0) { C.n_agents[r] = n; C.u_par[r] = 0; }   // an upload lands in the first multiplex buffer
     if (a >= n) return;
     int age = S.age[a], job = S.job_level[a], edu = S.education_level[a], w = S.wealth_level[a];
     if (age < 0 || job < 0 || job > 15 || edu < 0 || edu > 15 || w < 0 || w > 15) atomicExch(err, 1);
@@ -38,6 +41,7 @@ __global__ void k_pack_agents(DevCtx C, int r, int n, StageCols S, int *err) {
     C.propensity[o] = S.propensity[a]; C.tendency[o] = S.tendency[a]; C.sentence[o] = S.sentence[a];
     C.arrest_w[o] = S.arrest_weight[a];
     C.emb_stamp[o] = 0;
+    C.ncrim_dead[o] = 0;
 }
 
 __global__ void k_unpack_agents(DevCtx C, int r, int n, StageCols S) {
@@ -121,7 +125,7 @@ __global__ void k_link_criminal(DevCtx C, int r, int n) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     Graph g = graph_of(C, r);
-    uint32_t *uent = RP(C.u_ent, r, C.ucap);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
     int2 *cent = RP(C.c_ent, r, C.ccap);
     for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
         int2 ce = cent[e];
@@ -137,13 +141,17 @@ __global__ void k_link_criminal(DevCtx C, int r, int n) {
 __global__ void k_layer_totals(DevCtx C, int r, int n) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (a < n && (RP(C.attr, r, C.Ncap)[a] & F_ALIVE)) {
+    if (a < n) {
         Graph g = graph_of(C, r);
         for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {
             uint32_t m = ENT_MASK(g.u_ent[e]);
 #pragma unroll
             for (int l = 0; l < 8; l++) cnt[l] += (m >> l) & 1;
         }
+        // Person.number_of_children is not among the uploaded columns: it starts from the offspring links
+        // (poc_upload_children replaces it)
+        RP(C.n_children, r, C.Ncap)[a] = cnt[1];
+        if (!(RP(C.attr, r, C.Ncap)[a] & F_ALIVE)) for (int l = 0; l < 8; l++) cnt[l] = 0;
     }
 #pragma unroll
     for (int l = 0; l < 8; l++) {
@@ -162,7 +170,7 @@ __global__ void k_begin_tick(DevCtx C) {
     size_t o = (size_t)r * C.Ncap + a;
     uint32_t x = C.attr[o];
     if (!(x & F_ALIVE)) return;
-    int tpy = C.params[r].ticks_per_year;
+    const int tpy = 12;   // extra._age hard-codes 12 (extra.py:359-361), whatever ticks_per_year is set to
     int dt = tick - C.birth[o];
     int age = (dt >= 0) ? dt / tpy : -((-dt + tpy - 1) / tpy);
     age = age < 0 ? 0 : (age > 255 ? 255 : age);
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
     int chunk = (n + NT - 1) / NT;
     int a_begin = min(n, tid * chunk), a_end = min(n, a_begin + chunk);
     int alive_cnt = 0;
-    int tick_now = C.ti[C.grp].tick, tpy = P.ticks_per_year;
+    const int tick_now = C.ti[C.grp].tick, tpy = 12;   // extra._age hard-codes 12 (extra.py:359-361)
     for (int a = a_begin; a < a_end; a++) {
         uint32_t x = attr[a];
         if (!(x & F_ALIVE)) continue;
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(1024) k_tendency_eps(DevCtx C, int mode) {
 // model.py:1427-1440 + extra.py:102-149.  One block per replica.  The CDF is built exactly as
 // weighted_n_of + Generator.choice build it: optional min-shift, left-to-right sum, p/sum, sequential
 // cumsum, divide by the last element; one lane per cell runs the two order-defined chains.
-__global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
+__global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles, int allow_fit) {
     extern __shared__ double wt_sm[];
     int tick = C.ti[C.grp].tick;
     int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
@@ -521,7 +529,9 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles) {
     }
     __syncthreads();
     int total = off[nc], ptotal = poff[nc];
-    const bool fit = ptotal <= smem_doubles;
+    // allow_fit = 0: the launch reserved the chain windows only (populations too large for the whole-cell layout), not the
+    // cell-of-eight bytes behind the weights, whatever this replica's own alive count happens to be
+    const bool fit = allow_fit && ptotal <= smem_doubles;
     unsigned char *cellof8 = (unsigned char *)(wt_sm + smem_doubles);   // cell of every block of eight positions
     const int *woff = fit ? poff : off;
     double *wt = fit ? wt_sm : cdf;
@@ -1114,7 +1124,7 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     // ---- receiving rows: one warp per row.  An old entry moves right by the new links of this row that sort
     // before it (and takes the new count if a pair names it); a new link goes behind the old entries that sort
     // before it and the new links before it.
-    uint32_t *uent_rw = RP(C.u_ent, r, C.ucap);
+    uint32_t *uent_rw = const_cast<uint32_t *>(g.u_ent);
     int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
     for (int k = w; k < nins; k += nw) {
         int pb = ins[k], pe = (k + 1 < nins) ? ins[k + 1] : nu;
@@ -1271,6 +1281,7 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
                         }
                         for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
                             int2 ce = g.c_ent[e];
+                            if (CE_IS_DEAD(ce.y)) continue;
                             if (attr[ce.x] & F_OC) { sumco += CE_CNT(ce.y); cntoc++; if (!CE_SMASK(ce.y)) nn++; }
                         }
                         pos = (double)(nn + sumco - cntoc);
@@ -1347,7 +1358,7 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
     }
     // A11 get_caught
     double *sentence = RP(C.sentence, r, C.Ncap);
-    uint32_t *uent = RP(C.u_ent, r, C.ucap);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
     int2 *cent_rw = const_cast<int2 *>(g.c_ent);
     for (int i = 0; i < nfound; i++) {
         int a = gmem[found[i]];
@@ -1418,6 +1429,7 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap), *nct = RP(C.ncrimes_tick, r, C.Ncap);
     const int32_t *crp = graph_of(C, r).c_rowptr;
+    const int32_t *ncd = RP(C.ncrim_dead, r, C.Ncap);
     const double *tend = RP(C.tendency, r, C.Ncap);
     enum { I_OC = 0, I_PRIS, I_LINK, I_SUMCR, I_OCOC, I_ALIVE, I_AGE, I_AGE2, I_EDU, I_EDU2, I_CR2, I_EMPL, I_FAC, I_STUD, NI };
     long long vi[NI];
@@ -1432,7 +1444,7 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
         if (x & F_OC) { vi[I_OC]++; vi[I_OCOC] += nct[a]; }
         vi[I_PRIS] += (x & F_PRISONER) != 0; vi[I_EMPL] += (x & F_HASJOB) != 0; vi[I_FAC] += (x & F_FAC) != 0;
         vi[I_STUD] += (x & F_HASSCHOOL) != 0;
-        vi[I_LINK] += crp[a + 1] - crp[a];
+        vi[I_LINK] += crp[a + 1] - crp[a] - ncd[a];
         vi[I_SUMCR] += c; vi[I_CR2] += c * c; vi[I_AGE] += age; vi[I_AGE2] += age * age; vi[I_EDU] += edu; vi[I_EDU2] += edu * edu;
         double tv = tend[a];
         vd[0] += tv; vd[1] += tv * tv;
@@ -1444,25 +1456,46 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     }
     __shared__ long long wi[16][NI];
     __shared__ double wd[16][2];
+    __shared__ double s_mean[4], s_ss[4];   // tendency, age, education level, crimes committed: mean and sum of squared deviations
     if (lane_id() == 0) { for (int k = 0; k < NI; k++) wi[warp_id()][k] = vi[k]; for (int k = 0; k < 2; k++) wd[warp_id()][k] = vd[k]; }
     __syncthreads();
+    const int nw = blockDim.x >> 5;
     if (tid == 0) {
-        int nw = blockDim.x >> 5;
         for (int ww = 1; ww < nw; ww++) { for (int k = 0; k < NI; k++) vi[k] += wi[ww][k]; for (int k = 0; k < 2; k++) vd[k] += wd[ww][k]; }
+        double nn = (double)vi[I_ALIVE], inv = nn > 0 ? 1.0 / nn : 0.0;
+        s_mean[0] = vd[0] * inv; s_mean[1] = (double)vi[I_AGE] * inv; s_mean[2] = (double)vi[I_EDU] * inv; s_mean[3] = (double)vi[I_SUMCR] * inv;
+        s_ss[0] = s_ss[1] = s_ss[2] = s_ss[3] = 0.0;
+    }
+    __syncthreads();
+    {   // second pass: np.std is sqrt(mean((x - mean)^2)) (model.py:1698-1709); E[x^2] - mean^2 would cancel
+        double q[4] = { 0.0, 0.0, 0.0, 0.0 };
+        const double m0 = s_mean[0], m1 = s_mean[1], m2 = s_mean[2], m3 = s_mean[3];
+        for (int a = tid; a < n; a += blockDim.x) {
+            uint32_t x = attr[a];
+            if (!(x & F_ALIVE)) continue;
+            double d0 = tend[a] - m0, d1 = (double)attr_age(x) - m1, d2 = (double)attr_edu(x) - m2, d3 = (double)ncr[a] - m3;
+            q[0] += d0 * d0; q[1] += d1 * d1; q[2] += d2 * d2; q[3] += d3 * d3;
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            for (int k = 0; k < 4; k++) q[k] += __shfl_xor_sync(FULL_MASK, q[k], o);
+        if (lane_id() == 0) for (int k = 0; k < 4; k++) atomicAdd(&s_ss[k], q[k]);
+    }
+    __syncthreads();
+    if (tid == 0) {
         const int *cn = RP(C.counters, r, CN_COUNT);
         const int *pv = RP(C.prev_counters, r, CN_COUNT);
         const long long *lt = RP(C.layer_tot, r, 8);
         double *row = C.reporters + ((size_t)r * C.Tcap + t) * POC_N_REPORTERS;
         double nn = (double)vi[I_ALIVE], inv = nn > 0 ? 1.0 / nn : 0.0;
-        auto sd = [&](double s1, double s2) { double m = s1 * inv, v = s2 * inv - m * m; return v > 0 ? sqrt(v) : 0.0; };
+        auto sd = [&](int k) { double v = s_ss[k] * inv; return v > 0 ? sqrt(v) : 0.0; };
         row[0] = cn[CN_NUMBER_CRIMES]; row[1] = cn[CN_SIZE_FAILS]; row[2] = cn[CN_FAC_CRIMES]; row[3] = cn[CN_FAC_FAILS];
         row[4] = cn[CN_BIG_CRIME]; row[5] = cn[CN_OFFSPRING_RECRUITED]; row[6] = cn[CN_PEOPLE_JAILED];
         row[7] = (double)vi[I_OC]; row[8] = (double)vi[I_PRIS]; row[9] = (double)vi[I_LINK]; row[10] = (double)vi[I_SUMCR];
-        row[11] = (double)vi[I_OCOC]; row[12] = vd[0] * inv; row[13] = sd(vd[0], vd[1]); row[14] = nn;
+        row[11] = (double)vi[I_OCOC]; row[12] = s_mean[0]; row[13] = sd(0); row[14] = nn;
         row[15] = C.crime_mult[r];
-        row[16] = (double)vi[I_AGE] * inv; row[17] = sd((double)vi[I_AGE], (double)vi[I_AGE2]);
-        row[18] = (double)vi[I_EDU] * inv; row[19] = sd((double)vi[I_EDU], (double)vi[I_EDU2]);
-        row[20] = (double)vi[I_SUMCR] * inv; row[21] = sd((double)vi[I_SUMCR], (double)vi[I_CR2]);
+        row[16] = s_mean[1]; row[17] = sd(1);
+        row[18] = s_mean[2]; row[19] = sd(2);
+        row[20] = s_mean[3]; row[21] = sd(3);
         row[22] = (double)vi[I_EMPL]; row[23] = (double)vi[I_FAC]; row[24] = (double)vi[I_STUD];
         // sibling, offspring, parent, partner, household, friendship, professional, school
         for (int l = 0; l < 8; l++) row[25 + l] = (double)lt[l];

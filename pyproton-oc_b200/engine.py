@@ -45,6 +45,17 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+class _PackedState:
+    __slots__ = ("blob", "holder", "n")
+
+    def __init__(self, blob, holder, n):
+        self.blob, self.holder, self.n = blob, holder, n
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.blob.nbytes)
+
+
 class CrimeEngine:
     def __init__(self, n_replicas: int, max_agents: int, max_static_entries: int, max_criminal_entries: int,
                  device: int = 0):
@@ -56,6 +67,7 @@ class CrimeEngine:
                                     int(max_criminal_entries), C.byref(h)))
         self.h = h
         self.R, self.max_agents = n_replicas, max_agents
+        self.max_static, self.max_criminal = int(max_static_entries), int(max_criminal_entries)
         self.n_agents = [0] * n_replicas
         self.device = device
         self._keepalive = []   # host arrays of uploads queued with wait=False, released at sync()
@@ -119,6 +131,45 @@ class CrimeEngine:
             self._ck(self.L.poc_build_graph_async(self.h, replica))
             self._keepalive.append(keep)
 
+    @staticmethod
+    def pack_state(st: Dict[str, np.ndarray], pinned: bool = False):
+        """One contiguous block holding the whole state (poc_pack_state): build it once per distinct initial state and
+        hand it to upload_packed for every replica that starts from it.  pinned=True returns a pinned torch uint8
+        tensor's numpy view (asynchronous copies); otherwise a plain numpy array."""
+        L = _cabi.lib()
+        n = int(len(st["alive"]))
+        ne = np.array([len(st["col_%d" % l]) for l in range(NUM_LAYERS)], dtype=np.int64)
+        size = int(L.poc_packed_size(n, ne.ctypes.data))
+        if pinned:
+            import torch
+            holder = torch.empty(size, dtype=torch.uint8).pin_memory()
+            blob = holder.numpy()
+        else:
+            holder = blob = np.empty(size, np.uint8)
+        cols, keep = AgentCols(), []
+        for f, key in STATE_KEYS.items():
+            arr = np.ascontiguousarray(st[key], dtype=_DTYPES[f])
+            keep.append(arr)
+            setattr(cols, f, arr.ctypes.data)
+        rps = (C.c_void_p * NUM_LAYERS)()
+        cls = (C.c_void_p * NUM_LAYERS)()
+        for l in range(NUM_LAYERS):
+            rp, col = _i32(st["rowptr_%d" % l]), _i32(st["col_%d" % l])
+            keep += [rp, col]
+            rps[l], cls[l] = rp.ctypes.data, (col.ctypes.data if len(col) else None)
+        co = _i32(st["co_off"])
+        rc = L.poc_pack_state(n, C.byref(cols), rps, cls, co.ctypes.data if len(co) else None, blob.ctypes.data, size)
+        if rc:
+            raise PocError("poc_pack_state failed (%d)" % rc)
+        blob_obj = _PackedState(blob, holder, n)
+        return blob_obj
+
+    def upload_packed(self, replica: int, packed: "_PackedState"):
+        """Queue the upload of a packed state (one copy + the unpack / merge kernels); errors surface at sync()."""
+        self._ck(self.L.poc_upload_packed(self.h, replica, packed.blob.ctypes.data, packed.blob.nbytes))
+        self.n_agents[replica] = packed.n
+        self._keepalive.append(packed)
+
     def download_agents(self, replica: int = 0, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """Agent columns of one replica.  `out` (a dict from agent_buffers()) is filled in place when given: writing
         into already-touched host memory is about five times faster than into freshly allocated arrays."""
@@ -157,6 +208,39 @@ class CrimeEngine:
             if l == CRIMINAL:
                 st["co_off"] = co
         return st
+
+    # ------------------------------------------------------------------ demography phases
+    PHASE_BABY, PHASE_FRIENDS, PHASE_DIE = 1, 2, 4
+
+    def set_demography(self, d):
+        self._ck(self.L.poc_set_demography(self.h, C.byref(d)))
+
+    def set_phases(self, mask: int):
+        """Which of make_baby (1) / make_friends (2) / make_people_die (4) run_ticks runs every tick (default 0)."""
+        self._ck(self.L.poc_set_phases(self.h, int(mask)))
+        self._phases = int(mask)
+
+    def _refresh_counts(self):
+        v = C.c_int32(0)
+        for r in range(self.R):
+            self._ck(self.L.poc_n_agents(self.h, r, C.byref(v)))
+            self.n_agents[r] = int(v.value)
+
+    def run_phase(self, phase: int, tick: int, philox_keys: Sequence[int]):
+        keys = np.ascontiguousarray(philox_keys, dtype=np.uint64)
+        assert len(keys) == self.R
+        self._ck(self.L.poc_run_phase(self.h, int(phase), int(tick), keys.ctypes.data))
+        self._refresh_counts()
+
+    def upload_children(self, replica: int, n_children):
+        a = _i32(n_children)
+        assert len(a) == self.n_agents[replica]
+        self._ck(self.L.poc_upload_children(self.h, replica, a.ctypes.data))
+
+    def download_children(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros(self.n_agents[replica], np.int32)
+        self._ck(self.L.poc_download_children(self.h, replica, out.ctypes.data))
+        return out
 
     # ------------------------------------------------------------------ hot path
     def begin_tick(self, tick: int):
@@ -245,6 +329,8 @@ class CrimeEngine:
                 raise ValueError("run_ticks: out must be a contiguous float64 array of shape (R, n_ticks, %d)" % N_REPORTERS)
         self._ck(self.L.poc_run_ticks(self.h, tick0, n_ticks, keys.ctypes.data,
                                       rep.ctypes.data if rep is not None else None))
+        if getattr(self, "_phases", 0) & 1:
+            self._refresh_counts()   # births added agent slots on the device
         return rep
 
     def run_ticks_device(self, tick0: int, n_ticks: int, philox_keys: Sequence[int]):
@@ -282,6 +368,14 @@ class CrimeEngine:
         names = ["emb_requests", "emb_full", "emb_bytes", "emb_nodes", "search_crimes", "search_bytes",
                  "search_candidates", "spare"] + ["phase%d" % i for i in range(8)]
         return {k: int(v) for k, v in zip(names, s)}
+
+    def stats_per_replica(self) -> Dict[str, np.ndarray]:
+        """The same counters per replica: name -> uint64 [R]."""
+        a = np.zeros((self.R, 16), np.uint64)
+        self._ck(self.L.poc_read_stats(self.h, a.ctypes.data, 0))
+        names = ["emb_requests", "emb_full", "emb_bytes", "emb_nodes", "search_crimes", "search_bytes",
+                 "search_candidates", "spare"] + ["phase%d" % i for i in range(8)]
+        return {k: a[:, i].copy() for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------ timers
     def set_timing(self, on: bool):
@@ -327,6 +421,24 @@ class CrimeEngine:
         out = np.zeros(len(a), np.float64)
         self._ck(self.L.poc_embeddedness(self.h, replica, len(a), a.ctypes.data, out.ctypes.data))
         return out
+
+    def embeddedness_accumulated(self, agents: Sequence[int], over=None, replica: int = 0) -> np.ndarray:
+        """Test hook: the evaluations `agents`, in this order, on the accumulating tick-global meta graph,
+        exactly as one reference commit_crimes computes them (model.py:1515-1536).  over: int32 [m, 4] rows
+        (evaluation index, a, b, multiplicity in use).  The values become the cache of the next commit_crimes."""
+        a = _i32(agents)
+        ov = np.zeros((0, 4), np.int32) if over is None else np.ascontiguousarray(over, dtype=np.int32).reshape(-1, 4)
+        out = np.zeros(len(a), np.float64)
+        self._ck(self.L.poc_embeddedness_accumulated(self.h, replica, len(a), a.ctypes.data, len(ov),
+                                                     ov.ctypes.data if len(ov) else None, out.ctypes.data))
+        return out
+
+    def preload_embeddedness(self, agents: Sequence[int], values, replica: int = 0):
+        """Test hook: hand the next commit_crimes its per-tick oc_embeddedness cache (entities.py:531)."""
+        a = _i32(agents)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert len(a) == len(v)
+        self._ck(self.L.poc_preload_embeddedness(self.h, replica, len(a), a.ctypes.data, v.ctypes.data))
 
     def candidate_weights(self, selfs: Sequence[int], cands: Sequence[int], replica: int = 0) -> np.ndarray:
         a, b = _i32(selfs), _i32(cands)

@@ -61,8 +61,9 @@ def partition(n_items: int, world: int, rank: int) -> List[int]:
 
 # ---------------------------------------------------------------------------------------------- execution
 def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] = None) -> Callable:
-    """Returns runner(batch of run-arg dicts) -> float64 array [len(batch), num_ticks, len(REPORTER_NAMES)]
-    executing the whole batch as one CrimeEngine (one replica per run)."""
+    """Returns runner(batch of run-arg dicts) -> float64 array [len(batch), num_ticks + 1, len(REPORTER_NAMES)]
+    executing the whole batch as one CrimeEngine (one replica per run).  Row 0 of a run is the state after setup
+    (the row the reference's DataCollector collects at model.py:1042), row t the state after tick t."""
     from .engine import CrimeEngine
 
     def runner(batch: List[Dict]) -> np.ndarray:
@@ -78,7 +79,9 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
                 from . import synth
                 m.load_state(synth.synthetic_state(m.initial_agents, seed=m.seed, template=template,
                                                    num_oc_persons=m.num_oc_persons,
-                                                   likelihood_of_facilitators=m.likelihood_of_facilitators))
+                                                   likelihood_of_facilitators=m.likelihood_of_facilitators,
+                                                   nat_propensity_m=m.nat_propensity_m,
+                                                   nat_propensity_sigma=m.nat_propensity_sigma))
             models.append(m)
             states.append(m.state_dict())
         ticks = {m.num_ticks for m in models}
@@ -91,7 +94,11 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
                 E.set_params(m._params(), replica=r)
                 E.upload_state(r, st, wait=False)
             E.sync()   # input errors of the queued uploads surface here
-            rep = E.run_ticks(1, T, [m._philox_key for m in models], reporters=True)
+            E.crime_multiplier()   # ProtonOC.setup: model.py:1029-1030
+            E.tendency()
+            rep = np.zeros((len(batch), T + 1, len(REPORTER_NAMES)), np.float64)
+            rep[:, 0] = E.report()
+            rep[:, 1:] = E.run_ticks(1, T, [m._philox_key for m in models], reporters=True)
             cn, _ = E.counters()
             if cn[:, 9].any():
                 raise RuntimeError("crime path error codes %s" % cn[:, 9].tolist())
@@ -118,7 +125,9 @@ def run_ensemble(args: List[Dict], runner: Callable, replicas_per_batch: int = 6
     shape = torch.zeros(3, dtype=torch.int64)
     if local is not None:
         shape = torch.tensor(local.shape[0:3], dtype=torch.int64)
-    dev = device if device is not None else torch.device("cpu")
+    if device is None:   # NCCL moves device tensors only; gloo (the CPU tests) host tensors
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    dev = device
     # ranks may hold different run counts: exchange the shapes, pad to the maximum, gather, trim
     shapes = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(shapes, shape.to(dev))
@@ -204,11 +213,25 @@ class OverrideMode(BaseMode):
             for a in self.args:
                 self._single_run(a)
             return
+        # a run without a seed draws one (run_modes.py:80-81); here before the batch, so that every rank and the
+        # frames written below see the same value
+        seeds = [a["seed"] if a["seed"] is not None else int.from_bytes(os.urandom(4), "little") for a in self.args]
+        if dist is not None:
+            box = [seeds]
+            dist.broadcast_object_list(box, src=0)
+            seeds = box[0]
+        for a, sd in zip(self.args, seeds):
+            a["seed"] = sd
         rep = run_ensemble(self.args, gpu_batch_runner(device, template), replicas_per_batch=int(self.parallel), dist=dist)
         if rep is None:
             return
         for a, rows in zip(self.args, rep):
-            df = reporter_frame(rows)
+            # the same pickle as _single_run writes: the reference's (T+1) x 80 model-vars frame (extra.py:246-274)
+            m = ProtonOC(seed=a["seed"], collect_agents=False)
+            if a["source_override"] is not None:
+                m.override_dict(a["source_override"])
+            m.choose_intervention_setting()
+            df = m.frame_from_device_rows(rows)
             if a["snapshot"]:
                 df = df.iloc[list(a["snapshot"])]
             with open(os.path.join(a["save_path"], a["filename"] + ".pkl"), "wb") as f:

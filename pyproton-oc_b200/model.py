@@ -627,17 +627,35 @@ class ProtonOC:
         cn, _ = e.counters()
         if cn[0, 9]:
             raise RuntimeError("crime path error code %d" % cn[0, 9])
-        floats = {"criminal_tendency_mean", "criminal_tencency_sd", "crime_multiplier", "age_mean", "age_sd",
-                  "education_level_mean", "education_level_sd", "num_crime_committed_mean", "num_crime_committed_sd"}
-        skip = {"tick", "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code"}
         for t in range(self.num_ticks):
-            for name, v in zip(REPORTER_NAMES, rep[t]):  # every calculate_fast_reporters column comes from k_report
-                if name not in skip:
-                    setattr(self, name, float(v) if name in floats else int(v))
-            self.number_jobs = self.employed
+            self._apply_device_row(rep[t])   # every calculate_fast_reporters column comes from k_report
             self.schedule.step()
             self.datacollector.collect(self)
             self.tick += 1
+
+    _ROW_SKIP = {"tick", "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code"}
+
+    def _apply_device_row(self, row) -> None:
+        for name, v in zip(REPORTER_NAMES, row):
+            if name not in self._ROW_SKIP:
+                setattr(self, name, float(v) if name in self._FLOAT_REPORTERS else int(v))
+        self.number_jobs = self.employed
+
+    def frame_from_device_rows(self, rows) -> "pd.DataFrame":
+        """The (T+1) x 80 model-vars frame of the reference's DataCollector (extra.py:246-274; row 0 collected after
+        setup, model.py:1042, row t after step t, :287) from device reporter rows [T+1][len(REPORTER_NAMES)] whose row 0
+        is the state after setup: what a batched run (override mode on the GPU) pickles, so that it has the columns,
+        the row count and the snapshot indices of a single run."""
+        self.datacollector = _DataCollector(MODEL_REPORTERS)
+        self.calculate_arrest_rate()   # ProtonOC.setup (model.py:1031)
+        self.tick = 1
+        for i, row in enumerate(rows):
+            self._apply_device_row(row)
+            if i > 0:
+                self.tick = i
+            self.datacollector.collect(self)
+        self.tick = len(rows)
+        return self.datacollector.get_model_vars_dataframe()
 
     def save_data(self, save_dir: str, name: str, snapshot: tuple):
         model_data = self.datacollector.get_model_vars_dataframe()

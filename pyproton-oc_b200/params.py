@@ -10,7 +10,7 @@ from typing import Dict, Iterable, Optional
 import numpy as np
 
 from . import tables
-from ._cabi import MAX_CELLS, MAX_TAB, Params
+from ._cabi import MAX_CELLS, MAX_TAB, Demography, Params
 
 # the model attributes the hot path reads (model.py:108-134, 82-83) with the reference defaults
 HOT_PATH_DEFAULTS = dict(
@@ -75,3 +75,24 @@ def make_params(attrs: Optional[Dict] = None, c_range=None, co_offenders=None, c
               "ticks_per_year"]:
         setattr(p, k, int(d[k]))
     return p
+
+
+def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None) -> Demography:
+    """poc_demography for the phases of SURVEY.md 8(f).  mortality: (female[ages], male[ages]) yearly probabilities
+    (initial_mortality_rates.csv, entities.py:615-626), fertility: [3][64] yearly by [min(children, 2)][age]
+    (initial_fertility_rates.csv, entities.py:605-613); defaults: the reference's Palermo tables."""
+    fem, mal = mortality if mortality is not None else (tables.MORTALITY_FEMALE, tables.MORTALITY_MALE)
+    fert = fertility if fertility is not None else tables.FERTILITY
+    d = Demography()
+    for a in range(128):
+        d.mort[0][a] = float(fem[a]) if a < len(fem) else 1.0
+        d.mort[1][a] = float(mal[a]) if a < len(mal) else 1.0
+    for k in range(3):
+        for a in range(64):
+            d.fert[k][a] = float(fert[k][a])
+    for i, v in enumerate(tables.poisson_cdf(3.0, 32)):
+        d.poisson_cdf[i] = v
+    for i, v in enumerate(tables.lognormal_quantiles(nat_propensity_m, nat_propensity_sigma, 1024)):
+        d.prop_q[i] = v
+    d.mort_max_age, d.n_prop = len(fem) - 1, 1024
+    return d

@@ -215,21 +215,62 @@ def test_determinism(P):
     assert not np.array_equal(c.state_dict()["num_crimes_committed"], sa["num_crimes_committed"])
 
 
+def _same_column(a, b):
+    """Equal, both NaN / None, or floats within 1e-12 relative (the setup row's standard deviations come from the host
+    in a single run and from the reporter kernel in a batch)."""
+    for x, y in zip(a, b):
+        if x == y or (x != x and y != y):
+            continue
+        if isinstance(x, float) and isinstance(y, float) and abs(x - y) <= 1e-12 * max(abs(x), abs(y)):
+            continue
+        return False
+    return True
+
+
 def test_ensemble_on_gpu_equals_individual_runs(P, tmp_path):
     from pyproton_oc_b200 import ensemble
     overrides = [{"initial_agents": 300, "num_ticks": 18, "number_arrests_per_year": 60},
                  {"initial_agents": 300, "num_ticks": 18, "intervention": "facilitators", "num_oc_persons": 200}]
     args = ensemble.seed_sweep(3, overrides, save_path=str(tmp_path))
     rep = ensemble.run_ensemble(args, ensemble.gpu_batch_runner(0), replicas_per_batch=4)
-    assert rep.shape == (6, 18, 40)
+    assert rep.shape == (6, 19, 40)   # row 0 = after setup, like the reference's DataCollector (model.py:1042)
     for i in (0, 4):
         m = P.ProtonOC(seed=args[i]["seed"])
         m.override_dict(args[i]["source_override"])
         m.run()
         df = m.datacollector.get_model_vars_dataframe()
-        assert df["number_crimes"].tolist()[1:] == rep[i, :, 0].astype(int).tolist()
-        assert df["current_oc_members"].tolist()[1:] == rep[i, :, 7].astype(int).tolist()
-        assert df["people_jailed"].tolist()[1:] == rep[i, :, 6].astype(int).tolist()
+        assert df["number_crimes"].tolist() == rep[i, :, 0].astype(int).tolist()
+        assert df["current_oc_members"].tolist() == rep[i, :, 7].astype(int).tolist()
+        assert df["people_jailed"].tolist() == rep[i, :, 6].astype(int).tolist()
+        # the frame a batched override-mode run pickles = the frame of the single run, column for column
+        m2 = P.ProtonOC(seed=args[i]["seed"])
+        m2.override_dict(args[i]["source_override"])
+        m2.choose_intervention_setting()
+        df2 = m2.frame_from_device_rows(rep[i])
+        assert list(df2.columns) == list(df.columns) and df2.shape == df.shape == (19, 80)
+        for c in df.columns:
+            assert _same_column(df[c].tolist(), df2[c].tolist()), c
+
+
+def test_override_mode_parallel_pickles_the_reference_frame(P, tmp_path):
+    """OverrideMode with `parallel` set (batched replicas on the GPU) writes the same pickle as the serial path: the
+    reference's (T+1) x 80 model-vars frame with the same snapshot indices (run_modes.py:73-88, model.py:1604-1633)."""
+    import json
+    import pickle
+    from pyproton_oc_b200 import ensemble
+    src = tmp_path / "sweep.json"
+    src.write_text(json.dumps({"a": {"initial_agents": 250, "num_ticks": 14}, "b": {"initial_agents": 250, "num_ticks": 14, "num_oc_persons": 150}}))
+    (tmp_path / "ser").mkdir(); (tmp_path / "par").mkdir()
+    ensemble.OverrideMode(str(src), str(tmp_path / "ser"), (0, 7, 14), False, 77, None).run()
+    ensemble.OverrideMode(str(src), str(tmp_path / "par"), (0, 7, 14), False, 77, 2).run()
+    names = sorted(p.name for p in (tmp_path / "ser").iterdir())
+    assert names == sorted(p.name for p in (tmp_path / "par").iterdir()) and len(names) == 2
+    for nme in names:
+        a = pickle.load(open(tmp_path / "ser" / nme, "rb"))
+        b = pickle.load(open(tmp_path / "par" / nme, "rb"))
+        assert a.shape == b.shape == (3, 80) and list(a.columns) == list(b.columns) and list(a.index) == list(b.index)
+        for c in a.columns:
+            assert _same_column(a[c].tolist(), b[c].tolist()), (nme, c)
 
 
 def test_whole_run_distribution_vs_reference(P):

@@ -40,21 +40,25 @@ def test_tick_replay(path):
     fx = U.load_fixture(path)
     S = O.OracleState(U.pre_state(fx))
     P = O.make_params(U.fixture_params(fx), co_offenders=U.fixture_co_offenders(fx))
+    # candidates of OC initiators are ranked with oc_embeddedness as the reference had it in this very tick: on the
+    # accumulating meta graph, in the recorded order (H1 exact mode).  Every recorded evaluation must match.
+    if len(fx["emb_slot"]):
+        acc = S.embeddedness_accumulated(fx["emb_slot"], int(fx["param_oc_embeddedness_radius"]), fx["emb_over"])
+        assert np.all(np.abs(acc - fx["emb_accumulated"]) <= 1e-9 * np.abs(fx["emb_accumulated"]))
+        S.preload_embeddedness(fx["emb_slot"], fx["emb_accumulated"])   # the reference's own values: keys bit-exact
     res = S.commit_crimes(P, int(fx["tick"]), float(fx["crime_multiplier"]), U.fixture_replay(fx))
     assert res["out"]["error"] == 0
     # A3: initiators and group sizes are bit-exact given the reference's uniforms
     assert np.array_equal(res["initiator"], fx["crime_initiator"])
     assert np.array_equal(res["k"], fx["crime_k"])
     assert res["out"]["d_number_crimes"] == int(fx["d_number_crimes"])
-    # A6: groups equal, or differ only by a permutation among equal keys (H2) /
-    # keys equal within the H1 band for OC initiators
+    # A6: groups equal, or differ only by a permutation among EXACTLY equal keys (H2), OC initiators included
     exact = True
     for c, (g, r) in enumerate(zip(res["groups"], U.ref_groups(fx))):
         if list(g) == U.canonical_group(r):
             continue
         exact = False
-        rel = 0.05 if fx["crime_oc"][c] else 0.0
-        assert U.tie_explains(fx, c, g, rel=rel), "crime %d: %s vs %s" % (c, list(g), U.canonical_group(r))
+        assert U.tie_explains(fx, c, g, rel=0.0), "crime %d: %s vs %s" % (c, list(g), U.canonical_group(r))
     if not exact:
         return
     # with identical groups everything downstream is integer-exact: A8, A9 and counters
@@ -105,9 +109,10 @@ def test_rings_and_keys_match_reference_records():
 
 
 def test_embeddedness_vs_reference_fresh_graph():
-    """A7 within 1e-6 relative (north-star tolerance) of the reference evaluated on a fresh
-    meta_graph, for every recorded evaluation whose ball has no asymmetric multiplicity
-    (where the reference itself depends on set order).  Observed: <= 2e-11."""
+    """A7 (production formulation: the caller's own ball) against the reference evaluated on a fresh meta_graph, for
+    EVERY recorded evaluation.  Balls without asymmetric multiplicities: the production function itself, <= 1e-9
+    relative (the north star asks 1e-6).  Balls with them (one-sided clears, Q11: the reference keeps whichever
+    direction its set iteration visited last): the same evaluation with the recorded direction winners, <= 1e-9."""
     n_sym = n_asym = 0
     for path in U.golden_files("tick"):
         fx = U.load_fixture(path)
@@ -115,14 +120,40 @@ def test_embeddedness_vs_reference_fresh_graph():
             continue
         S = O.OracleState(U.pre_state(fx))
         R = int(fx["param_oc_embeddedness_radius"])
-        for a, want in zip(fx["emb_slot"], fx["emb_fresh"]):
+        over = fx["emb_over"]
+        for j, (a, want) in enumerate(zip(fx["emb_slot"], fx["emb_fresh"])):
             got, _, _, nasym = S.embeddedness_ex(int(a), R)
-            if nasym:
+            mine = over[over[:, 0] == j].copy()
+            if nasym == 0:
+                assert len(mine) == 0
+                n_sym += 1
+                assert abs(got - want) <= 1e-9 * abs(want), (path, a, got, want)
+            else:
                 n_asym += 1
-                continue
-            n_sym += 1
-            assert abs(got - want) <= 1e-6 * abs(want), (path, a, got, want)
-    assert n_sym >= 30
+                mine[:, 0] = 0
+                exact = S.embeddedness_accumulated([int(a)], R, mine)[0]
+                assert abs(exact - want) <= 1e-9 * abs(want), (path, a, exact, want)
+                # the production value (larger multiplicity on such pairs) stays close: the pairs are few (observed <= 7 %)
+                assert abs(got - want) <= 0.2 * abs(want), (path, a, got, want)
+    assert n_sym >= 800 and n_asym >= 300 and n_sym + n_asym >= 2000
+
+
+def test_embeddedness_accumulated_matches_every_recorded_evaluation():
+    """H1 exact mode: on the accumulating tick-global meta graph, in the recorded order, every oc_embeddedness value
+    of every fixture equals what the reference computed inside its own commit_crimes (<= 1e-9 relative; none skipped),
+    at 100 ... 10,000 agents."""
+    n = n10k = 0
+    for path in U.golden_files("tick"):
+        fx = U.load_fixture(path)
+        if not len(fx["emb_slot"]):
+            continue
+        S = O.OracleState(U.pre_state(fx))
+        acc = S.embeddedness_accumulated(fx["emb_slot"], int(fx["param_oc_embeddedness_radius"]), fx["emb_over"])
+        want = fx["emb_accumulated"]
+        assert np.all(np.abs(acc - want) <= 1e-9 * np.abs(want)), path
+        n += len(want)
+        n10k += len(want) if len(fx["pre_alive"]) > 9000 else 0
+    assert n >= 2000 and n10k >= 250
 
 
 # ------------------------------------------------------------------ the reference's known-answer tests

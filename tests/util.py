@@ -70,22 +70,34 @@ def canonical_group(g: Iterable[int]) -> List[int]:
 
 
 def tie_explains(fx, crime: int, mine: Iterable[int], rel: float = 0.0) -> bool:
-    """True when `mine` and the reference's group for this crime differ only by a
-    permutation among candidates whose sort keys are equal or, with
-    rel > 0, equal within `rel` (H1: accumulated vs own-ball embeddedness)."""
+    """True when `mine` and the reference's group for this crime differ only by a permutation among ranked
+    candidates whose sort keys are equal (`rel` > 0: equal within that relative tolerance, used for
+    OC initiators whose keys carry a 1/dist sum that the reference adds up in set order).  The ranked accomplices are
+    the members with a recorded key; a member without one is the facilitator drawn after the rings
+    (entities.py:439-445), whose pool -- the facilitators near the accomplices -- follows from who was picked, so a
+    tie among the ranked ones may add, drop or change it."""
     ref = [int(x) for x in ref_groups(fx)[crime]]
     mine = [int(x) for x in mine]
-    if ref[-1] != mine[-1] or len(ref) != len(mine):
+    if ref[-1] != mine[-1]:
         return False
     keys = ref_keys(fx, crime)
-    fac = int(fx["replay_fac_pick"][crime])  # a facilitator drawn after the rings is not a ranked candidate
-    ra = [m for m in ref[:-1] if not (m == fac and m not in keys)]
-    ma = [m for m in mine[:-1] if not (m == fac and m not in keys)]
-    if len(ra) != len(ma) or any(m not in keys for m in ma):
+    ra, ma = [m for m in ref[:-1] if m in keys], [m for m in mine[:-1] if m in keys]
+    if len(ref) - 1 - len(ra) > 1 or len(mine) - 1 - len(ma) > 1:
         return False
-    ka = sorted(keys[m] for m in ra)
-    kb = sorted(keys[m] for m in ma)
+    fac = pre_state_facilitators(fx)
+    if any(not fac[m] for m in ref[:-1] + mine[:-1] if m not in keys):
+        return False
+    if sorted(ra) == sorted(ma):
+        return False    # the ranked picks agree, so the rest must as well: not a tie
+    # a facilitator among the ranked picks raises the target by one (Q6): compare the common prefix of the sorted keys
+    ka, kb = sorted(keys[m] for m in ra), sorted(keys[m] for m in ma)
+    if len(ka) != len(kb) and not any(fac[m] for m in ra + ma):
+        return False
     return all(abs(x - y) <= rel * max(abs(x), abs(y)) for x, y in zip(ka, kb))
+
+
+def pre_state_facilitators(fx):
+    return fx["pre_facilitator"]
 
 
 # ---------------------------------------------------------------- hand-built states
