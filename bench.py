@@ -413,8 +413,19 @@ def main():
             if i >= 1:
                 e2e_times.append(dt * 1e3)
         e2e_ms = max_over_ranks(float(np.mean(e2e_times)))
+        # where the end-to-end time goes (one extra step with a synchronisation after every part; single GPU only)
+        breakdown = None
+        if dist is None:
+            t0 = time.perf_counter(); W.upload_all(); E.sync()
+            t1 = time.perf_counter(); E.run_ticks(W.tick0, T, W.keys, reporters=True, out=host_rep)
+            t2 = time.perf_counter()
+            for r in range(Rw):
+                E.download_agents(r, out=host_cols[r])
+            E.sync()
+            t3 = time.perf_counter()
+            breakdown = {"upload": 1e3 * (t1 - t0), "run_and_reporter_rows": 1e3 * (t2 - t1), "agent_columns": 1e3 * (t3 - t2)}
         return {"value": W.agent_ticks * world / (e2e_ms / 1e3), "unit": "agent-ticks/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(W.h2d), "d2h_bytes_per_step": int(d2h)}
+                "h2d_bytes_per_step": int(W.h2d), "d2h_bytes_per_step": int(d2h), "breakdown_ms": breakdown}
 
     peaks = {}
     try:

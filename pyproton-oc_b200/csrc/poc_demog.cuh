@@ -22,6 +22,12 @@
 #define DM_M(k) ((unsigned)((k) & 0xffu))
 #define FRIEND_CAND_MAX 64   /* CANON: the 64 lowest slots among an agent's potential friends are considered */
 
+// a criminal entry carries a copy of the static layer mask of the same neighbour (poc_device.cuh): keep it current
+__device__ __forceinline__ void crim_mask_or(const Graph &g, int u, int v, unsigned bits) {
+    const int ci = crim_find_idx(g, u, v);
+    if (ci >= 0 && !CE_IS_DEAD(g.c_ent[ci].y)) atomicOr(&const_cast<int2 *>(g.c_ent)[ci].y, (int)(bits << 24));
+}
+
 // ---------------------------------------------------------------------------------------------- make_baby
 // one block per replica: eligible mothers draw, the births are listed in ascending slot order of the mother, every birth
 // fills its slot and queues its directed entries
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
         const bool ualive = (attr[u] & F_ALIVE) != 0;
         if (idx >= 0) {
             const unsigned old = atomicOr(&ent_old[idx], m << 24);
+            if (old & ENT_CRIM) crim_mask_or(g, u, v, m);
             if (ualive) for (int l = 0; l < 8; l++) if (((m >> l) & 1u) && !((old >> (24 + l)) & 1u)) atomicAdd((unsigned long long *)&ltot[l], 1ull);
         } else {
             if (ualive) for (int l = 0; l < 8; l++) if ((m >> l) & 1u) atomicAdd((unsigned long long *)&ltot[l], 1ull);
@@ -247,8 +254,15 @@ __global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
             while (lo < hi) { int m = (lo + hi) >> 1; if (ENT_COL(ent_old[m]) < v) lo = m + 1; else hi = m; }
             // a criminal entry towards v may exist already (the flag lives in the static entry)
             const unsigned crim = (a < n_old && crim_find(g, a, v) >= 0) ? ENT_CRIM : 0u;
+            if (crim) crim_mask_or(g, a, v, DM_M(kk));
             ent_new[nbase + (lo - ob) + (isnew_ex[j] - isnew_ex[pb])] = (uint32_t)v | crim | (DM_M(kk) << 24);
         }
+    }
+    // newborns have empty criminal rows
+    {
+        int32_t *crp = const_cast<int32_t *>(g.c_rowptr);
+        const int ctot = crp[n_old];
+        for (int a = n_old + 1 + tid; a <= n_new; a += blockDim.x) crp[a] = ctot;
     }
     __syncthreads();
     if (tid == 0) { C.u_par[r] = upar ^ 1; C.n_agents[r] = n_new; dmn[0] = 0; dmn[2] = 0; }
@@ -344,8 +358,16 @@ __global__ void __launch_bounds__(256) k_apply_friends(DevCtx C) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
         const int a = DM_U(pairs[i]), c = DM_V(pairs[i]);
         const int e1 = static_find_idx(g, a, c), e2 = static_find_idx(g, c, a);
-        if (e1 >= 0 && !(atomicOr(&ent[e1], MB_FRIEND << 24) & (MB_FRIEND << 24)) && (attr[a] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
-        if (e2 >= 0) { if (!(atomicOr(&ent[e2], MB_FRIEND << 24) & (MB_FRIEND << 24)) && (attr[c] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull); }
+        if (e1 >= 0) {
+            const unsigned old = atomicOr(&ent[e1], MB_FRIEND << 24);
+            if (old & ENT_CRIM) crim_mask_or(g, a, c, MB_FRIEND);
+            if (!(old & (MB_FRIEND << 24)) && (attr[a] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
+        }
+        if (e2 >= 0) {
+            const unsigned old = atomicOr(&ent[e2], MB_FRIEND << 24);
+            if (old & ENT_CRIM) crim_mask_or(g, c, a, MB_FRIEND);
+            if (!(old & (MB_FRIEND << 24)) && (attr[c] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
+        }
         else {
             // c's row has no slot for a (a one-sided link in the uploaded state: c cleared its own sets when it was
             // arrested before the upload, entities.py:601-602): the entry is created by the insert pass that follows

@@ -1,0 +1,153 @@
+"""SURVEY.md 8(f) rows on the device: make_baby, make_friends, make_people_die (poc_demog.cuh).
+  * bit for bit against the CPU restatement of the same batch semantics (oracle/hotpath.c), phase by phase and over
+    whole runs with the crime path in between;
+  * in distribution against the reference itself: tests/golden/distdemog_* holds 30 continuations of one reference
+    setup state by the UNMODIFIED reference with exactly these phases (and the crime path) active."""
+import numpy as np
+import pytest
+
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+COLS = ["alive", "male", "oc_member", "facilitator", "prisoner", "has_job", "has_school", "target_of_intervention",
+        "job_level", "education_level", "wealth_level", "age", "birth_tick", "num_crimes_committed",
+        "num_crimes_committed_this_tick", "father", "new_recruit", "propensity", "criminal_tendency", "sentence_countdown"]
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pyproton_oc_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle_c
+    return oracle_c
+
+
+def engine_for(P, states, extra_agents=600, extra_static=40000, crim_headroom=60000):
+    n, stat, crim = P.CrimeEngine.capacity_for(states, crim_headroom)
+    return P.CrimeEngine(len(states), n + extra_agents, stat + extra_static, crim)
+
+
+def children_of(st):
+    return st["number_of_children"] if "number_of_children" in st else np.diff(st["rowptr_1"]).astype(np.int32)
+
+
+def assert_equal(E, r, S, what):
+    got, oc = E.download_state(r), S.cols()
+    assert len(got["alive"]) == len(oc["alive"]), what + ": agent slots"
+    for k in COLS:
+        assert np.array_equal(got[k], oc[k]), "%s: column %s" % (what, k)
+    for l in range(9):
+        rp, col, co = S.layer(l)
+        assert np.array_equal(got["rowptr_%d" % l], rp), "%s: layer %d rowptr" % (what, l)
+        assert np.array_equal(got["col_%d" % l], col), "%s: layer %d col" % (what, l)
+        if l == 6:
+            assert np.array_equal(got["co_off"], co), what
+    assert np.array_equal(E.download_children(r), S.children()), what + ": number_of_children"
+
+
+@pytest.mark.parametrize("name", ["tick_n1000_s42_t12", "tick_n1000_s5_late_t252", "tick_n1000_s11_oc200_t15",
+                                  "tick_n3000_s42_t24", "tick_n1000_s7_disruptive_strong_t25"])
+def test_each_phase_matches_the_oracle(P, O, name):
+    """One phase at a time on reference states (late ones carry one-sided links and dead-but-referenced agents): the
+    whole state -- columns, all nine layers, children counts, new slots -- equals the oracle's after every phase."""
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    tick, key = int(fx["tick"]), 424242
+    S = O.OracleState(st)
+    S.reserve(len(st["alive"]) + 600)
+    S.set_children(children_of(st))
+    OP, OD = O.make_params(prm), O.make_demog()
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.upload_state(0, st)
+        E.upload_children(0, children_of(st))
+        for rep in range(6):   # several rounds so that the phases see each other's edits
+            t = tick + rep
+            S.begin_tick(t); E.begin_tick(t)
+            nb = S.make_baby(OP, OD, t, key); E.run_phase(E.PHASE_BABY, t, [key])
+            assert_equal(E, 0, S, "%s make_baby round %d (%d births)" % (name, rep, nb))
+            nf = S.make_friends(OP, OD, t, key); E.run_phase(E.PHASE_FRIENDS, t, [key])
+            assert_equal(E, 0, S, "%s make_friends round %d (%d friendships)" % (name, rep, nf))
+            nd = S.make_people_die(OP, OD, t, key); E.run_phase(E.PHASE_DIE, t, [key])
+            assert_equal(E, 0, S, "%s make_people_die round %d (%d deaths)" % (name, rep, nd))
+        cn, _ = E.counters()
+        assert cn[0, 9] == 0
+        dc = S.demog_counters()
+        assert cn[0, 16] == dc["number_deceased"] and cn[0, 17] == dc["number_born"]
+        # the tot_<layer>_link reporters (kept incrementally on the device) equal the layer sizes over the living
+        row = dict(zip(P.REPORTER_NAMES, E.report()[0]))
+        al = S.cols()["alive"] > 0
+        for l, lname in enumerate(P.LAYER_NAMES):
+            rp, _, _ = S.layer(l)
+            assert row["tot_%s_link" % lname] == int(np.diff(rp)[al].sum()), lname
+        assert row["current_num_persons"] == int(al.sum())
+
+
+@pytest.mark.parametrize("name,ticks", [("tick_n1000_s42_t12", 60), ("tick_n1000_s11_oc200_t3", 36), ("tick_n3000_s42_t1", 30)])
+def test_runs_with_all_phases_match_the_oracle(P, O, name, ticks):
+    """poc_run_ticks with the three phases switched on (crime path, make_baby, make_friends, prisoner countdown,
+    make_people_die per tick, one CUDA graph) equals the oracle's run tick for tick, two replicas with different keys."""
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    tick0, keys = int(fx["tick"]), [77, 78]
+    mult0 = float(fx["crime_multiplier"])
+    with engine_for(P, [st, st]) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_phases(7)
+        for r in range(2):
+            E.upload_state(r, st)
+            E.upload_children(r, children_of(st))
+            E.set_crime_multiplier(mult0, r)
+        rep = E.run_ticks(tick0, ticks, keys)
+        cn, _ = E.counters()
+        assert (cn[:, 9] == 0).all()
+        for r in range(2):
+            S = O.OracleState(st)
+            S.reserve(len(st["alive"]) + 600)
+            S.set_children(children_of(st))
+            mult, tot = S.run_ticks_phases(O.make_params(prm), O.make_demog(), 7, tick0, ticks, keys[r], mult0)
+            assert_equal(E, r, S, "%s replica %d after %d ticks" % (name, r, ticks))
+            assert rep[r, -1, 0] == tot[0] and rep[r, -1, 15] == mult
+            al = S.cols()["alive"] > 0
+            assert rep[r, -1, 14] == int(al.sum())
+            assert rep[r, -1, 30] == int(np.diff(S.layer(5)[0])[al].sum())   # tot_friendship_link
+
+
+def test_phases_in_distribution_against_the_reference(P):
+    """30 replicas from the reference's 1,000-agent setup state against 30 continuations of that state by the
+    unmodified reference with the same phases active (oracle/make_states.py distdemog): two-sample KS per column at
+    three ticks, and the means within a few per cent."""
+    from scipy.stats import ks_2samp
+    fx = U.load_fixture(U.GOLDEN + "/distdemog_n1000_s42.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 60000)
+    with P.CrimeEngine(runs, n + 300, stat + 20000, crim) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_phases(7)
+        for r in range(runs):
+            E.upload_state(r, st)
+            E.upload_children(r, st["number_of_children"])
+        rep = E.run_ticks(1, ticks, [9000 + r for r in range(runs)])
+        cn, _ = E.counters()
+    assert (cn[:, 9] == 0).all()
+    names = list(P.REPORTER_NAMES)
+    for col in ["current_num_persons", "tot_friendship_link", "tot_household_link", "tot_sibling_link", "tot_offspring_link",
+                "tot_parent_link", "number_crimes", "tot_criminal_link", "current_oc_members"]:
+        mine = rep[:, :, names.index(col)]
+        ref = fx["refdemog_" + col]
+        for t in (5, 23, ticks - 1):
+            p = ks_2samp(mine[:, t], ref[:, t]).pvalue
+            assert p > 0.005, (col, t, p, mine[:, t].mean(), ref[:, t].mean())
+        if ref[:, -1].mean() > 20:
+            assert abs(mine[:, -1].mean() - ref[:, -1].mean()) <= 0.12 * ref[:, -1].mean(), (col, mine[:, -1].mean(), ref[:, -1].mean())
+    assert ks_2samp(cn[:, 16], fx["refdemog_number_deceased"][:, -1]).pvalue > 0.005
+    assert ks_2samp(cn[:, 17], fx["refdemog_number_born"][:, -1]).pvalue > 0.005

