@@ -1457,6 +1457,7 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
     __shared__ long long wi[16][NI];
     __shared__ double wd[16][2];
     __shared__ double s_mean[4], s_ss[4];   // tendency, age, education level, crimes committed: mean and sum of squared deviations
+    __shared__ double wq[16][4];
     if (lane_id() == 0) { for (int k = 0; k < NI; k++) wi[warp_id()][k] = vi[k]; for (int k = 0; k < 2; k++) wd[warp_id()][k] = vd[k]; }
     __syncthreads();
     const int nw = blockDim.x >> 5;
@@ -1478,10 +1479,12 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
         }
         for (int o = 16; o > 0; o >>= 1)
             for (int k = 0; k < 4; k++) q[k] += __shfl_xor_sync(FULL_MASK, q[k], o);
-        if (lane_id() == 0) for (int k = 0; k < 4; k++) atomicAdd(&s_ss[k], q[k]);
+        if (lane_id() == 0) for (int k = 0; k < 4; k++) wq[warp_id()][k] = q[k];
     }
     __syncthreads();
     if (tid == 0) {
+        // warp partials added in warp order: the row is the same bits run after run (a floating-point atomicAdd is not)
+        for (int ww = 0; ww < nw; ww++) for (int k = 0; k < 4; k++) s_ss[k] += wq[ww][k];
         const int *cn = RP(C.counters, r, CN_COUNT);
         const int *pv = RP(C.prev_counters, r, CN_COUNT);
         const long long *lt = RP(C.layer_tot, r, 8);

@@ -22,7 +22,9 @@ def main():
     args = ap.parse_args()
     import bench
     import pyproton_oc_b200 as pkg
-    name, st, prm, tick0, mult = bench.load_workload()
+    cfg = bench.homogeneous_config(1)
+    name = cfg["name"]
+    st, prm, tick0, mult = cfg["entries"][0]
     if args.synthetic:
         import util as U
         from pyproton_oc_b200 import synth
