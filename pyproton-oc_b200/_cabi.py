@@ -138,7 +138,8 @@ _lib = None
 
 
 def sources():
-    return [os.path.join(SRC_DIR, f) for f in ("poc_api.cu", "poc_kernels.cuh", "poc_embed.cuh", "poc_device.cuh")] + [HEADER]
+    import glob
+    return sorted(glob.glob(os.path.join(SRC_DIR, "*.cu")) + glob.glob(os.path.join(SRC_DIR, "*.cuh"))) + [HEADER]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

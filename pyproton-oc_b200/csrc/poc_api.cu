@@ -36,7 +36,7 @@ struct poc_ctx {
     int emb_gx = 4;        // blocks per replica of the embeddedness grid
     size_t smem_search = 0, smem_emb = 0, smem_emb2 = 0;
     int emb_blocks = 8;    // resident blocks per SM the second formulation is compiled / sized for
-    int emb_v = 2;         // embeddedness formulation: 2 = poc_embed2.cuh (level-ordered stage-and-relax), 1 = poc_embed.cuh
+    int emb_v = 3;         // embeddedness formulation: 3 = poc_embed3.cuh (each meta edge once), 2 = poc_embed2.cuh, 1 = poc_embed.cuh
     // staging
     StageCols stage{};
     uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
@@ -151,7 +151,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
 
 int poc_ctx_create(int device, int n_replicas, int max_agents, int64_t max_static_entries,
                    int64_t max_criminal_entries, poc_ctx **out) {
-    if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 23) || max_static_entries < 0 || max_criminal_entries < 0)
+    if (!out || n_replicas < 1 || max_agents < 1 || max_agents >= (1 << 22) || max_static_entries < 0 || max_criminal_entries < 0)
         return fail(nullptr, POC_ERR_ARG, "poc_ctx_create: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -181,7 +181,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     int pc = 16384;
     while (pc < d.Ccap * 8) pc <<= 1;
     d.Pcap = pc;
-    d.ucap = std::max<long long>(max_static_entries, 1);
+    d.ucap = (std::max<long long>(max_static_entries, 1) + 3) & ~3LL;   // rows are read 16 bytes at a time: replica bases stay aligned
     d.ccap = std::max<long long>(max_criminal_entries, 1);
     d.Tcap = 1;
     // one block per accomplice search / embeddedness evaluation: at 10k agents a replica issues about 25 searches
@@ -212,15 +212,18 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
     ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
     if (ctx->smem_emb + 2 * 1024 > 220 * 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
-    if (const char *e = getenv("POC_EMB_V")) ctx->emb_v = (atoi(e) == 1) ? 1 : 2;
+    if (const char *e = getenv("POC_EMB_V")) { int v = atoi(e); if (v >= 1 && v <= 3) ctx->emb_v = v; }
+    // third formulation, large batches: 128 threads per evaluation (641 us per launch at 1,024 replicas against 730 with 256:
+    // fewer warps of a block wait at its barriers while one of them walks a short level; profiles/r02h_ab.log)
+    if (ctx->emb_v == 3 && R >= 256 && !getenv("POC_EMB_G")) ctx->emb_g = 128;
     if (ctx->emb_g == 32) ctx->emb_v = 1;   // the warp-per-evaluation variant exists in the first formulation only
     {
         // second formulation: the block's dynamic shared memory is whatever its share of the SM allows (227 KB per SM,
         // 1 KB reserved per block) at the residency its block size permits; the kernel splits it into distances + staged entries
-        int g = ctx->emb_g, blocks = (g == 1024) ? 2 : (g == 512) ? 4 : (g == 256) ? 8 : 12;
+        int g = ctx->emb_g, blocks = (g == 1024) ? 2 : (g == 512) ? 4 : (g == 256) ? 8 : (ctx->emb_v == 3 ? 14 : 12);
         if (g == 64) { g = ctx->emb_g = 128; ctx->smem_emb = emb_smem_bytes(128, N); }
         if (const char *e = getenv("POC_EMB_BLOCKS")) blocks = std::max(1, std::min(16, atoi(e)));
-        size_t fixed = emb2_fixed_bytes(g, N);
+        size_t fixed = (ctx->emb_v == 3) ? emb3_fixed_bytes(g, N) : emb2_fixed_bytes(g, N);
         size_t share = ((size_t)227 * 1024 / blocks - 1024) & ~(size_t)15;
         while (blocks > 1 && share < fixed + 8 * 1024) { blocks--; share = ((size_t)227 * 1024 / blocks - 1024) & ~(size_t)15; }
         if (share < fixed + 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
@@ -236,6 +239,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     DA(d.c_rowptr_tmp, (size_t)R * (N + 1)); DA(d.c_ent_tmp, (size_t)R * d.ccap); DA(d.c_addlen, RN);
     DA(d.c_par, R);
     DA(d.u_rowptr_tmp, (size_t)R * (N + 1)); DA(d.u_ent_tmp, (size_t)R * d.ucap); DA(d.u_par, R);
+    DA(d.u_mid, RN); DA(d.u_mid_tmp, RN);
     DA(d.n_children, RN); DA(d.ncrim_dead, RN); DA(d.dm_list, RN); DA(d.dm_n, (size_t)R * 4);
     d.DPcap = std::max(4 * N, 16384);
     DA(d.dm_pairs, (size_t)R * d.DPcap); DA(d.dm_defer, (size_t)R * 1024);
@@ -324,6 +328,9 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
 #define EMB2_ATTR(G, MB) cudaFuncSetAttribute(k_emb2<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb2)
     EMB2_ATTR(128, 12); EMB2_ATTR(256, 8); EMB2_ATTR(256, 6); EMB2_ATTR(256, 5); EMB2_ATTR(512, 4); EMB2_ATTR(512, 3); EMB2_ATTR(1024, 2); EMB2_ATTR(1024, 1);
 #undef EMB2_ATTR
+#define EMB3_ATTR(G, MB) cudaFuncSetAttribute(k_emb3<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb2)
+    EMB3_ATTR(128, 16); EMB3_ATTR(128, 14); EMB3_ATTR(128, 12); EMB3_ATTR(256, 8); EMB3_ATTR(256, 6); EMB3_ATTR(512, 4); EMB3_ATTR(1024, 2);
+#undef EMB3_ATTR
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_emb_acc_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
@@ -520,6 +527,7 @@ static int build_union(poc_ctx *ctx, int replica, int n, const StageLayers &L) {
         k_exscan_i32<<<1, 1024, 0, st>>>(lens, urp, n);
         k_union_rows<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n, L, lens, 1, ctx->d_err);
         k_link_criminal<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
+        k_mark_asym<<<(n + 3) / 4, 128, 0, st>>>(ctx->d, replica, n);
         CU(cudaMemsetAsync(ctx->d.layer_tot + (size_t)replica * 8, 0, sizeof(long long) * 8, st));
         k_layer_totals<<<(n + 127) / 128, 128, 0, st>>>(ctx->d, replica, n);
     } else CU(cudaMemsetAsync(urp, 0, sizeof(int32_t), st));
@@ -773,6 +781,22 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
 
 static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity) {
     dim3 grid(ctx->emb_gx, D.Rg);
+    if (ctx->emb_v == 3) {
+        int sm = (int)ctx->smem_emb2, mb = ctx->emb_blocks;
+        if (ctx->emb_g == 128) {
+            // register budget by residency: 32 at 16 blocks per SM, 36 at 14, 40 at 12 (POC_EMB_REGS picks one for A/B runs)
+            int rb = mb >= 16 ? 16 : 12;
+            if (const char *e = getenv("POC_EMB_REGS")) rb = atoi(e);
+            if (rb >= 16) k_emb3<128, 16><<<grid, 128, sm, s>>>(D, parity, sm);
+            else if (rb >= 14) k_emb3<128, 14><<<grid, 128, sm, s>>>(D, parity, sm);
+            else k_emb3<128, 12><<<grid, 128, sm, s>>>(D, parity, sm);
+        }
+        else if (ctx->emb_g == 512) k_emb3<512, 4><<<grid, 512, sm, s>>>(D, parity, sm);
+        else if (ctx->emb_g == 1024) k_emb3<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm);
+        else if (mb >= 8) k_emb3<256, 8><<<grid, 256, sm, s>>>(D, parity, sm);
+        else k_emb3<256, 6><<<grid, 256, sm, s>>>(D, parity, sm);
+        return;
+    }
     if (ctx->emb_v == 2) {
         int sm = (int)ctx->smem_emb2, mb = ctx->emb_blocks;
         if (ctx->emb_g == 128) k_emb2<128, 12><<<grid, 128, sm, s>>>(D, parity, sm);

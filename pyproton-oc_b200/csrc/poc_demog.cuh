@@ -266,6 +266,16 @@ __global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
     }
     __syncthreads();
     if (tid == 0) { C.u_par[r] = upar ^ 1; C.n_agents[r] = n_new; dmn[0] = 0; dmn[2] = 0; }
+    __syncthreads();
+    // the pairs that changed may no longer mirror their reverse entries (poc_device.cuh: ENT_ASYM); rows as laid out now
+    {
+        Graph gn = g;
+        gn.u_rowptr = rp_new; gn.u_ent = ent_new;
+        gn.u_mid = (upar ? C.u_mid : C.u_mid_tmp) + (size_t)r * C.Ncap;
+        for (int a = tid; a < n_new; a += blockDim.x) gn.u_mid[a] = row_mid(gn, a);   // every row moved
+        __syncthreads();
+        for (int i = tid; i < nu; i += blockDim.x) ent_asym_update(gn, DM_U(pairs[i]), DM_V(pairs[i]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- make_friends
@@ -358,17 +368,25 @@ __global__ void __launch_bounds__(256) k_apply_friends(DevCtx C) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
         const int a = DM_U(pairs[i]), c = DM_V(pairs[i]);
         const int e1 = static_find_idx(g, a, c), e2 = static_find_idx(g, c, a);
+        unsigned m1 = 0u, m2 = 0u;   // the two entries as this phase leaves them (only friendship bits are set here)
         if (e1 >= 0) {
             const unsigned old = atomicOr(&ent[e1], MB_FRIEND << 24);
+            m1 = old | (MB_FRIEND << 24);
             if (old & ENT_CRIM) crim_mask_or(g, a, c, MB_FRIEND);
             if (!(old & (MB_FRIEND << 24)) && (attr[a] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
         }
         if (e2 >= 0) {
             const unsigned old = atomicOr(&ent[e2], MB_FRIEND << 24);
+            m2 = old | (MB_FRIEND << 24);
             if (old & ENT_CRIM) crim_mask_or(g, c, a, MB_FRIEND);
             if (!(old & (MB_FRIEND << 24)) && (attr[c] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[5], 1ull);
         }
-        else {
+        // ENT_ASYM (poc_device.cuh) when the two no longer mirror each other
+        if (e1 < 0 || e2 < 0 || ((m1 ^ m2) & ENT_CRIM) || __popc(ENT_MASK(m1)) != __popc(ENT_MASK(m2))) {
+            if (e1 >= 0) ent_flag_asym(g, a, e1);
+            if (e2 >= 0) ent_flag_asym(g, c, e2);
+        }
+        if (e2 < 0) {
             // c's row has no slot for a (a one-sided link in the uploaded state: c cleared its own sets when it was
             // arrested before the upload, entities.py:601-602): the entry is created by the insert pass that follows
             const int q = atomicAdd(&dmn[2], 1);
@@ -462,6 +480,7 @@ __global__ void __launch_bounds__(256) k_die_apply(DevCtx C) {
                 if (!CE_IS_DEAD(ce.y)) v = ce.x;
             }
             if (v < 0 || v == a || (attr[v] & F_DYING)) continue;
+            if (j < len0) ent_flag_asym(g, a, b0 + j);   // the reverse entry is emptied below: this one stands alone
             const bool valive = (attr[v] & F_ALIVE) != 0;
             const int idx = static_find_idx(g, v, a);
             if (idx >= 0) {

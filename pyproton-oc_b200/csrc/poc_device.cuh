@@ -5,7 +5,8 @@
 //   tendency  f64, propensity f64, sentence f64, arrest_w f64
 //   birth, ncrimes, ncrimes_tick, father, new_recruit   i32
 //   u_rowptr  i32 [Ncap+1], u_ent u32 [ucap]: the eight non-criminal layers merged into one directed CSR,
-//             entry = neighbour slot (23 bit) | also-criminal flag (bit 23) | layer mask (8 bit) << 24 ; rows ascending
+//             entry = neighbour slot (22 bit) | one-sided flag (bit 22) | also-criminal flag (bit 23) | layer mask (8 bit) << 24 ;
+//             rows ascending
 //   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses | static mask << 24}, rows
 //             ascending.  The flag and the mask copy make the multiplicity of an edge (model.py:1528-1535) a single
 //             load from either row: no row intersection on the traversal paths.
@@ -38,7 +39,15 @@ __host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < PO
 #define MB_FRIEND 0x20u
 #define MB_PROF 0x40u
 #define MB_SCHOOL 0x80u
-#define ENT_COL(e) ((int)((e) & 0x007fffffu))
+#define ENT_COL(e) ((int)((e) & 0x003fffffu))
+// ENT_ASYM on the entry u -> v: the reverse entry v -> u does not carry the same multiplicity (it is missing, has another
+// number of layers, or is weighed through a criminal entry while this one is not).  Links are made in pairs, so the flag
+// is rare (one-sided clears of get_caught, entities.py:601-602, and Person.die, :652-661); a traversal that wants every
+// undirected meta edge ONCE (poc_embed3.cuh) takes an entry when v > u or the flag is set.  The flag may be set where it
+// is not needed (never the other way round): it is a performance hint, not state; downloads do not see it.
+// u_mid[u] = index of the first entry of row u such a traversal must read: the first entry with a neighbour slot > u
+// (rows ascend), or the row's begin when an entry before that carries the flag.
+#define ENT_ASYM 0x00400000u
 #define ENT_CRIM 0x00800000u /* the same neighbour also has an entry in the criminal row */
 #define ENT_MASK(e) ((e) >> 24)
 // criminal entry .y = num_co_offenses (23 bit) | removed flag (bit 23) | copy of the static layer mask of the same neighbour << 24
@@ -78,6 +87,7 @@ struct DevCtx {
     // graph
     int32_t *u_rowptr; uint32_t *u_ent;
     int32_t *u_rowptr_tmp; uint32_t *u_ent_tmp;   // second multiplex buffer: make_baby lays the rows out again (k_multiplex_insert)
+    int32_t *u_mid, *u_mid_tmp;     // [R][Ncap] per row: first entry a once-per-pair traversal has to look at (see ENT_ASYM)
     int *u_par;                     // [R] which multiplex CSR is current
     int32_t *c_rowptr; int2 *c_ent;
     int32_t *c_rowptr_tmp; int2 *c_ent_tmp; int32_t *c_addlen;
@@ -235,6 +245,7 @@ __device__ __forceinline__ double warp_chain32(double v, double &acc) {
 // ---- multiplex traversal ---------------------------------------------------------------------------
 struct Graph {
     const int32_t *u_rowptr; const uint32_t *u_ent;
+    int32_t *u_mid;
     const int32_t *c_rowptr; const int2 *c_ent;
 };
 __device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
@@ -242,6 +253,7 @@ __device__ __forceinline__ Graph graph_of(const DevCtx &C, int r) {
     int upar = C.u_par[r];
     g.u_rowptr = (upar ? C.u_rowptr_tmp : C.u_rowptr) + (size_t)r * (C.Ncap + 1);
     g.u_ent = (upar ? C.u_ent_tmp : C.u_ent) + (size_t)r * C.ucap;
+    g.u_mid = (upar ? C.u_mid_tmp : C.u_mid) + (size_t)r * C.Ncap;
     int par = C.c_par[r];
     g.c_rowptr = (par ? C.c_rowptr_tmp : C.c_rowptr) + (size_t)r * (C.Ncap + 1);
     g.c_ent = (par ? C.c_ent_tmp : C.c_ent) + (size_t)r * C.ccap;
@@ -355,6 +367,35 @@ __device__ __forceinline__ int static_find_idx(const Graph &g, int u, int v) {  
     int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;
     while (lo < hi) { int m = (lo + hi) >> 1; if (ENT_COL(g.u_ent[m]) < v) lo = m + 1; else hi = m; }
     return (lo < end && ENT_COL(g.u_ent[lo]) == v) ? lo : -1;
+}
+// ENT_ASYM of the entry u -> v (value `e`), from the rows as they are now
+__device__ __forceinline__ bool ent_is_asym(const Graph &g, int u, uint32_t e) {
+    if (e & ENT_CRIM) return false;   // weighed at its criminal entry, which every traversal takes from both sides
+    const int ri = static_find_idx(g, ENT_COL(e), u);
+    if (ri < 0) return true;
+    const uint32_t re = g.u_ent[ri];
+    return (re & ENT_CRIM) || __popc(ENT_MASK(re)) != __popc(ENT_MASK(e));
+}
+// flag entry idx of row u; a flagged entry in the lower part of the row makes the traversal read the whole row
+__device__ __forceinline__ void ent_flag_asym(const Graph &g, int u, int idx) {
+    uint32_t *ent = const_cast<uint32_t *>(g.u_ent);
+    const uint32_t old = atomicOr(&ent[idx], ENT_ASYM);
+    if (ENT_COL(old) < u) g.u_mid[u] = g.u_rowptr[u];
+}
+// after the masks of the pair (u, v) changed: set the flag on both entries if they no longer mirror each other.  Only
+// ever sets (a stale flag costs a little time, a missing one would drop a meta edge).
+__device__ __forceinline__ void ent_asym_update(const Graph &g, int u, int v) {
+    const int i1 = static_find_idx(g, u, v), i2 = static_find_idx(g, v, u);
+    if (i1 >= 0 && ent_is_asym(g, u, g.u_ent[i1])) ent_flag_asym(g, u, i1);
+    if (i2 >= 0 && ent_is_asym(g, v, g.u_ent[i2])) ent_flag_asym(g, v, i2);
+}
+// u_mid of row a from the row as it is (one thread)
+__device__ __forceinline__ int row_mid(const Graph &g, int a) {
+    const int b = g.u_rowptr[a], e = g.u_rowptr[a + 1];
+    int i = b;
+    bool low_flag = false;
+    for (; i < e; i++) { const uint32_t en = g.u_ent[i]; if (ENT_COL(en) > a) break; low_flag |= (en & ENT_ASYM) != 0; }
+    return low_flag ? b : i;
 }
 __device__ __forceinline__ uint32_t static_find_mask(const Graph &g, int u, int v) {  // layer mask of v in u's row or 0
     int lo = g.u_rowptr[u], hi = g.u_rowptr[u + 1], end = hi;

@@ -7,6 +7,7 @@
 #define RP(ptr, r, stride) ((ptr) + (size_t)(r) * (size_t)(stride))
 #include "poc_embed.cuh"
 #include "poc_embed2.cuh"
+#include "poc_embed3.cuh"
 #include "poc_embed_acc.cuh"
 #include "poc_demog.cuh"
 
@@ -134,6 +135,30 @@ __global__ void k_link_criminal(DevCtx C, int r, int n) {
         if (idx >= 0) { smask = ENT_MASK(uent[idx]); uent[idx] |= ENT_CRIM; }
         cent[e].y = CE_CNT(ce.y) | (int)(smask << 24);
     }
+}
+
+// ENT_ASYM of every multiplex entry of an uploaded state (poc_device.cuh); warp per agent, lane per entry
+__global__ void k_mark_asym(DevCtx C, int r, int n) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (a >= n) return;
+    Graph g = graph_of(C, r);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
+    const int b = g.u_rowptr[a], end = g.u_rowptr[a + 1];
+    int lower = 0;
+    bool low_flag = false;
+    for (int e0 = b; e0 < end; e0 += 32) {
+        const int e = e0 + lane_id();
+        bool below = false, flag = false;
+        if (e < end) {
+            const uint32_t en = uent[e] & ~ENT_ASYM;
+            flag = ent_is_asym(g, a, en);
+            uent[e] = en | (flag ? ENT_ASYM : 0u);
+            below = ENT_COL(en) < a;
+        }
+        lower += __popc(__ballot_sync(FULL_MASK, below));
+        low_flag |= __any_sync(FULL_MASK, below && flag);
+    }
+    if (lane_id() == 0) g.u_mid[a] = low_flag ? b : b + lower;
 }
 
 // tot_<layer>_link of calculate_fast_reporters (model.py:1715-1732) for the eight static layers: computed once here
@@ -1379,6 +1404,11 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
             uint32_t en = uent[e];
             nprof += (ENT_MASK(en) & MB_PROF) != 0; nschool += (ENT_MASK(en) & MB_SCHOOL) != 0;
             uent[e] = en & ~((MB_PROF | MB_SCHOOL) << 24);
+            if (ENT_MASK(en) & (MB_PROF | MB_SCHOOL)) {   // the pair no longer mirrors itself (poc_device.cuh: ENT_ASYM)
+                ent_flag_asym(g, a, e);
+                const int ri = static_find_idx(g, ENT_COL(en), a);
+                if (ri >= 0) ent_flag_asym(g, ENT_COL(en), ri);
+            }
         }
         if (x & F_ALIVE) { RP(C.layer_tot, r, 8)[6] -= nprof; RP(C.layer_tot, r, 8)[7] -= nschool; }
         for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) cent_rw[e].y &= ~(int)((MB_PROF | MB_SCHOOL) << 24);
