@@ -34,7 +34,7 @@ struct poc_ctx {
     int gx = 4;            // blocks per replica of the search grid (and of the block-per-evaluation embeddedness grid)
     int emb_g = 256;       // threads per embeddedness evaluation: 256 (block) for small batches, 32 (warp) for large ones
     int emb_gx = 4;        // blocks per replica of the embeddedness grid
-    size_t smem_search = 0, smem_emb = 0, smem_emb2 = 0;
+    size_t smem_search = 0, smem_emb = 0, smem_emb2 = 0, smem_emb_big = 0;
     int emb_blocks = 8;    // resident blocks per SM the second formulation is compiled / sized for
     int emb_v = 3;         // embeddedness formulation: 3 = poc_embed3.cuh (each meta edge once), 2 = poc_embed2.cuh, 1 = poc_embed.cuh
     // staging
@@ -229,6 +229,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
         if (share < fixed + 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
         ctx->smem_emb2 = share;
         ctx->emb_blocks = blocks;
+        ctx->smem_emb_big = ((size_t)227 * 1024 / 2 - 1024) & ~(size_t)15;   // the large-block launch: two blocks of 1,024 threads per SM
     }
     size_t RN = (size_t)R * N;
     DA(d.n_agents, R);
@@ -254,6 +255,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     DA(d.cr_target, RC); DA(d.cr_nacc, RC); DA(d.cr_d, RC); DA(d.cr_state, RC); DA(d.cr_fails, RC);
     DA(d.cr_acc, RC * POC_MAX_GROUP); DA(d.search_list, RC); DA(d.n_search, R);
     DA(d.emb_list, 2 * RN); DA(d.n_emb, 2 * R); DA(d.emb_stamp, RN); DA(d.emb_val, RN);
+    d.big_cap = std::min(N, 4096);
+    DA(d.emb_big, (size_t)R * d.big_cap); DA(d.n_emb_big, R);
     DA(d.group_off, (size_t)R * (d.Ccap + 1)); DA(d.group_mem, RM);
     DA(d.pairs, (size_t)R * d.Pcap); DA(d.pair_cnt, (size_t)R * d.Pcap); DA(d.n_pairs, R);
     DA(d.pair_new_ex, (size_t)R * (d.Pcap + 1)); DA(d.ins_row, (size_t)R * d.Pcap);
@@ -329,7 +332,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     EMB2_ATTR(128, 12); EMB2_ATTR(256, 8); EMB2_ATTR(256, 6); EMB2_ATTR(256, 5); EMB2_ATTR(512, 4); EMB2_ATTR(512, 3); EMB2_ATTR(1024, 2); EMB2_ATTR(1024, 1);
 #undef EMB2_ATTR
 #define EMB3_ATTR(G, MB) cudaFuncSetAttribute(k_emb3<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_emb2)
-    EMB3_ATTR(128, 16); EMB3_ATTR(128, 14); EMB3_ATTR(128, 12); EMB3_ATTR(256, 8); EMB3_ATTR(256, 6); EMB3_ATTR(512, 4); EMB3_ATTR(1024, 2);
+    EMB3_ATTR(128, 16); EMB3_ATTR(128, 14); EMB3_ATTR(128, 12); EMB3_ATTR(256, 8); EMB3_ATTR(256, 6); EMB3_ATTR(512, 4);
+    cudaFuncSetAttribute(k_emb3<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->smem_emb2, ctx->smem_emb_big));
 #undef EMB3_ATTR
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
@@ -783,18 +787,23 @@ static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity
     dim3 grid(ctx->emb_gx, D.Rg);
     if (ctx->emb_v == 3) {
         int sm = (int)ctx->smem_emb2, mb = ctx->emb_blocks;
-        if (ctx->emb_g == 128) {
-            // register budget by residency: 32 at 16 blocks per SM, 36 at 14, 40 at 12 (POC_EMB_REGS picks one for A/B runs)
-            int rb = mb >= 16 ? 16 : 12;
-            if (const char *e = getenv("POC_EMB_REGS")) rb = atoi(e);
-            if (rb >= 16) k_emb3<128, 16><<<grid, 128, sm, s>>>(D, parity, sm);
-            else if (rb >= 14) k_emb3<128, 14><<<grid, 128, sm, s>>>(D, parity, sm);
-            else k_emb3<128, 12><<<grid, 128, sm, s>>>(D, parity, sm);
+        if (ctx->emb_g == 128 || ctx->emb_g == 256) {
+            // small blocks for the evaluations that fit them, then a few large blocks for the rest (mode 0 / mode 1)
+            if (ctx->emb_g == 128) {
+                // register budget by residency: 32 at 16 blocks per SM, 36 at 14, 40 at 12 (POC_EMB_REGS picks one for A/B runs)
+                int rb = mb >= 16 ? 16 : 12;
+                if (const char *e = getenv("POC_EMB_REGS")) rb = atoi(e);
+                if (rb >= 16) k_emb3<128, 16><<<grid, 128, sm, s>>>(D, parity, sm, 0);
+                else if (rb >= 14) k_emb3<128, 14><<<grid, 128, sm, s>>>(D, parity, sm, 0);
+                else k_emb3<128, 12><<<grid, 128, sm, s>>>(D, parity, sm, 0);
+            }
+            else if (mb >= 8) k_emb3<256, 8><<<grid, 256, sm, s>>>(D, parity, sm, 0);
+            else k_emb3<256, 6><<<grid, 256, sm, s>>>(D, parity, sm, 0);
+            ctx->launches++;
+            k_emb3<1024, 2><<<dim3(std::min(4, ctx->emb_gx), D.Rg), 1024, (int)ctx->smem_emb_big, s>>>(D, parity, (int)ctx->smem_emb_big, 1);
         }
-        else if (ctx->emb_g == 512) k_emb3<512, 4><<<grid, 512, sm, s>>>(D, parity, sm);
-        else if (ctx->emb_g == 1024) k_emb3<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm);
-        else if (mb >= 8) k_emb3<256, 8><<<grid, 256, sm, s>>>(D, parity, sm);
-        else k_emb3<256, 6><<<grid, 256, sm, s>>>(D, parity, sm);
+        else if (ctx->emb_g == 512) k_emb3<512, 4><<<grid, 512, sm, s>>>(D, parity, sm, 2);
+        else k_emb3<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm, 2);
         return;
     }
     if (ctx->emb_v == 2) {
@@ -1252,6 +1261,7 @@ static int run_emb(poc_ctx *ctx, int replica, int n, const int32_t *agents) {
     std::vector<int32_t> zero(2 * d.R, 0);
     zero[replica] = n;
     CU(cudaMemcpyAsync(d.n_emb, zero.data(), sizeof(int32_t) * zero.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d.n_emb_big, 0, sizeof(int32_t) * d.R, st));
     if (n) CU(cudaMemcpyAsync(d.emb_list + (size_t)replica * d.Ncap, agents, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     { Timed t(ctx, TM_EMB); launch_emb(ctx, ctx->d, ctx->stream, 0); }
     CU(cudaGetLastError());

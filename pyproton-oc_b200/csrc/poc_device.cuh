@@ -119,6 +119,8 @@ struct DevCtx {
     // embeddedness requests
     int32_t *emb_list;              // [2][R][Ncap]
     int32_t *n_emb;                 // [2][R]
+    int32_t *emb_big, *n_emb_big;   // [R][big_cap], [R] evaluations the small blocks hand to the large-block launch (poc_embed3.cuh)
+    int big_cap;
     int32_t *emb_stamp;             // [R][Ncap]
     double *emb_val;                // [R][Ncap]
     // groups of the tick, canonical

@@ -12,9 +12,7 @@
 //     over half as many staged entries.  The relaxations that remain are the same set of float64 sums: distances, and
 //     so the result, are bit-identical to poc_embed2.cuh, poc_embed.cuh and oracle/hotpath.c.
 //   * multiplex rows and criminal rows are walked by separate, uniform loops (a warp whose 32 entries straddled both
-//     kinds used to execute both bodies); the staged entry is rank(u) | rank(v) << 12 | weight index << 24 with a
-//     compile-time layout: the weight index addresses a 128-entry table of 1/w in shared memory whose upper half is
-//     filled per evaluation with the few large multiplicities (co-offence counts of long-lived pairs) a ball holds.
+//     kinds used to execute both bodies).
 //   * 13 block barriers per evaluation instead of 19: per-level append counters (nobody waits for thread 0 to publish a
 //     level), the OC test folded into a voting barrier, the source's distance set by the warp that stages its row;
 //     small BFS levels are spread over all warps (one row each) because their length is latency, not work.
@@ -30,7 +28,6 @@ struct Emb3Shared {
     int over, nreq, nevals;
     int cnt[MAX_RADIUS + 2];                            // members appended at each BFS level
     int ws[33];
-    int wkey[64];                                       // multiplicities behind weight indices 64..127 (0 = free)
 };
 
 template <int G> struct Emb3Layout {
@@ -65,12 +62,15 @@ static inline size_t emb3_fixed_bytes(int G, int Ncap) {
     }
 
 template <int G, int MB>
-__global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_bytes) {
+__global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_bytes, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Emb3Layout<G> L;
     constexpr int NW = L::NW;
-    constexpr unsigned RB = 12, RMASK = (1u << RB) - 1u;
-    if ((int)blockIdx.x >= C.n_emb[parity * C.R + C.r0 + blockIdx.y]) return;  // one block per request; the rest leave at once
+    // mode 0: the tick's request list; an evaluation whose ball does not fit this block's shared memory is handed to the
+    //         second launch (mode 1: few large blocks over C.emb_big) instead of walking the rows from global memory
+    // mode 2: the request list, everything evaluated here (small batches run large blocks in the first place)
+    const int nreqs = (mode == 1) ? C.n_emb_big[C.r0 + blockIdx.y] : C.n_emb[parity * C.R + C.r0 + blockIdx.y];
+    if ((int)blockIdx.x >= nreqs) return;  // one block per request; the rest leave at once
     const int r = C.r0 + blockIdx.y, n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
     const int gt = threadIdx.x, w = gt >> 5;
     int lane = threadIdx.x & 31;
@@ -94,19 +94,17 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
     Graph g = graph_of(C, r);
     asm volatile("" : "+l"(g.u_ent)); asm volatile("" : "+l"(g.c_ent));
     const uint32_t *attr = RP(C.attr, r, C.Ncap);
-    const int32_t *reqs = C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
-    const int nreqs = C.n_emb[parity * C.R + r];
+    const int32_t *reqs = (mode == 1) ? C.emb_big + (size_t)r * C.big_cap : C.emb_list + ((size_t)parity * C.R + r) * C.Ncap;
     const int R = P.oc_embeddedness_radius;
     if (gt < 8) S->ph[gt] = 0;
     if (gt == 8) { S->st_bytes = 0ull; S->st_edges = 0ull; S->st_nodes = 0ull; S->nreq = 0; S->nevals = 0; }
-    for (int i = gt; i < 64; i += G) invw[i] = C.invw[i];
+    for (int i = gt; i < 128; i += G) invw[i] = C.invw[i];
 #define PHASE(k) { long long t1 = clock64(); S->ph[k] += t1 - S->t0; S->t0 = t1; }
     for (int item = blockIdx.x; item < nreqs; item += gridDim.x) {
         const int self = reqs[item];
         // ---- radius-R ball: frontier BFS over the multiplex + criminal rows, visited bits in bp[].x
         for (int i = gt; i < nwords; i += G) bp[i] = make_uint2((i == (self >> 5)) ? (1u << (self & 31)) : 0u, 0u);
         if (gt < MAX_RADIUS + 2) S->cnt[gt] = 0;
-        if (gt >= 64 && gt < 128) S->wkey[gt - 64] = 0;
         if (gt == 0) {
             list[0] = self; S->over = 0; S->nreq++; S->num = 0ull; S->den = 0ull;
             S->t0 = clock64(); S->ev_bytes = 0u; S->ev_edges = 0u;
@@ -167,10 +165,12 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                                 if (p0 + 2 < rt.y || p0 + 2 >= rt.z) q.z = 0u;
                                 if (p0 + 3 < rt.y || p0 + 3 >= rt.z) q.w = 0u;
                             }
-                            { const int v = ENT_MASK(q.x) ? ENT_COL(q.x) : -1; EMB3_VISIT(v) }
-                            { const int v = ENT_MASK(q.y) ? ENT_COL(q.y) : -1; EMB3_VISIT(v) }
-                            { const int v = ENT_MASK(q.z) ? ENT_COL(q.z) : -1; EMB3_VISIT(v) }
-                            { const int v = ENT_MASK(q.w) ? ENT_COL(q.w) : -1; EMB3_VISIT(v) }
+#pragma unroll 1
+                            for (int c = 0; c < 4; c++) {
+                                const int v = ENT_MASK(q.x) ? ENT_COL(q.x) : -1;
+                                EMB3_VISIT(v)
+                                q.x = q.y; q.y = q.z; q.z = q.w;
+                            }
                         }
                         __syncwarp();   // the criminal parts overwrite the row table
                     }
@@ -220,6 +220,20 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
         const int dist_bytes = (total * 8 + 15) & ~15;
         unsigned long long *dist = (unsigned long long *)(smem_raw + off_dyn);
         bool staged = total <= RCAP && dist_bytes + NW * 256 <= dyn_bytes;
+        // (block-uniform) hand the evaluation to the large-block launch; `continue`s when the list took it
+#define EMB3_DEFER(UNDO_EVAL)                                                                                          \
+        {                                                                                                              \
+            if (gt == 0) {                                                                                             \
+                const int q_ = atomicAdd(&C.n_emb_big[r], 1);                                                          \
+                S->ws[32] = q_;                                                                                        \
+                if (q_ < C.big_cap) { (C.emb_big + (size_t)r * C.big_cap)[q_] = self; S->nreq--; S->st_nodes -= total; S->nevals -= (UNDO_EVAL); } \
+            }                                                                                                          \
+            __syncthreads();                                                                                           \
+            const bool deferred_ = S->ws[32] < C.big_cap;                                                              \
+            __syncthreads();                                                                                           \
+            if (deferred_) continue;                                                                                   \
+        }
+        if (!staged && mode == 0) EMB3_DEFER(0)
         {
             const int chunk = (((nwords + NW - 1) / NW) + 31) & ~31;
             const int wb = w * chunk, we = min(nwords, wb + chunk);
@@ -243,6 +257,9 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
         if (gt == 0) { S->nevals++; PHASE(PH_PREFIX) }
 #define RANK(v) ((int)(bp[(v) >> 5].y + __popc(bp[(v) >> 5].x & ((1u << ((v) & 31)) - 1u))))
         int rounds = 0;
+        // a staged entry is rank(u) | rank(v) << 12 | multiplicity << 24.  Multiplicities from 254 on (co-offence counts of a
+        // long-lived OC pair pass 255 late in a run) take two slots: the entry with 255 in the field, then 254 << 24 | count
+        constexpr unsigned RB = 12, RMASK = (1u << RB) - 1u;
         if (staged) {
             // ---- split of the dynamic region: distances of the ball first, one region of staged entries per warp behind them
             int ecap_w = ((dyn_bytes - dist_bytes) >> 2) / NW;          // staged entries per warp in shared memory
@@ -266,12 +283,38 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                 }                                                                                                      \
                 wcnt += __popc(m_);                                                                                    \
             }
+            // the same for a criminal entry, whose multiplicity may need the second slot
+#define EMB3_TAKE_C(OK, RU, RV, WGT)                                                                                   \
+            {                                                                                                          \
+                const bool big_ = (OK) && (WGT) >= 254;                                                                \
+                const unsigned m_ = __ballot_sync(FULL_MASK, OK), mb_ = __ballot_sync(FULL_MASK, big_);                \
+                if (OK) {                                                                                              \
+                    const int pos_ = wcnt + __popc(m_ & ltmask) + __popc(mb_ & ltmask);                                \
+                    const unsigned pk_ = (unsigned)(RU) | ((unsigned)(RV) << RB) | ((big_ ? 255u : (unsigned)(WGT)) << (2 * RB)); \
+                    if (pos_ + (big_ ? 1 : 0) < ecap_w) {                                                              \
+                        sts_u32(a_sedge + 4u * pos_, pk_);                                                             \
+                        if (big_) sts_u32(a_sedge + 4u * pos_ + 4u, (254u << 24) | (unsigned)(WGT));                   \
+                    } else if (pos_ >= ecap_w && pos_ + (big_ ? 1 : 0) - ecap_w < gcap_w) {                            \
+                        gedge[pos_ - ecap_w] = pk_;                                                                    \
+                        if (big_) gedge[pos_ + 1 - ecap_w] = (254u << 24) | (unsigned)(WGT);                           \
+                    } else if (pos_ < ecap_w && gcap_w > 0) {   /* the pair straddles the two regions */               \
+                        sts_u32(a_sedge + 4u * pos_, pk_); gedge[0] = (254u << 24) | (unsigned)(WGT);                  \
+                    } else S->over = 1;                                                                                \
+                }                                                                                                      \
+                wcnt += __popc(m_) + __popc(mb_);                                                                      \
+            }
             // relax the warp's staged entries [FROM, TO) both ways (undirected meta edge); CHG: any distance moved
 #define EMB3_RELAX(FROM, TO, CHG)                                                                                      \
             for (int e_ = (FROM) + lane; e_ < (TO); e_ += 32) {                                                        \
                 const unsigned pk_ = (e_ < ecap_w) ? lds_u32(a_sedge + 4u * e_) : gedge[e_ - ecap_w];                  \
                 const unsigned ru_ = pk_ & RMASK, rv_ = (pk_ >> RB) & RMASK;                                           \
-                const double wt_ = lds_f64(a_invw + 8u * (pk_ >> (2 * RB)));                                           \
+                const unsigned wg_ = pk_ >> (2 * RB);                                                                  \
+                if (wg_ == 254u) continue;   /* second slot of the entry before it */                                  \
+                double wt_;                                                                                            \
+                if (wg_ == 255u) {                                                                                     \
+                    const unsigned nx_ = (e_ + 1 < ecap_w) ? lds_u32(a_sedge + 4u * (e_ + 1)) : gedge[e_ + 1 - ecap_w]; \
+                    wt_ = 1.0 / (double)(nx_ & 0xffffffu);                                                             \
+                } else wt_ = (wg_ < 128u) ? lds_f64(a_invw + 8u * wg_) : 1.0 / (double)wg_;                            \
                 const double du_ = lds_f64(a_dist + 8u * ru_), dv_ = lds_f64(a_dist + 8u * rv_);                       \
                 const double nv_ = du_ + wt_, nu_ = dv_ + wt_;                                                         \
                 if (nv_ < dv_) { smin_f64(a_dist + 8u * rv_, nv_); CHG = true; }                                       \
@@ -348,7 +391,13 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                                     }                                                                                  \
                                     EMB3_TAKE(ok_, tru, rv_, __popc(ENT_MASK(ENT)))                                    \
                                 }
-                                EMB3_ENTRY(q.x) EMB3_ENTRY(q.y) EMB3_ENTRY(q.z) EMB3_ENTRY(q.w)
+                                // (a rolled loop over the quad: four copies of the body cost more in instruction-cache misses --
+                                //  1.2 stalled warps per issue in profiles/r02i -- than the three moves per step cost here)
+#pragma unroll 1
+                                for (int c = 0; c < 4; c++) {
+                                    EMB3_ENTRY(q.x)
+                                    q.x = q.y; q.y = q.z; q.z = q.w;
+                                }
 #undef EMB3_ENTRY
                             }
                             __syncwarp();   // the criminal parts overwrite the row table
@@ -374,17 +423,10 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                                         if (wgt > 0 && ((bw.x >> (v & 31)) & 1u)) {   // 0: the reference divides by zero here
                                             ok = true; tru = rt.z; wi = wgt;
                                             rv = (int)bw.y + __popc(bw.x & ((1u << (v & 31)) - 1u));
-                                            if (wgt >= 64) {   // a large multiplicity gets one of the 64 per-evaluation table slots
-                                                wi = -1;
-                                                for (int t = 0; t < 64 && wi < 0; t++) {
-                                                    const int h = (wgt + t) & 63, old = atomicCAS(&S->wkey[h], 0, wgt);
-                                                    if (old == 0 || old == wgt) { wi = 64 + h; sts_f64(a_invw + 8u * wi, 1.0 / (double)wgt); }
-                                                }
-                                                if (wi < 0) { S->over = 1; ok = false; }
-                                            }
+                                            if (wgt > 0xffffff) { S->over = 1; ok = false; }
                                         }
                                     }
-                                    EMB3_TAKE(ok, tru, rv, wi)
+                                    EMB3_TAKE_C(ok, tru, rv, wi)
                                 }
                                 __syncwarp();
                             }
@@ -402,8 +444,10 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                 __syncthreads();
             }
 #undef EMB3_TAKE
+#undef EMB3_TAKE_C
             if (S->over) staged = false;
             if (gt == 0) PHASE(PH_STAGE)
+            if (!staged && mode == 0) EMB3_DEFER(1)
             if (staged) {
                 if (lane == 0 && wcnt > ecap_w) S->ph[PH_SPILL]++;
                 for (;;) {   // plain sweeps (every warp over the entries it staged) until one changes nothing
@@ -491,6 +535,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
     }
 #undef RANK
 #undef PHASE
+#undef EMB3_DEFER
     if (gt == 0) {
         unsigned long long *stq = RP(C.stats, r, ST_COUNT);
         if (S->st_edges) atomicAdd(&C.edges[r], S->st_edges);

@@ -962,7 +962,7 @@ __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     double *keys = C.scr_key + (size_t)slot * (C.Ncap + 1);
     unsigned long long edges = 0, abytes = 0, ncand = 0, ncrimes = 0;
     // the next round's request list must start empty; nobody appends to it during this launch
-    if (blockIdx.x == 0 && threadIdx.x == 0) C.n_emb[(parity ^ 1) * C.R + r] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C.n_emb[(parity ^ 1) * C.R + r] = 0; C.n_emb_big[r] = 0; }
     int ns = C.n_search[r];
     for (int item = blockIdx.x; item < ns; item += gridDim.x) {
         int c = RP(C.search_list, r, C.Ccap)[item];
@@ -1400,16 +1400,19 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
         x &= ~F_HASSCHOOL;
         attr[a] = x;
         int nprof = 0, nschool = 0;
+        bool low_flag = false;
         for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {  // Q11: own sets only
             uint32_t en = uent[e];
             nprof += (ENT_MASK(en) & MB_PROF) != 0; nschool += (ENT_MASK(en) & MB_SCHOOL) != 0;
-            uent[e] = en & ~((MB_PROF | MB_SCHOOL) << 24);
-            if (ENT_MASK(en) & (MB_PROF | MB_SCHOOL)) {   // the pair no longer mirrors itself (poc_device.cuh: ENT_ASYM)
-                ent_flag_asym(g, a, e);
-                const int ri = static_find_idx(g, ENT_COL(en), a);
-                if (ri >= 0) ent_flag_asym(g, ENT_COL(en), ri);
+            if (ENT_MASK(en) & (MB_PROF | MB_SCHOOL)) {
+                // the pair loses a layer on this side only: it no longer mirrors itself (poc_device.cuh: ENT_ASYM).  The
+                // reverse entries are flagged by the whole block afterwards (k_recruit_arrest)
+                en = (en & ~((MB_PROF | MB_SCHOOL) << 24)) | ENT_ASYM;
+                low_flag |= ENT_COL(en) < a;
+                uent[e] = en;
             }
         }
+        if (low_flag) g.u_mid[a] = g.u_rowptr[a];
         if (x & F_ALIVE) { RP(C.layer_tot, r, 8)[6] -= nprof; RP(C.layer_tot, r, 8)[7] -= nschool; }
         for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) cent_rw[e].y &= ~(int)((MB_PROF | MB_SCHOOL) << 24);
     }
@@ -1423,6 +1426,21 @@ __global__ void __launch_bounds__(256, 4) k_recruit_arrest(DevCtx C, int end_tic
     int tick = C.ti[C.grp].tick;
     int r = C.r0 + blockIdx.x;
     if (warp_id() == 0) recruit_arrest_warp(C, r, tick);
+    __syncthreads();
+    {   // get_caught flagged the entries it changed in the arrested agents' rows: flag their reverse entries (warp per agent)
+        Graph g = graph_of(C, r);
+        const int na = min(C.n_arrested[r], C.Mcap);
+        const int32_t *arr = RP(C.arrested, r, C.Mcap);
+        for (int i = warp_id(); i < na; i += (int)(blockDim.x >> 5)) {
+            const int a = arr[i];
+            for (int e = g.u_rowptr[a] + lane_id(); e < g.u_rowptr[a + 1]; e += 32) {
+                const uint32_t en = g.u_ent[e];
+                if (!(en & ENT_ASYM)) continue;
+                const int ri = static_find_idx(g, ENT_COL(en), a);
+                if (ri >= 0) ent_flag_asym(g, ENT_COL(en), ri);
+            }
+        }
+    }
     if (!end_tick) return;
     __syncthreads();
     int n = C.n_agents[r];
