@@ -25,7 +25,12 @@
 // a criminal entry carries a copy of the static layer mask of the same neighbour (poc_device.cuh): keep it current
 __device__ __forceinline__ void crim_mask_or(const Graph &g, int u, int v, unsigned bits) {
     const int ci = crim_find_idx(g, u, v);
-    if (ci >= 0 && !CE_IS_DEAD(g.c_ent[ci].y)) atomicOr(&const_cast<int2 *>(g.c_ent)[ci].y, (int)(bits << 24));
+    if (ci >= 0 && !CE_IS_DEAD(g.c_ent[ci].y)) {
+        // the pair may no longer weigh the same from both rows: both entries stand for themselves from now on (CE_ASYM)
+        atomicOr(&const_cast<int2 *>(g.c_ent)[ci].y, (int)(bits << 24) | CE_ASYM);
+        const int cj = crim_find_idx(g, v, u);
+        if (cj >= 0) atomicOr(&const_cast<int2 *>(g.c_ent)[cj].y, CE_ASYM);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- make_baby
@@ -481,6 +486,7 @@ __global__ void __launch_bounds__(256) k_die_apply(DevCtx C) {
             }
             if (v < 0 || v == a || (attr[v] & F_DYING)) continue;
             if (j < len0) ent_flag_asym(g, a, b0 + j);   // the reverse entry is emptied below: this one stands alone
+            else atomicOr(&cent[b1 + (j - len0)].y, CE_ASYM);
             const bool valive = (attr[v] & F_ALIVE) != 0;
             const int idx = static_find_idx(g, v, a);
             if (idx >= 0) {

@@ -7,7 +7,7 @@
 //   u_rowptr  i32 [Ncap+1], u_ent u32 [ucap]: the eight non-criminal layers merged into one directed CSR,
 //             entry = neighbour slot (22 bit) | one-sided flag (bit 22) | also-criminal flag (bit 23) | layer mask (8 bit) << 24 ;
 //             rows ascending
-//   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses | static mask << 24}, rows
+//   c_rowptr  i32 [Ncap+1], c_ent int2 [ccap]: criminal layer {neighbour, num_co_offenses | flags | static mask << 24}, rows
 //             ascending.  The flag and the mask copy make the multiplicity of an edge (model.py:1528-1535) a single
 //             load from either row: no row intersection on the traversal paths.
 // Reference mapping: Person attributes entities.py:49-83, the nine neighbour sets entities.py:38-47.
@@ -50,10 +50,11 @@ __host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < PO
 #define ENT_ASYM 0x00400000u
 #define ENT_CRIM 0x00800000u /* the same neighbour also has an entry in the criminal row */
 #define ENT_MASK(e) ((e) >> 24)
-// criminal entry .y = num_co_offenses (23 bit) | removed flag (bit 23) | copy of the static layer mask of the same neighbour << 24
+// criminal entry .y = num_co_offenses (22 bit) | one-sided flag (bit 22) | removed flag (bit 23) | copy of the static layer mask of the same neighbour << 24
 // A removed entry (Person.die took the owner's dead neighbour out of its criminal set, entities.py:652-661) stays in the
 // row as a tombstone with count 0 and mask 0 until the row is laid out again: traversals skip it, weights see 0.
-#define CE_CNT(y) ((int)((unsigned)(y) & 0x007fffffu))
+#define CE_CNT(y) ((int)((unsigned)(y) & 0x003fffffu))
+#define CE_ASYM 0x00400000 /* like ENT_ASYM: the reverse criminal entry is missing, removed or weighs differently */
 #define CE_DEAD 0x00800000
 #define CE_IS_DEAD(y) (((unsigned)(y) & 0x00800000u) != 0u)
 #define CE_SMASK(y) ((unsigned)(y) >> 24)
@@ -377,6 +378,13 @@ __device__ __forceinline__ bool ent_is_asym(const Graph &g, int u, uint32_t e) {
     if (ri < 0) return true;
     const uint32_t re = g.u_ent[ri];
     return (re & ENT_CRIM) || __popc(ENT_MASK(re)) != __popc(ENT_MASK(e));
+}
+// CE_ASYM of the criminal entry u -> v (value y), from the rows as they are now
+__device__ __forceinline__ bool crim_is_asym(const Graph &g, int u, int v, int y) {
+    const int ri = crim_find_idx(g, v, u);
+    if (ri < 0) return true;
+    const int ry = g.c_ent[ri].y;
+    return CE_IS_DEAD(ry) || CE_CNT(ry) + __popc(CE_SMASK(ry)) != CE_CNT(y) + __popc(CE_SMASK(y));
 }
 // flag entry idx of row u; a flagged entry in the lower part of the row makes the traversal read the whole row
 __device__ __forceinline__ void ent_flag_asym(const Graph &g, int u, int idx) {

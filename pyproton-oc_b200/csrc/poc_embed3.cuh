@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                             }
                             __syncwarp();   // the criminal parts overwrite the row table
                         }
-                        // -- criminal parts (few rows have one): weight = co-offences + layers of the mask copy, taken from both rows
+                        // -- criminal parts (few rows have one): weight = co-offences + layers of the mask copy
                         {
                             EMB3_SCAN(len1, excl, tot)
                             if (tot) {
@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                                         const int2 ce = __ldg(&g.c_ent[rt.x + f]);
                                         const int v = ce.x, wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
                                         const uint2 bw = lds_u2(a_bp + 8u * (v >> 5));
-                                        if (wgt > 0 && ((bw.x >> (v & 31)) & 1u)) {   // 0: the reference divides by zero here
+                                        // once per pair like the multiplex entries: from the lower slot's row unless flagged
+                                        if (wgt > 0 && (v > rt.y || (ce.y & CE_ASYM)) && ((bw.x >> (v & 31)) & 1u)) {   // 0: the reference divides by zero here
                                             ok = true; tru = rt.z; wi = wgt;
                                             rv = (int)bw.y + __popc(bw.x & ((1u << (v & 31)) - 1u));
                                             if (wgt > 0xffffff) { S->over = 1; ok = false; }

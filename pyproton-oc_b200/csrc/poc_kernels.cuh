@@ -159,6 +159,13 @@ __global__ void k_mark_asym(DevCtx C, int r, int n) {
         low_flag |= __any_sync(FULL_MASK, below && flag);
     }
     if (lane_id() == 0) g.u_mid[a] = low_flag ? b : b + lower;
+    int2 *cent = const_cast<int2 *>(g.c_ent);
+    for (int e = g.c_rowptr[a] + lane_id(); e < g.c_rowptr[a + 1]; e += 32) {
+        const int2 ce = cent[e];
+        if (CE_IS_DEAD(ce.y)) continue;
+        const int y = ce.y & ~CE_ASYM;
+        cent[e].y = y | (crim_is_asym(g, a, ce.x, y) ? CE_ASYM : 0);
+    }
 }
 
 // tot_<layer>_link of calculate_fast_reporters (model.py:1715-1732) for the eight static layers: computed once here
@@ -1160,7 +1167,7 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
             for (int j = pb; j < pe; j++) {
                 int b = (int)(pairs[j] & 0xffffffffu), pc = pcnt[j];
                 if (b < ce.x) shift += (pc & 0x40000000) ? 1 : 0;
-                else if (b == ce.x) ce.y = (pc & 0x3fffffff) | (int)(CE_SMASK(ce.y) << 24);
+                else if (b == ce.x) ce.y = (pc & 0x003fffff) | (ce.y & CE_ASYM) | (int)(CE_SMASK(ce.y) << 24);
             }
             ent_new[nb + (i - ob) + shift] = ce;
         }
@@ -1173,7 +1180,9 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
             int idx = static_find_idx(g, a, b);  // new link: copy the static mask of the pair and flag the static entry
             unsigned smask = 0;
             if (idx >= 0) { smask = ENT_MASK(uent_rw[idx]); atomicOr(&uent_rw[idx], ENT_CRIM); }
-            ent_new[nb + (lo - ob) + (pnew[j] - pnew[pb])] = make_int2(b, (pc & 0x3fffffff) | (int)(smask << 24));
+            // both rows of a new link see the same two static masks: one-sided (CE_ASYM) when their layer counts differ
+            const int asym = (__popc(static_find_mask(g, b, a)) != __popc(smask)) ? CE_ASYM : 0;
+            ent_new[nb + (lo - ob) + (pnew[j] - pnew[pb])] = make_int2(b, (pc & 0x003fffff) | asym | (int)(smask << 24));
         }
     }
     __syncthreads();
@@ -1414,7 +1423,10 @@ __device__ void recruit_arrest_warp(const DevCtx &C, int r, int tick) {
         }
         if (low_flag) g.u_mid[a] = g.u_rowptr[a];
         if (x & F_ALIVE) { RP(C.layer_tot, r, 8)[6] -= nprof; RP(C.layer_tot, r, 8)[7] -= nschool; }
-        for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) cent_rw[e].y &= ~(int)((MB_PROF | MB_SCHOOL) << 24);
+        for (int e = g.c_rowptr[a]; e < g.c_rowptr[a + 1]; e++) {
+            const int y = cent_rw[e].y;
+            if (CE_SMASK(y) & (MB_PROF | MB_SCHOOL)) cent_rw[e].y = (y & ~(int)((MB_PROF | MB_SCHOOL) << 24)) | CE_ASYM;
+        }
     }
     C.n_arrested[r] = nfound;
     cn[CN_TICK_ARRESTS] = nfound;
@@ -1438,6 +1450,13 @@ __global__ void __launch_bounds__(256, 4) k_recruit_arrest(DevCtx C, int end_tic
                 if (!(en & ENT_ASYM)) continue;
                 const int ri = static_find_idx(g, ENT_COL(en), a);
                 if (ri >= 0) ent_flag_asym(g, ENT_COL(en), ri);
+            }
+            int2 *cent = const_cast<int2 *>(g.c_ent);
+            for (int e = g.c_rowptr[a] + lane_id(); e < g.c_rowptr[a + 1]; e += 32) {
+                const int2 ce = cent[e];
+                if (!(ce.y & CE_ASYM) || CE_IS_DEAD(ce.y)) continue;
+                const int ri = crim_find_idx(g, ce.x, a);
+                if (ri >= 0) atomicOr(&cent[ri].y, CE_ASYM);
             }
         }
     }
