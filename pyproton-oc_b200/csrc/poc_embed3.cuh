@@ -304,8 +304,9 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                 wcnt += __popc(m_) + __popc(mb_);                                                                      \
             }
             // relax the warp's staged entries [FROM, TO) both ways (undirected meta edge); CHG: any distance moved
-#define EMB3_RELAX(FROM, TO, CHG)                                                                                      \
-            for (int e_ = (FROM) + lane; e_ < (TO); e_ += 32) {                                                        \
+#define EMB3_RELAX(FROM, TO, CHG, REV)                                                                                 \
+            for (int t_ = (FROM) + lane; t_ < (TO); t_ += 32) {                                                        \
+                const int e_ = (REV) ? (FROM) + (TO) - 1 - t_ : t_;                                                    \
                 const unsigned pk_ = (e_ < ecap_w) ? lds_u32(a_sedge + 4u * e_) : gedge[e_ - ecap_w];                  \
                 const unsigned ru_ = pk_ & RMASK, rv_ = (pk_ >> RB) & RMASK;                                           \
                 const unsigned wg_ = pk_ >> (2 * RB);                                                                  \
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                         if (!S->over) {
                             bool chg_ = false;
                             __syncwarp();
-                            EMB3_RELAX(wrel, wcnt, chg_)
+                            EMB3_RELAX(wrel, wcnt, chg_, false)
                             (void)chg_;
                         }
                         wrel = wcnt;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                 if (lane == 0 && wcnt > ecap_w) S->ph[PH_SPILL]++;
                 for (;;) {   // plain sweeps (every warp over the entries it staged) until one changes nothing
                     bool changed = false;
-                    EMB3_RELAX(0, wcnt, changed)
+                    EMB3_RELAX(0, wcnt, changed, false)   // (alternating the direction of the passes measured slower: 3.8 passes per evaluation against 3.5)
                     rounds++;
                     if (!__syncthreads_or(changed) || rounds > total + 2) break;
                 }
