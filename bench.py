@@ -466,7 +466,7 @@ def main():
                     "units_per_launch": units / nl, "unit_of_work": unit_name, "bytes_per_unit": alg_bytes / max(units, 1),
                     "share_of_step": t_ms / total_ms if total_ms else None,
                     "peak_source": "MEASURED_PEAKS.json (copy bandwidth, of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
-        r1 = roof("embeddedness", stats["emb_bytes"], stats["emb_requests"], "oc_embeddedness evaluation", "k_emb2")
+        r1 = roof("embeddedness", stats["emb_bytes"], stats["emb_requests"], "oc_embeddedness evaluation", "k_emb3")
         r1["note"] = ("latency / instruction-issue bound, not bandwidth bound: one evaluation is a BFS, a per-row gather pass and a "
                       "shortest-path fixed point on a few hundred nodes; DESIGN.md section 5 gives the measured ceilings (issue slots, "
                       "shared-memory wavefronts) and profiles/README.md the ncu captures")

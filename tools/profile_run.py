@@ -56,6 +56,7 @@ def main():
     if args.warm_ticks:
         E.run_ticks(tick0, args.warm_ticks, keys, reporters=False)
         tick0 += args.warm_ticks
+        E.stats(reset=True)   # the counters printed below cover the measured ticks only
     E.sync()
     if args.timing:
         E.set_timing(True)
