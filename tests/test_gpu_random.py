@@ -95,9 +95,13 @@ def test_random_states(seed):
     assert totals[0] > 0
 
 
-def test_dense_clique_overflows_staged_edges():
-    """150-member OC clique + co-offence counts above 255: more induced entries than ECAP and multiplicities that do
-    not fit the staged edge word -> the embeddedness kernel's unstaged relaxation path."""
+@pytest.mark.parametrize("emb_g", [None, "128", "256"])
+def test_dense_clique_overflows_staged_edges(emb_g, monkeypatch):
+    """150-member OC clique + co-offence counts above 255: more induced entries than the staged-edge capacity and
+    multiplicities that need the two-slot entry form.  With small blocks (128 / 256 threads per evaluation, the shapes
+    large batches run) the evaluations that do not fit are handed to the large-block launch."""
+    if emb_g:
+        monkeypatch.setenv("POC_EMB_G", emb_g)
     import pyproton_oc_b200 as P
     from oracle import oracle_c as O
     rng = np.random.default_rng(5)
@@ -113,9 +117,61 @@ def test_dense_clique_overflows_staged_edges():
     run_both(P, O, st, {"number_crimes_yearly_per10k": 4000}, ticks=6, key=9)
 
 
-def test_huge_ball_uses_global_distance_array():
+def hub_state(rng, n=6000, hub=17, nfriends=2600):
+    st = random_state(rng, n, mean_deg=6, oc_frac=0.02)
+    others = [i for i in range(n) if i != hub][:nfriends]
+    rp, col = st["rowptr_5"], st["col_5"]
+    src = np.repeat(np.arange(n), np.diff(rp))
+    pairs = set(zip(src.tolist(), col.tolist())) | {(hub, o) for o in others} | {(o, hub) for o in others}
+    key = np.array(sorted(a * n + b for a, b in pairs), dtype=np.int64)
+    s, dd = key // n, key % n
+    newrp = np.zeros(n + 1, np.int32)
+    np.add.at(newrp, s + 1, 1)
+    st["rowptr_5"], st["col_5"] = np.cumsum(newrp).astype(np.int32), dd.astype(np.int32)
+    st["oc_member"][hub] = 1
+    st["alive"][hub] = 1
+    return st
+
+
+def test_large_blocks_take_what_small_blocks_cannot_in_concurrent_groups(monkeypatch):
+    """256 replicas of the hub state in four replica groups on their own streams, 128 threads per evaluation: the small
+    blocks hand the hub's neighbourhood to the large-block launch (second size class), whose scratch slots must not be
+    shared with the launches of the other groups running at the same time.  Sampled replicas equal their single runs."""
+    monkeypatch.setenv("POC_GROUPS", "4")
+    monkeypatch.setenv("POC_EMB_G", "128")
+    import pyproton_oc_b200 as P
+    st = hub_state(np.random.default_rng(6), n=3000, nfriends=1400)
+    prm = P.make_params({"number_crimes_yearly_per10k": 3000, "oc_embeddedness_radius": 2})
+    R, ticks = 256, 3
+    keys = [31 + 5 * r for r in range(R)]
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 200000)
+    with P.CrimeEngine(R, n, stat, crim) as E:
+        E.set_params(prm)
+        for r in range(R):
+            E.upload_state(r, st, wait=False)
+        E.run_ticks(1, ticks, keys)
+        got = {r: E.download_state(r) for r in (0, 25, 100, 200, 255)}
+        cn, _ = E.counters()
+    assert (cn[:, 9] == 0).all()
+    monkeypatch.delenv("POC_GROUPS")
+    monkeypatch.delenv("POC_EMB_G")
+    for r, g in got.items():
+        with P.CrimeEngine(1, n, stat, crim) as E1:
+            E1.set_params(prm)
+            E1.upload_state(0, st)
+            E1.run_ticks(1, ticks, [keys[r]])
+            want = E1.download_state(0)
+        for k in COLS:
+            assert np.array_equal(g[k], want[k]), (r, k)
+        assert np.array_equal(g["col_6"], want["col_6"]) and np.array_equal(g["co_off"], want["co_off"]), r
+
+
+@pytest.mark.parametrize("emb_g", [None, "128"])
+def test_huge_ball_uses_global_distance_array(emb_g, monkeypatch):
     """A hub with 2600 friends: balls larger than the shared-memory distance array (and than the 12-bit rank
     fields when the radius is 2)."""
+    if emb_g:
+        monkeypatch.setenv("POC_EMB_G", emb_g)
     import pyproton_oc_b200 as P
     from oracle import oracle_c as O
     rng = np.random.default_rng(6)
