@@ -235,8 +235,13 @@ typedef struct poc_demography {
     double prop_q[1024];      /* quantiles of lognormal(nat_propensity_m, nat_propensity_sigma): a newborn's propensity */
     int32_t mort_max_age;     /* last age of the mortality table */
     int32_t n_prop;           /* quantiles in use (<= 1024) */
+    int32_t retirement_age;   /* model.py:121 */
+    int32_t _pad;
 } poc_demography;
-enum { POC_PHASE_BABY = 1, POC_PHASE_FRIENDS = 2, POC_PHASE_DIE = 4 };
+/* make_baby, make_friends, make_people_die; then retire_persons (model.py:1538-1551), remove_excess_friends (:629-643) and
+ * remove_excess_professional_links (:646-659) */
+enum { POC_PHASE_BABY = 1, POC_PHASE_FRIENDS = 2, POC_PHASE_DIE = 4, POC_PHASE_RETIRE = 8, POC_PHASE_XFRIENDS = 16,
+       POC_PHASE_XPROF = 32, POC_PHASE_ALL = 63 };
 int poc_set_demography(poc_ctx *ctx, const poc_demography *d);
 /* which of the phases poc_run_ticks runs after commit_crimes every tick, in the order of model.py:273-284 (default 0).
  * max_agents / max_static_entries of the ctx must leave room for the newborns and their links. */

@@ -52,6 +52,12 @@ def main(argv):
     if len(argv) > 1 and argv[1] == "distdemog":
         export_distribution_demog()
         return
+    if len(argv) > 1 and argv[1] == "distdemog2":   # + retire_persons, remove_excess_friends / _professional_links
+        export_distribution_demog("distdemog2_n1000_s42", keep=DEMOG_KEEP2)
+        return
+    if len(argv) > 1 and argv[1] == "distdemog3":   # + wedding
+        export_distribution_demog("distdemog3_n1000_s42", keep=DEMOG_KEEP2 + ["wedding"])
+        return
     if len(argv) > 2 and argv[1] == "pool":   # python -m oracle.make_states pool <variant> <seed> [<seed> ...]
         export_sweep_pool(argv[2], [int(x) for x in argv[3:]])
         return
@@ -84,16 +90,22 @@ OUT_OF_SCOPE_PHASES = ["wedding", "retire_persons", "make_baby", "remove_excess_
 
 
 DEMOG_KEEP = ["make_baby", "make_friends", "make_people_die"]
+DEMOG_KEEP2 = DEMOG_KEEP + ["retire_persons", "remove_excess_friends", "remove_excess_professional_links"]
 DEMOG_COLS = ["number_crimes", "current_oc_members", "people_jailed", "tot_criminal_link", "tot_friendship_link",
               "tot_household_link", "tot_sibling_link", "tot_offspring_link", "tot_parent_link", "number_deceased",
-              "number_born", "current_num_persons", "facilitators", "criminal_tendency_mean", "age_mean"]
+              "number_born", "current_num_persons", "facilitators", "criminal_tendency_mean", "age_mean",
+              "tot_professional_link", "tot_partner_link", "tot_school_link", "employed", "number_weddings"]
 
 
-def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42, n_runs=30, ticks=48):
+def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42, n_runs=30, ticks=48, keep=None):
     """Whole-run distribution fixture for the SURVEY.md 8(f) rows built on the device: the reference continued from ONE
     setup state with `n_runs` RNG streams, with its own make_baby / make_friends / make_people_die and the crime path
     active and every other phase of step() replaced by a no-op (`refdemog_*`).  Per tick: DEMOG_COLS."""
-    ref_model, _, _ = H.load_reference()
+    ref_model, ref_entities, _ = H.load_reference()
+    if keep and "retire_persons" in keep:
+        # the yearly hiring loop is written out inside step() (model.py:257-269), not a phase that can be switched off: its
+        # find_job would refill the jobs the retired leave and add professional links; with find_job a no-op the loop does nothing
+        ref_entities.Person.find_job = lambda self: None
     d = {}
     rows_all = []
     for j in range(n_runs):
@@ -108,7 +120,7 @@ def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42
             d["crime_multiplier"] = np.float64(model.crime_multiplier)
         model.random = np.random.default_rng(1000 + j)
         for ph in OUT_OF_SCOPE_PHASES:
-            if ph not in DEMOG_KEEP:
+            if ph not in (keep or DEMOG_KEEP):
                 setattr(model, ph, lambda *a, **k: None)
         rows = []
         for _ in range(ticks):

@@ -104,7 +104,8 @@ class TickOut(C.Structure):
 class Demog(C.Structure):
     """Mirror of orc_demog (hotpath.c)."""
     _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
-                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32)]
+                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32),
+                ("retirement_age", C.c_int32), ("_pad", C.c_int32)]
 
 
 def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None) -> Demog:
@@ -124,6 +125,7 @@ def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25
     for i, v in enumerate(tables.lognormal_quantiles(nat_propensity_m, nat_propensity_sigma, 1024)):
         d.prop_q[i] = v
     d.mort_max_age, d.n_prop = len(fem) - 1, 1024
+    d.retirement_age = 65
     return d
 
 
@@ -187,6 +189,11 @@ def lib():
         for fn in ("orc_make_baby", "orc_make_friends", "orc_make_people_die"):
             getattr(L, fn).restype = C.c_int32
             getattr(L, fn).argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_uint64]
+        L.orc_retire_persons.restype = C.c_int32
+        L.orc_retire_persons.argtypes = [C.c_void_p, C.POINTER(Demog)]
+        for fn in (L.orc_remove_excess_friends, L.orc_remove_excess_professional):
+            fn.restype = C.c_int32
+            fn.argtypes = [C.c_void_p, C.c_int32, C.c_uint64]
         L.orc_run_ticks_phases.restype = C.c_int32
         L.orc_run_ticks_phases.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_uint64, C.POINTER(C.c_double), C.c_void_p]
@@ -325,8 +332,18 @@ class OracleState:
     def make_people_die(self, p, dm, tick, key):
         return int(self.L.orc_make_people_die(self.h, C.byref(p), C.byref(dm), tick, key))
 
+    def retire_persons(self, dm):
+        return int(self.L.orc_retire_persons(self.h, C.byref(dm)))
+
+    def remove_excess_friends(self, tick, key):
+        return int(self.L.orc_remove_excess_friends(self.h, tick, key))
+
+    def remove_excess_professional(self, tick, key):
+        return int(self.L.orc_remove_excess_professional(self.h, tick, key))
+
     def run_ticks_phases(self, p, dm, phases: int, tick0: int, n_ticks: int, philox_key: int, crime_multiplier: float = 0.0):
-        """Hot path + the demography phases in `phases` (1 make_baby, 2 make_friends, 4 make_people_die)."""
+        """Hot path + the demography phases in `phases` (1 make_baby, 2 make_friends, 4 make_people_die, 8 retire_persons,
+        16 remove_excess_friends, 32 remove_excess_professional_links)."""
         mult = C.c_double(crime_multiplier)
         totals = np.zeros(6, dtype=np.int64)
         rc = self.L.orc_run_ticks_phases(self.h, C.byref(p), C.byref(dm), phases, tick0, n_ticks, philox_key, C.byref(mult),

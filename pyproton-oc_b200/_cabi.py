@@ -25,7 +25,8 @@ class PocError(RuntimeError):
 class Demography(C.Structure):
     """poc_demography (include/protonoc_b200.h)."""
     _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
-                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32)]
+                ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32),
+                ("retirement_age", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Params(C.Structure):

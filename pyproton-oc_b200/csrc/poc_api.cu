@@ -865,10 +865,26 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
 static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask, int n) {
     if (!mask || !n) return POC_OK;
     if (!ctx->demog_set) return fail(ctx, POC_ERR_STATE, "demography phases requested before poc_set_demography");
+    if (mask & POC_PHASE_RETIRE) {   // model.py:274
+        Timed t(ctx, TM_OTHER, s);
+        k_retire<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D);
+    }
     if (mask & POC_PHASE_BABY) {
         Timed t(ctx, TM_OTHER, s);
         k_make_baby<<<D.Rg, 1024, 0, s>>>(D);
         k_multiplex_insert<<<D.Rg, 1024, 0, s>>>(D);
+    }
+    if (mask & POC_PHASE_XFRIENDS) {   // model.py:276
+        Timed t(ctx, TM_OTHER, s);
+        k_remove_excess<<<dim3((n + 127) / 128, D.Rg), 128, 0, s>>>(D, MB_FRIEND, ST_XFRIEND, 1);
+        k_apply_removals<<<dim3(8, D.Rg), 256, 0, s>>>(D, MB_FRIEND, 5);
+        k_removals_done<<<(D.Rg + 127) / 128, 128, 0, s>>>(D);
+    }
+    if (mask & POC_PHASE_XPROF) {   // model.py:277
+        Timed t(ctx, TM_OTHER, s);
+        k_remove_excess<<<dim3((n + 127) / 128, D.Rg), 128, 0, s>>>(D, MB_PROF, ST_XPROF, 0);
+        k_apply_removals<<<dim3(8, D.Rg), 256, 0, s>>>(D, MB_PROF, 6);
+        k_removals_done<<<(D.Rg + 127) / 128, 128, 0, s>>>(D);
     }
     if (mask & POC_PHASE_FRIENDS) {
         Timed t(ctx, TM_OTHER, s);
@@ -895,7 +911,7 @@ static int refresh_counts(poc_ctx *ctx) {   // births add agent slots on the dev
 int poc_set_demography(poc_ctx *ctx, const poc_demography *dm) {
     CHECK_CTX();
     static_assert(sizeof(poc_demography) == sizeof(DevDemog), "poc_demography / DevDemog out of sync");
-    if (!dm || dm->n_prop < 1 || dm->n_prop > 1024 || dm->mort_max_age < 0 || dm->mort_max_age > 127) return fail(ctx, POC_ERR_ARG, "poc_set_demography: bad argument");
+    if (!dm || dm->n_prop < 1 || dm->n_prop > 1024 || dm->mort_max_age < 0 || dm->mort_max_age > 127 || dm->retirement_age < 0) return fail(ctx, POC_ERR_ARG, "poc_set_demography: bad argument");
     CU(cudaMemcpyAsync(ctx->d_demog, dm, sizeof(DevDemog), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->demog_set = true;
@@ -904,7 +920,7 @@ int poc_set_demography(poc_ctx *ctx, const poc_demography *dm) {
 
 int poc_set_phases(poc_ctx *ctx, int mask) {
     CHECK_CTX();
-    if (mask & ~7) return fail(ctx, POC_ERR_ARG, "poc_set_phases: unknown phase");
+    if (mask & ~POC_PHASE_ALL) return fail(ctx, POC_ERR_ARG, "poc_set_phases: unknown phase");
     if (mask && !ctx->demog_set) return fail(ctx, POC_ERR_STATE, "poc_set_phases: poc_set_demography first");
     ctx->phases = mask;
     return POC_OK;
@@ -912,7 +928,7 @@ int poc_set_phases(poc_ctx *ctx, int mask) {
 
 int poc_run_phase(poc_ctx *ctx, int phase, int tick, const uint64_t *keys) {
     CHECK_CTX();
-    if (phase != POC_PHASE_BABY && phase != POC_PHASE_FRIENDS && phase != POC_PHASE_DIE) return fail(ctx, POC_ERR_ARG, "poc_run_phase: one phase at a time");
+    if (phase <= 0 || (phase & ~POC_PHASE_ALL) || (phase & (phase - 1))) return fail(ctx, POC_ERR_ARG, "poc_run_phase: one phase at a time");
     if (keys) CU(cudaMemcpyAsync(ctx->d.philox_key, keys, sizeof(uint64_t) * ctx->d.R, cudaMemcpyHostToDevice, ctx->stream));
     TickInfo t{tick, ctx->epoch, 0, 0};
     CU(cudaMemcpyAsync(ctx->d_ti, &t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1069,8 +1085,8 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
                 if (rc2) return rc2;
                 rc2 = launch_commit(ctx, D, s, true, false, (k == 0 && g + 1 < G) ? ctx->gstag[g] : nullptr, 0);
                 if (rc2) return rc2;
-                // model.py:274-278: make_baby, make_friends (retire / remove_excess_* are not built)
-                rc2 = launch_phases(ctx, D, s, ctx->phases & (POC_PHASE_BABY | POC_PHASE_FRIENDS), n);
+                // model.py:274-278: retire_persons, make_baby, remove_excess_friends / _professional_links, make_friends
+                rc2 = launch_phases(ctx, D, s, ctx->phases & ~POC_PHASE_DIE, n);
                 if (rc2) return rc2;
                 if (n) { Timed t(ctx, TM_OTHER, s); k_end_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, 0); }
                 rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_DIE, n);   // model.py:284

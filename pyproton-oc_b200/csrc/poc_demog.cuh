@@ -511,3 +511,107 @@ __global__ void __launch_bounds__(256) k_die_apply(DevCtx C) {
     for (int i = tid; i < nd; i += blockDim.x) { const int a = list[i]; attr[a] &= ~(F_ALIVE | F_DYING | (1u << 30)); }
     if (tid == 0) { RP(C.counters, r, CN_COUNT)[CN_DECEASED] += nd; dmn[1] = 0; }
 }
+
+// ---------------------------------------------------------------------------------------------- the next rows of 8(f)
+// a layer bit leaves the criminal entry's copy of the static mask too; the pair stands for itself from then on
+__device__ __forceinline__ void crim_mask_clear(const Graph &g, int u, int v, unsigned bits) {
+    const int ci = crim_find_idx(g, u, v);
+    if (ci >= 0 && !CE_IS_DEAD(g.c_ent[ci].y)) {
+        int2 *cent = const_cast<int2 *>(g.c_ent);
+        atomicAnd(&cent[ci].y, ~(int)(bits << 24));
+        atomicOr(&cent[ci].y, CE_ASYM);
+        const int cj = crim_find_idx(g, v, u);
+        if (cj >= 0) atomicOr(&cent[cj].y, CE_ASYM);
+    }
+}
+
+// retire_persons, model.py:1538-1551 (oracle/hotpath.c orc_retire_persons): thread per agent, no draws
+__global__ void __launch_bounds__(256) k_retire(DevCtx C) {
+    const int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    uint32_t *attr = RP(C.attr, r, C.Ncap);
+    const uint32_t x = attr[a];
+    if (!(x & F_ALIVE) || !(x & F_HASJOB) || attr_age(x) < C.demog->retirement_age) return;
+    attr[a] = x & ~F_HASJOB;
+    Graph g = graph_of(C, r);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
+    int nprof = 0;
+    for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) {   // the OWN professional set only
+        const uint32_t en = uent[e];
+        if (!(ENT_MASK(en) & MB_PROF)) continue;
+        nprof++;
+        atomicAnd(&uent[e], ~(MB_PROF << 24));
+        if (en & ENT_CRIM) crim_mask_clear(g, a, ENT_COL(en), MB_PROF);
+        ent_flag_asym(g, a, e);   // one-sided: neither entry of the pair mirrors the other now
+        const int ri = static_find_idx(g, ENT_COL(en), a);
+        if (ri >= 0) ent_flag_asym(g, ENT_COL(en), ri);
+    }
+    if (nprof) atomicAdd((unsigned long long *)&RP(C.layer_tot, r, 8)[6], (unsigned long long)(-(long long)nprof));
+}
+
+// remove_excess_friends / remove_excess_professional_links, pass 1 (thread per agent, decisions on the state the phase
+// started from): selection sampling over the row in ascending slot order, the chosen links are queued
+__global__ void __launch_bounds__(128) k_remove_excess(DevCtx C, unsigned bit, int stage, int dunbar) {
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C.n_agents[r]) return;
+    const uint32_t xa = RP(C.attr, r, C.Ncap)[a];
+    if (!(xa & F_ALIVE)) return;
+    Graph g = graph_of(C, r);
+    const int b = g.u_rowptr[a], e = g.u_rowptr[a + 1];
+    int len = 0;
+    for (int i = b; i < e; i++) len += (ENT_MASK(g.u_ent[i]) & bit) != 0;
+    const int age = attr_age(xa), limit = dunbar ? 150 - abs(age - 30) : 30;
+    if (len <= limit) return;
+    int need = len - limit, k = 0;
+    const unsigned long long key = C.philox_key[r];
+    int *dmn = RP(C.dm_n, r, 4);
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    for (int i = b; i < e && need > 0; i++) {
+        const uint32_t en = g.u_ent[i];
+        if (!(ENT_MASK(en) & bit)) continue;
+        const double u = philox_u1s(key, tick, stage, a, k);
+        if (u * (double)(len - k) < (double)need) {
+            const int pos = atomicAdd(&dmn[3], 1);
+            if (pos < C.DPcap) pairs[pos] = DM_KEY(a, ENT_COL(en), bit); else atomicExch(&RP(C.counters, r, CN_COUNT)[CN_ERROR], 25);
+            need--;
+        }
+        k++;
+    }
+}
+
+// pass 2: the bit leaves both entries of every queued link (Person.remove_link, entities.py:226-237)
+__global__ void __launch_bounds__(256) k_apply_removals(DevCtx C, unsigned bit, int layer) {
+    const int r = C.r0 + blockIdx.y;
+    int *dmn = RP(C.dm_n, r, 4);
+    const int np = min(dmn[3], C.DPcap);
+    const unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    Graph g = graph_of(C, r);
+    uint32_t *ent = const_cast<uint32_t *>(g.u_ent);
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    long long *ltot = RP(C.layer_tot, r, 8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const int a = DM_U(pairs[i]), c = DM_V(pairs[i]);
+        const int e1 = static_find_idx(g, a, c), e2 = static_find_idx(g, c, a);
+        if (e1 >= 0) {
+            const unsigned old = atomicAnd(&ent[e1], ~(bit << 24));
+            if (old & (bit << 24)) {
+                if (attr[a] & F_ALIVE) atomicAdd((unsigned long long *)&ltot[layer], (unsigned long long)-1ll);
+                if (old & ENT_CRIM) crim_mask_clear(g, a, c, bit);
+            }
+        }
+        if (e2 >= 0) {
+            const unsigned old = atomicAnd(&ent[e2], ~(bit << 24));
+            if (old & (bit << 24)) {
+                if (attr[c] & F_ALIVE) atomicAdd((unsigned long long *)&ltot[layer], (unsigned long long)-1ll);
+                if (old & ENT_CRIM) crim_mask_clear(g, c, a, bit);
+            }
+        }
+        // a link that was one-sided before may leave the pair unbalanced (or balance it: the flag only ever gets set)
+        ent_asym_update(g, a, c);
+    }
+}
+__global__ void k_removals_done(DevCtx C) {
+    const int r = C.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < C.r0 + C.Rg) RP(C.dm_n, r, 4)[3] = 0;
+}

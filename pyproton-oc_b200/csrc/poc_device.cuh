@@ -163,11 +163,12 @@ struct DevDemog {
     double poisson_cdf[32];   // CDF of Poisson(3) (model.py:619)
     double prop_q[1024];      // quantiles of the newborns' propensity lognormal (entities.py:71)
     int mort_max_age, n_prop;
+    int retirement_age, _pad;
 };
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) -----------------------------------------------------------
 enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4, ST_DIE = 5, ST_FACREP = 6, ST_BABY = 7,
-       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10 };
+       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10, ST_XFRIEND = 11, ST_XPROF = 12 };
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
 #pragma unroll
@@ -187,6 +188,14 @@ __device__ __forceinline__ void philox_u2(unsigned long long key, int tick, int 
     unsigned long long a = ((unsigned long long)o[1] << 32) | o[0], b = ((unsigned long long)o[3] << 32) | o[2];
     u0 = __dmul_rn((double)(a >> 11), 1.0 / 9007199254740992.0);
     u1 = __dmul_rn((double)(b >> 11), 1.0 / 9007199254740992.0);
+}
+
+// one uniform from the counter (tick, stage, idx, sub): phases that draw per (agent, entry)
+__device__ __forceinline__ double philox_u1s(unsigned long long key, int tick, int stage, int idx, int sub) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)tick, (uint32_t)stage, (uint32_t)idx, (uint32_t)sub, (uint32_t)key, (uint32_t)(key >> 32), o);
+    unsigned long long a = ((unsigned long long)o[1] << 32) | o[0];
+    return __dmul_rn((double)(a >> 11), 1.0 / 9007199254740992.0);
 }
 
 // searchsorted(cdf, u, side='right')

@@ -210,13 +210,14 @@ class CrimeEngine:
         return st
 
     # ------------------------------------------------------------------ demography phases
-    PHASE_BABY, PHASE_FRIENDS, PHASE_DIE = 1, 2, 4
+    PHASE_BABY, PHASE_FRIENDS, PHASE_DIE, PHASE_RETIRE, PHASE_XFRIENDS, PHASE_XPROF, PHASE_ALL = 1, 2, 4, 8, 16, 32, 63
 
     def set_demography(self, d):
         self._ck(self.L.poc_set_demography(self.h, C.byref(d)))
 
     def set_phases(self, mask: int):
-        """Which of make_baby (1) / make_friends (2) / make_people_die (4) run_ticks runs every tick (default 0)."""
+        """Which of make_baby (1) / make_friends (2) / make_people_die (4) / retire_persons (8) / remove_excess_friends (16) /
+        remove_excess_professional_links (32) run_ticks runs every tick, in the order of ProtonOC.step (default 0)."""
         self._ck(self.L.poc_set_phases(self.h, int(mask)))
         self._phases = int(mask)
 

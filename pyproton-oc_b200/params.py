@@ -77,7 +77,8 @@ def make_params(attrs: Optional[Dict] = None, c_range=None, co_offenders=None, c
     return p
 
 
-def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None) -> Demography:
+def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None,
+                    retirement_age: int = 65) -> Demography:
     """poc_demography for the phases of SURVEY.md 8(f).  mortality: (female[ages], male[ages]) yearly probabilities
     (initial_mortality_rates.csv, entities.py:615-626), fertility: [3][64] yearly by [min(children, 2)][age]
     (initial_fertility_rates.csv, entities.py:605-613); defaults: the reference's Palermo tables."""
@@ -95,4 +96,5 @@ def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float =
     for i, v in enumerate(tables.lognormal_quantiles(nat_propensity_m, nat_propensity_sigma, 1024)):
         d.prop_q[i] = v
     d.mort_max_age, d.n_prop = len(fem) - 1, 1024
+    d.retirement_age = int(retirement_age)   # model.py:121
     return d

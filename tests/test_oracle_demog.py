@@ -89,3 +89,97 @@ def test_phase_invariants():
     assert S.n >= n0 and S.demog_counters()["number_born"] == S.n - n0
     # friendship symmetric among pairs created by make_friends (one-sided links exist only where get_caught cleared a side)
     assert len(pairs) > 0
+
+
+def test_six_phases_in_distribution_against_the_reference():
+    """retire_persons, remove_excess_friends, remove_excess_professional_links added to the three above: the oracle's runs
+    against 30 continuations by the unmodified reference with exactly these six phases and the crime path active
+    (oracle/make_states.py distdemog2), KS per column at three ticks."""
+    fx = U.load_fixture(U.GOLDEN + "/distdemog2_n1000_s42.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    P, D = O.make_params(prm), O.make_demog()
+    layer_of = {"tot_friendship_link": 5, "tot_household_link": 4, "tot_professional_link": 7, "tot_criminal_link": 6}
+    names = ["current_num_persons", "employed", "number_crimes", "current_oc_members"] + list(layer_of)
+    checks = (5, 23, ticks - 1)
+    cols = {k: np.zeros((runs, len(checks))) for k in names}
+    for j in range(runs):
+        S = O.OracleState(st)
+        S.reserve(len(st["alive"]) + 300)
+        S.set_children(st["number_of_children"])
+        mult, crimes, t_done = 0.0, 0, 0
+        for ci, t_end in enumerate(checks):
+            mult, tot = S.run_ticks_phases(P, D, 63, t_done + 1, t_end + 1 - t_done, 7100 + j, mult)
+            crimes += int(tot[0])
+            t_done = t_end + 1
+            c = S.cols()
+            al = c["alive"] > 0
+            vals = {"current_num_persons": al.sum(), "employed": c["has_job"][al].sum(), "number_crimes": crimes,
+                    "current_oc_members": c["oc_member"][al].sum()}
+            for k, l in layer_of.items():
+                vals[k] = np.diff(S.layer(l)[0])[al].sum()
+            for k in names:
+                cols[k][j, ci] = vals[k]
+    for k in names:
+        ref = fx["refdemog_" + k]
+        for ci, t in enumerate(checks):
+            p = ks_2samp(cols[k][:, ci], ref[:, t]).pvalue
+            assert p > 0.005, (k, t, p, cols[k][:, ci].mean(), ref[:, t].mean())
+        if ref[:, -1].mean() > 20:
+            assert abs(cols[k][:, -1].mean() - ref[:, -1].mean()) <= 0.12 * ref[:, -1].mean(), (k, cols[k][:, -1].mean(), ref[:, -1].mean())
+
+
+def _with_hub(st, layer, hub, members):
+    """the state with `hub` linked to every agent of `members` in `layer` (both directions)"""
+    st = {k: v.copy() for k, v in st.items()}
+    n = len(st["alive"])
+    rp, col = st["rowptr_%d" % layer], st["col_%d" % layer]
+    src = np.repeat(np.arange(n), np.diff(rp))
+    pairs = set(zip(src.tolist(), col.tolist())) | {(hub, o) for o in members} | {(o, hub) for o in members}
+    key = np.array(sorted(a * n + b for a, b in pairs), dtype=np.int64)
+    newrp = np.zeros(n + 1, np.int64)
+    np.add.at(newrp, key // n + 1, 1)
+    st["rowptr_%d" % layer], st["col_%d" % layer] = np.cumsum(newrp).astype(np.int32), (key % n).astype(np.int32)
+    return st
+
+
+def test_retire_and_remove_excess_invariants():
+    """retire_persons: nobody of retirement age keeps a job or an own professional set, the colleagues keep theirs (one-sided,
+    model.py:1550); remove_excess_*: afterwards no living agent is over its limit, exactly the surplus went where nobody else
+    cut, and the layer stays symmetric."""
+    fx = U.load_fixture(U.GOLDEN + "/state_n3000_s42_baseline.npz")
+    st = U.pre_state(fx)
+    n = len(st["alive"])
+    alive = np.flatnonzero(st["alive"] > 0)
+    hub_f, hub_p = int(alive[10]), int(alive[20])
+    st = _with_hub(st, 5, hub_f, [int(x) for x in alive[100:400]])     # 300 friends: over any Dunbar number
+    st = _with_hub(st, 7, hub_p, [int(x) for x in alive[500:580]])     # 80 colleagues: over 30
+    D = O.make_demog()
+    S = O.OracleState(st)
+    S.begin_tick(12)   # the first birthday tick of a setup state (birth_tick = -12 * age, entities.py:271): the 64-year-olds turn 65
+    c0 = S.cols()
+    prof0 = S.layer(7)
+    old = np.flatnonzero((c0["alive"] > 0) & (c0["age"] >= 65) & (c0["has_job"] > 0))
+    nr = S.retire_persons(D)
+    assert nr == len(old) and nr > 0
+    c1, prof1 = S.cols(), S.layer(7)
+    assert not c1["has_job"][old].any() and (np.diff(prof1[0])[old] == 0).all()
+    src = np.repeat(np.arange(n), np.diff(prof1[0]))
+    still = np.isin(prof1[1], old) & ~np.isin(src, old)
+    assert still.sum() == (np.isin(prof0[1], old) & ~np.isin(np.repeat(np.arange(n), np.diff(prof0[0])), old)).sum()   # colleagues untouched
+    assert S.retire_persons(D) == 0   # idempotent
+    for layer, fn, lim in ((5, S.remove_excess_friends, lambda age: 150 - abs(int(age) - 30)), (7, S.remove_excess_professional, lambda age: 30)):
+        before = np.diff(S.layer(layer)[0])
+        over = [a for a in alive.tolist() if before[a] > lim(c1["age"][a])]
+        assert over, layer
+        nrem = fn(1, 99)
+        rp, col, _ = S.layer(layer)
+        after = np.diff(rp)
+        assert nrem == 2 * sum(before[a] - lim(c1["age"][a]) for a in over) or len(over) > 1
+        for a in alive.tolist():
+            assert after[a] <= max(lim(c1["age"][a]), 0) or before[a] <= lim(c1["age"][a]), (layer, a, after[a])
+        srcs = np.repeat(np.arange(n), after)
+        pairs = set(zip(srcs.tolist(), col.tolist()))
+        hub = hub_f if layer == 5 else hub_p
+        assert all((v, u) in pairs for (u, v) in pairs if u == hub)
+        assert fn(2, 99) == 0   # nobody is over the limit any more
