@@ -186,7 +186,7 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay_or
 /* n_ticks iterations of {begin_tick; yearly tendency + multiplier; commit_crimes; end_tick}
  * (the hot-path subset of ProtonOC.step, model.py:226-288) with no host synchronisation inside.
  * reporters_out: [n_replicas][n_ticks][POC_N_REPORTERS] doubles, copied back at the end (may be NULL). */
-#define POC_N_REPORTERS 40 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
+#define POC_N_REPORTERS 42 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
 int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *philox_keys, double *reporters_out);
 /* the same, but the reporter rows stay on the device (for a collective over NVLink, run_modes.py:221-232 gathers the
  * outputs of the runs): *rows_dev points at [n_replicas][*ticks_per_replica][POC_N_REPORTERS] doubles owned by the ctx and

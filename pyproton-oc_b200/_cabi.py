@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libprotonoc_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "protonoc_b200.h")
 
-NUM_LAYERS, MAX_CELLS, MAX_TAB, MAX_GROUP, N_REPORTERS, CN_COUNT = 9, 32, 16, 32, 40, 24
+NUM_LAYERS, MAX_CELLS, MAX_TAB, MAX_GROUP, N_REPORTERS, CN_COUNT = 9, 32, 16, 32, 42, 24
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

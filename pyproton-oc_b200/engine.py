@@ -37,7 +37,8 @@ REPORTER_NAMES = ["number_crimes", "crime_size_fails", "facilitator_crimes", "fa
                   "tot_offspring_link", "tot_parent_link", "tot_partner_link", "tot_household_link",
                   "tot_friendship_link", "tot_professional_link", "tot_school_link",
                   "number_protected_recruited_this_tick", "number_law_interventions_this_tick", "tick",
-                  "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code"]
+                  "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code",
+                  "number_born", "number_deceased"]
 TIMER_CLASSES = ["cells", "tendency", "draw", "search", "embeddedness", "commit", "arrests", "other"]
 
 

@@ -89,11 +89,22 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
             raise ValueError("all runs of one batch must have the same num_ticks")
         T = ticks.pop()
         n, stat, crim = CrimeEngine.capacity_for(states, headroom_criminal=max(200000, 16 * max(len(s["alive"]) for s in states)))
-        with CrimeEngine(len(batch), n, stat, crim, device=device) as E:
+        phases = models[0].device_phases
+        if any(m.device_phases != phases for m in models):
+            raise ValueError("all runs of one batch must run the same device phases")
+        # births add agent slots and links on the device (the same head room as a single run, ProtonOC._engine_ready)
+        grow = (max(n // 2, 2000), max(stat, 1)) if phases else (0, 0)
+        with CrimeEngine(len(batch), n + grow[0], 2 * max(stat, 1) + grow[1], crim, device=device) as E:
+            from .params import make_demography
+            m0 = models[0]   # the demography tables are per engine: one batch, one (nat_propensity, retirement_age) setting
+            E.set_demography(make_demography(m0.nat_propensity_m, m0.nat_propensity_sigma, retirement_age=m0.retirement_age))
             for r, (m, st) in enumerate(zip(models, states)):
                 E.set_params(m._params(), replica=r)
                 E.upload_state(r, st, wait=False)
             E.sync()   # input errors of the queued uploads surface here
+            for r, st in enumerate(states):
+                E.upload_children(r, st["number_of_children"])
+            E.set_phases(phases)
             E.crime_multiplier()   # ProtonOC.setup: model.py:1029-1030
             E.tendency()
             rep = np.zeros((len(batch), T + 1, len(REPORTER_NAMES)), np.float64)

@@ -28,7 +28,7 @@ import pandas as pd
 
 from . import synth, tables
 from .engine import LAYER_NAMES, REPORTER_NAMES, CrimeEngine
-from .params import make_params
+from .params import make_demography, make_params
 
 free_parameters = ["migration_on", "initial_agents", "num_ticks", "intervention",
                    "max_accomplice_radius", "number_arrests_per_year",
@@ -93,7 +93,8 @@ _COLS = {"alive": np.uint8, "age": np.int32, "birth_tick": np.int32, "male": np.
          "facilitator": np.uint8, "prisoner": np.uint8, "retired": np.uint8, "has_job": np.uint8,
          "has_school": np.uint8, "target_of_intervention": np.uint8, "num_crimes_committed": np.int32,
          "num_crimes_committed_this_tick": np.int32, "criminal_tendency": np.float64,
-         "sentence_countdown": np.float64, "new_recruit": np.int32, "arrest_weight": np.float64, "father": np.int32}
+         "sentence_countdown": np.float64, "new_recruit": np.int32, "arrest_weight": np.float64, "father": np.int32,
+         "number_of_children": np.int32}
 _COL_DEFAULTS = {"alive": 1, "wealth_level": 1, "new_recruit": -2, "father": -1}
 # Person attribute -> state column
 _ATTR = {"gender_is_male": "male", "num_crimes_committed": "num_crimes_committed",
@@ -280,9 +281,11 @@ class _DataCollector:
 
 class ProtonOC:
     out_of_scope_phases = ["interventions (family / social / welfare)", "graduate_and_enter_jobmarket", "find_job",
-                           "let_migrants_in", "return_kids", "wedding", "retire_persons", "make_baby",
-                           "remove_excess_friends", "remove_excess_professional_links", "make_friends",
-                           "make_people_die"]
+                           "update_unemployment_status", "let_migrants_in", "return_kids", "wedding"]
+    # the phases of step() besides the crime path that run on the device (CrimeEngine.PHASE_*): retire_persons,
+    # make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, make_people_die, in the reference's
+    # order (model.py:274-284).  0 = the crime path alone.
+    device_phases: int = CrimeEngine.PHASE_ALL
 
     def __init__(self, seed: int = int.from_bytes(os.urandom(4), sys.byteorder), collect_agents: bool = False) -> None:
         self.seed: int = seed
@@ -432,6 +435,8 @@ class ProtonOC:
         n = len(st["alive"])
         self._st = {k: np.array(st[k], dtype=dt) if k in st else np.full(n, _COL_DEFAULTS.get(k, 0), dt)
                     for k, dt in _COLS.items()}
+        if "number_of_children" not in st:   # Person.number_of_children (entities.py:75): the offspring links when not exported
+            self._st["number_of_children"] = np.diff(st["rowptr_1"]).astype(np.int32)
         self._adj = []
         for li in range(len(LAYER_NAMES)):
             rp, col = st["rowptr_%d" % li], st["col_%d" % li]
@@ -474,11 +479,16 @@ class ProtonOC:
             if e is None or n > e.max_agents or stat > getattr(e, "_stat_cap", 0) or crim > getattr(e, "_crim_cap", 0):
                 if e is not None:
                     e.close()
-                e = CrimeEngine(1, max(n, 1), max(stat, 1) * 2, crim, device=self._device)
+                # births add agent slots and links on the device: room for them (a run that outgrows it raises, error 20-22)
+                grow = (max(n // 2, 2000), max(stat, 1)) if self.device_phases else (0, 0)
+                e = CrimeEngine(1, max(n, 1) + grow[0], max(stat, 1) * 2 + grow[1], crim, device=self._device)
                 e._stat_cap, e._crim_cap = max(stat, 1) * 2, crim
                 self._engine = e
             e.set_params(self._params())
+            e.set_demography(make_demography(self.nat_propensity_m, self.nat_propensity_sigma, retirement_age=self.retirement_age))
             e.upload_state(0, st)
+            if "number_of_children" in st:
+                e.upload_children(0, st["number_of_children"])
             e.set_crime_multiplier(float(self.crime_multiplier))
             self._dirty = False
         else:
@@ -491,7 +501,11 @@ class ProtonOC:
             return
         self._host_stale = False
         st = self._engine.download_state(0)
-        st["retired"] = self._st["retired"]
+        n = len(st["alive"])
+        retired = np.zeros(n, self._st["retired"].dtype)   # newborns (slots added by make_baby on the device) are not retired
+        retired[:len(self._st["retired"])] = self._st["retired"][:n]
+        st["retired"] = retired | ((st["age"] >= self.retirement_age) & (st["alive"] > 0)).astype(retired.dtype)
+        st["number_of_children"] = self._engine.download_children(0)
         self.load_state(st)
         self._dirty = False
 
@@ -600,7 +614,15 @@ class ProtonOC:
             self.calculate_crime_multiplier()
         self.reset_oc_embeddedness()
         self.commit_crimes()
+        e = self._engine_ready()
+        ph = self.device_phases
+        for p in (e.PHASE_RETIRE, e.PHASE_BABY, e.PHASE_XFRIENDS, e.PHASE_XPROF, e.PHASE_FRIENDS):   # model.py:274-278
+            if ph & p:
+                e.run_phase(p, self.tick, [self._philox_key])
         e.end_tick()
+        if ph & e.PHASE_DIE:                                                                          # model.py:284
+            e.run_phase(e.PHASE_DIE, self.tick, [self._philox_key])
+        self._host_stale = True
         self.schedule.step()
         self.calculate_fast_reporters()
         self.datacollector.collect(self)
@@ -622,7 +644,9 @@ class ProtonOC:
                 self.step()
             return
         e = self._engine_ready()
+        e.set_phases(self.device_phases)
         rep = e.run_ticks(self.tick, self.num_ticks, [self._philox_key], reporters=True)[0]
+        e.set_phases(0)
         self._host_stale = True
         cn, _ = e.counters()
         if cn[0, 9]:

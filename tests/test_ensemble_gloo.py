@@ -59,7 +59,8 @@ def _worker(rank, world, port, q):
 def test_two_rank_ensemble_equals_single_process():
     from pyproton_oc_b200 import ensemble
     want = ensemble.run_ensemble(_args(), _oracle_runner, replicas_per_batch=3)
-    assert want.shape == (10, T, 40)
+    from pyproton_oc_b200.engine import REPORTER_NAMES
+    assert want.shape == (10, T, len(REPORTER_NAMES))
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

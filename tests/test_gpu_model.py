@@ -148,11 +148,12 @@ def test_oc_crime_net_init_and_big_crimes(P):
     assert model.big_crime_from_small_fish > 0
     st = model.state_dict()
     assert (st["co_off"] >= 1).all()
-    # criminal links stay symmetric with equal counts (commit_crime, model.py:1495-1504)
+    # criminal links stay symmetric with equal counts (commit_crime, model.py:1495-1504) among the living: who died in these
+    # ticks (make_people_die runs on the device too) left the others' sets and kept its own (Person.die, entities.py:652-661)
     n = len(st["alive"])
     src = np.repeat(np.arange(n), np.diff(st["rowptr_6"]))
     fwd = dict(zip(zip(src.tolist(), st["col_6"].tolist()), st["co_off"].tolist()))
-    assert all(fwd.get((b, a)) == c for (a, b), c in fwd.items())
+    assert all(fwd.get((b, a)) == c for (a, b), c in fwd.items() if st["alive"][a] and st["alive"][b])
 
 
 def test_oc_crime_stats(P):
@@ -183,8 +184,12 @@ def test_run_output_contract_and_fast_equals_stepwise(P):
     # every column of calculate_fast_reporters: device reporter kernel (fast) == host computation from the state
     for col in ["employed", "facilitators", "number_students", "tot_friendship_link", "tot_household_link",
                 "tot_partner_link", "tot_offspring_link", "tot_school_link", "tot_professional_link",
-                "tot_sibling_link", "tot_parent_link", "number_law_interventions_this_tick"]:
+                "tot_sibling_link", "tot_parent_link", "number_law_interventions_this_tick", "current_num_persons",
+                "number_born", "number_deceased"]:
         assert fa[col].tolist()[1:] == fb[col].tolist()[1:], col
+    # the six device phases of step() were on (ProtonOC.device_phases): people died, friendships were made
+    assert fa["number_deceased"].iloc[-1] > 0 and fa["tot_friendship_link"].iloc[-1] != fa["tot_friendship_link"].iloc[0]
+    assert len(a.state_dict()["alive"]) == 400 + int(fa["number_born"].iloc[-1])
     for col in ["criminal_tendency_mean", "criminal_tencency_sd", "age_mean", "age_sd", "education_level_mean",
                 "education_level_sd", "num_crime_committed_mean", "num_crime_committed_sd"]:
         assert np.allclose(fa[col].astype(float)[1:], fb[col].astype(float)[1:], rtol=1e-9, atol=1e-12), col
@@ -233,7 +238,7 @@ def test_ensemble_on_gpu_equals_individual_runs(P, tmp_path):
                  {"initial_agents": 300, "num_ticks": 18, "intervention": "facilitators", "num_oc_persons": 200}]
     args = ensemble.seed_sweep(3, overrides, save_path=str(tmp_path))
     rep = ensemble.run_ensemble(args, ensemble.gpu_batch_runner(0), replicas_per_batch=4)
-    assert rep.shape == (6, 19, 40)   # row 0 = after setup, like the reference's DataCollector (model.py:1042)
+    assert rep.shape == (6, 19, len(P.REPORTER_NAMES))   # row 0 = after setup, like the reference's DataCollector (model.py:1042)
     for i in (0, 4):
         m = P.ProtonOC(seed=args[i]["seed"])
         m.override_dict(args[i]["source_override"])
@@ -302,6 +307,20 @@ def test_whole_run_distribution_vs_reference(P):
     # against the full reference the out-of-scope phases show up as drift; keep it bounded and on record
     drift = abs(mine["number_crimes"][:, -1].mean() - fx["ref_number_crimes"][:, -1].mean()) / fx["ref_number_crimes"][:, -1].mean()
     assert drift < 0.06
+    # with the six step() phases that run on the device switched on, the same check against the FULL reference step
+    with P.CrimeEngine(runs, n + 300, stat + 20000, crim) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_phases(E.PHASE_ALL)
+        for r in range(runs):
+            E.upload_state(r, st)
+            E.set_crime_multiplier(float(fx["crime_multiplier"]), r)
+        rep6 = E.run_ticks(1, ticks, [5000 + r for r in range(runs)])
+    drift6 = abs(rep6[:, -1, 0].mean() - fx["ref_number_crimes"][:, -1].mean()) / fx["ref_number_crimes"][:, -1].mean()
+    assert drift6 < 0.06, (drift, drift6)
+    for col, idx in (("current_oc_members", 7), ("people_jailed", 6)):
+        p = ks_2samp(rep6[:, -1, idx], fx["ref_" + col][:, -1]).pvalue
+        assert p > 0.005, (col, p, rep6[:, -1, idx].mean(), fx["ref_" + col][:, -1].mean())
 
 
 def test_reporter_rows_on_the_device_equal_the_downloaded_rows(P):
