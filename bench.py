@@ -330,8 +330,9 @@ def main():
     class Workload:
         """One batch on one engine: packed pinned states, per-replica parameters and keys."""
 
-        def __init__(self, c, E=None):
+        def __init__(self, c, E=None, phases=0):
             self.c = c
+            self.phases = phases
             ents, self.assign = c["entries"], c["assign"]
             self.R = len(self.assign)
             self.alive = [int(e[0]["alive"].sum()) for e in ents]
@@ -339,7 +340,12 @@ def main():
             states = [e[0] for e in ents]
             head = 160000 if max(len(s["alive"]) for s in states) <= 20000 else 16 * max(len(s["alive"]) for s in states)
             self.cap = pkg.CrimeEngine.capacity_for(states, head)
+            if phases:   # births add agent slots and links on the device
+                self.cap = (self.cap[0] + 3000, self.cap[1] + 100000, self.cap[2])
             self.E = E if E is not None else pkg.CrimeEngine(self.R, *self.cap, device=local)
+            if phases:
+                self.E.set_demography(pkg.make_demography())
+                self.E.set_phases(phases)
             self.packed = [pkg.CrimeEngine.pack_state(s, pinned=True) for s in states]
             self.params = [pkg.make_params(e[1]) for e in ents]
             self.tick0 = ents[0][2]
@@ -511,6 +517,26 @@ def main():
         SW.E.close()
         del SW
 
+    # ---- config 5 with the six step() phases that run on the device switched on (retire_persons, make_baby,
+    # remove_excess_friends / _professional_links, make_friends, make_people_die): births and deaths keep the age
+    # structure and the criminal layer from drifting the way the crime path alone lets them over 480 ticks
+    demog = None
+    if args.config == 5 and not args.no_sweep:
+        DW = Workload(homogeneous_config(R), phases=pkg.CrimeEngine.PHASE_ALL)
+        dms, dval, dl = DW.time_resident(1, max(1, min(args.steps, 2)))
+        cn0, _ = DW.E.counters()
+        dkp, _ = kernel_pass(DW)
+        cn, _ = DW.E.counters()
+        cn = cn - cn0 * (cn0 > 0) * np.isin(np.arange(cn.shape[1]), [0, 16, 17])[None, :]   # cumulative counters: this pass only
+        demog = {"phases": "retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, "
+                           "make_people_die (model.py:274-284) every tick, on the device",
+                 "value": dval, "ms_per_step": dms, "gpu_launches": int(dl), "kernel_ms": dkp["kernel_ms"],
+                 "roofline": dkp["roofline"], "errors": int((cn[:, 9] != 0).sum()),
+                 "born_per_run": float(cn[:, 17].mean()), "deceased_per_run": float(cn[:, 16].mean()),
+                 "crimes_per_run": float(cn[:, 0].mean()), "note": "value counts the agents of the initial state x ticks, like the headline"}
+        DW.E.close()
+        del DW
+
     # ---- single-run latency (batch of one): the "one 10k-agent run" figure
     single = None
     if rank == 0:
@@ -541,6 +567,7 @@ def main():
                        "l2": "L2 flushed between steps; batch state (%.0f MB) %s L2" % (R * 1.8 * n_agents / 1e4, "exceeds" if R * n_agents > 7e5 else "fits")},
             "runs_per_hour": R * world * 3600.0 / (ms / 1e3),
             "sweep": sweep,
+            "with_step_phases": demog,
             "single_run": single,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -229,15 +229,15 @@ __global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
         while (lo < hi) { int m = (lo + hi) >> 1; if (ins_rowid[m] < a) lo = m + 1; else hi = m; }
         rp_new[a] = ((a <= n_old) ? g.u_rowptr[a] : e_old) + ins_before[lo];
     }
-    // ---- rows without new entries move as they are; receiving rows are merged by one warp each
-    for (int a = tid; a < n_old; a += blockDim.x) {
-        int lo = 0, hi = nins;
-        while (lo < hi) { int m = (lo + hi) >> 1; if (ins_rowid[m] < a) lo = m + 1; else hi = m; }
-        if (lo < nins && ins_rowid[lo] == a) continue;
-        const int b = g.u_rowptr[a], e = g.u_rowptr[a + 1], sh = ins_before[lo];
-        for (int i = b; i < e; i++) ent_new[i + sh] = ent_old[i];
-    }
+    // ---- rows without new entries move as they are: the stretch of rows between two receiving rows shifts by one amount,
+    // so it is copied entry-parallel (coalesced); receiving rows are merged by one warp each
     const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    for (int k = 0; k <= nins; k++) {
+        const int ra = (k == 0) ? 0 : ins_rowid[k - 1] + 1, rb = (k < nins) ? min(ins_rowid[k], n_old) : n_old;   // rows [ra, rb)
+        if (ra >= rb || ra >= n_old) continue;
+        const int b = g.u_rowptr[ra], e = g.u_rowptr[rb], sh = ins_before[k];
+        for (int i = b + tid; i < e; i += blockDim.x) ent_new[i + sh] = ent_old[i];
+    }
     for (int k = w; k < nins; k += nw) {
         const int a = ins_rowid[k];
         const int ob = (a < n_old) ? g.u_rowptr[a] : e_old, oe = (a < n_old) ? g.u_rowptr[a + 1] : e_old, nbase = ob + ins_before[k];
@@ -277,7 +277,13 @@ __global__ void __launch_bounds__(1024) k_multiplex_insert(DevCtx C) {
         Graph gn = g;
         gn.u_rowptr = rp_new; gn.u_ent = ent_new;
         gn.u_mid = (upar ? C.u_mid : C.u_mid_tmp) + (size_t)r * C.Ncap;
-        for (int a = tid; a < n_new; a += blockDim.x) gn.u_mid[a] = row_mid(gn, a);   // every row moved
+        // every row moved: a row without new entries keeps its pointer relative to its begin, a receiving row is read again
+        for (int a = tid; a < n_new; a += blockDim.x) {
+            int lo = 0, hi = nins;
+            while (lo < hi) { int m = (lo + hi) >> 1; if (ins_rowid[m] < a) lo = m + 1; else hi = m; }
+            const bool receiving = (lo < nins && ins_rowid[lo] == a) || a >= n_old;
+            gn.u_mid[a] = receiving ? row_mid(gn, a) : rp_new[a] + (g.u_mid[a] - g.u_rowptr[a]);
+        }
         __syncthreads();
         for (int i = tid; i < nu; i += blockDim.x) ent_asym_update(gn, DM_U(pairs[i]), DM_V(pairs[i]));
     }
@@ -559,9 +565,10 @@ __global__ void __launch_bounds__(128) k_remove_excess(DevCtx C, unsigned bit, i
     if (!(xa & F_ALIVE)) return;
     Graph g = graph_of(C, r);
     const int b = g.u_rowptr[a], e = g.u_rowptr[a + 1];
+    const int age = attr_age(xa), limit = dunbar ? 150 - abs(age - 30) : 30;
+    if (e - b <= limit) return;   // not even the whole row is over the limit: nearly every agent leaves here
     int len = 0;
     for (int i = b; i < e; i++) len += (ENT_MASK(g.u_ent[i]) & bit) != 0;
-    const int age = attr_age(xa), limit = dunbar ? 150 - abs(age - 30) : 30;
     if (len <= limit) return;
     int need = len - limit, k = 0;
     const unsigned long long key = C.philox_key[r];

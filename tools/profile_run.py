@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--warm-ticks", type=int, default=0, help="ticks run before the measured ones (state ages)")
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--repeat", type=int, default=1, help="repeat upload+run and report the fastest")
+    ap.add_argument("--phases", type=int, default=0, help="device phases of step() to run every tick (CrimeEngine.PHASE_*, 63 = all six)")
     ap.add_argument("--synthetic", type=int, default=0, help="use a synthetic population of this many agents (config 4) instead of the bench workload")
     args = ap.parse_args()
     import bench
@@ -34,8 +35,13 @@ def main():
     if args.tick0 is not None:
         tick0 = args.tick0
     n, stat, crim = pkg.CrimeEngine.capacity_for([st], 16 * len(st["alive"]))
+    if args.phases:
+        n, stat = n + 3000, stat + 100000
     E = pkg.CrimeEngine(args.replicas, n, stat, crim)
     E.set_params(pkg.make_params(prm))
+    if args.phases:
+        E.set_demography(pkg.make_demography())
+        E.set_phases(args.phases)
     keys = [r * 7919 + 17 for r in range(args.replicas)]
     best = None
     for rep_i in range(args.repeat - 1):
