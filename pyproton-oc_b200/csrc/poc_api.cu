@@ -187,7 +187,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     // one block per accomplice search / embeddedness evaluation: at 10k agents a replica issues about 25 searches
     // and 20-50 evaluations per tick, so 32-64 blocks per replica let every block take at most one or two items
     // (blocks without work exit at once); 6 blocks of 256 threads are resident per SM
-    ctx->gx = (R >= 64) ? 32 : 64;
+    ctx->gx = (R >= 256) ? 16 : (R >= 64) ? 32 : 64;   // search at 1,024 replicas: 16 / 32 / 64 blocks per replica -> 168 / 174 / 197 ms per 480 ticks
     // a small batch of large populations has hundreds of evaluations per replica and tick: enough blocks for every SM
     if (N > 30000 && R * ctx->gx < 2 * 148) ctx->gx = (2 * 148 + R - 1) / R;
     // embeddedness: a chain of dependent gathers per evaluation, so large batches run one evaluation per warp
@@ -198,14 +198,17 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     if (const char *e = getenv("POC_EMB_G")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128 || g == 256 || g == 512 || g == 1024) ctx->emb_g = g; }  // experiments
     if (const char *e = getenv("POC_GX")) ctx->gx = std::max(1, atoi(e));
     ctx->draw_threads = (R > 148) ? 512 : 1024;   // measured at 512 replicas: 256 / 512 / 1024 threads -> 177 / 143 / 213 us
-    ctx->commit_threads = (R > 148) ? 512 : 1024;
+    ctx->commit_threads = (R > 512) ? 256 : (R > 148) ? 512 : 1024;   // 1,024 replicas: 256 / 512 / 1024 threads -> 137 / 147 / 169 ms per 480 ticks
     ctx->search_threads = (R < 8) ? 512 : (R < 256 ? 256 : 128);   // measured us per tick at 1 / 128 / 512 replicas: 128 threads - / 650 / 1723, 256: 175 / 641 / 1753, 512: 173 / 672 / 1916
     if (const char *e = getenv("POC_SEARCH_T")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512) ctx->search_threads = t; }
     ctx->cells_threads = 1024;   // measured: 512 threads is no faster at 512 replicas (59.6 vs 52 us)
     if (const char *e = getenv("POC_CELLS_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->cells_threads = t; }
     if (const char *e = getenv("POC_COMMIT_T")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) ctx->commit_threads = t; }
     if (const char *e = getenv("POC_DRAW_T")) { int t = atoi(e); if (t == 256 || t == 384 || t == 512 || t == 1024) ctx->draw_threads = t; }
-    ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : ctx->gx;
+    // embeddedness at 1,024 replicas: 16 / 32 / 64 / 96 / 128 blocks per replica -> 737 / 648 / 620 / 623 / 635 ms per 480 ticks
+    // (late in a run a replica asks for 40-100 evaluations per launch; a block that gets a second one is the tail)
+    ctx->emb_gx = (ctx->emb_g == 32) ? std::max(1, std::min(16, (148 * 24 + R * 8 - 1) / (R * 8))) : std::max(ctx->gx, 64);
+    if (const char *e = getenv("POC_EMB_GX")) ctx->emb_gx = std::max(1, atoi(e));
     int emb_slots = R * ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1);
     d.scr_slots = std::max(R * ctx->gx, emb_slots);
     size_t wcap = (size_t)(N + 31) / 32;
@@ -247,7 +250,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     DA(ctx->d_demog, 1); d.demog = ctx->d_demog;
     DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
-    DA(d.cdf, RN);
+    DA(d.cdf, RN); DA(d.cdf_valid, R); DA(d.cdf_nz, (size_t)R * POC_MAX_CELLS);
     d.pw_cap = N / 64 + POC_MAX_CELLS + 8;
     DA(d.pw_leaf, (size_t)R * d.pw_cap); DA(d.pw_sum, (size_t)R * d.pw_cap);
     size_t RC = (size_t)R * d.Ccap, RM = (size_t)R * d.Mcap;
@@ -780,6 +783,7 @@ int poc_set_crime_multiplier(poc_ctx *ctx, int replica, double v) {
     if (replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_set_crime_multiplier: bad replica");
     // pageable source: staged before the call returns, no synchronisation needed
     CU(cudaMemcpyAsync(ctx->d.crime_mult + replica, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d.cdf_valid + replica, 0, sizeof(int), ctx->stream));   // the crimes per cell follow the multiplier
     return POC_OK;
 }
 

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(1024) k_make_baby(DevCtx C) {
         __syncthreads();
     }
     const int nb = carry;
-    if (tid == 0) { RP(C.dm_n, r, 4)[0] = nb; RP(C.dm_n, r, 4)[2] = 0; }
+    if (tid == 0) { RP(C.dm_n, r, 4)[0] = nb; RP(C.dm_n, r, 4)[2] = 0; if (nb) C.cdf_valid[r] = 0; }
     if (nb == 0) return;
     if (n + nb > C.Ncap) { if (tid == 0) { atomicExch(&cn[CN_ERROR], 20); RP(C.dm_n, r, 4)[0] = 0; } return; }
     unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);

@@ -110,7 +110,9 @@ struct DevCtx {
     int2 *pw_leaf; double *pw_sum; int pw_cap;   // [R][pw_cap] pieces of the pairwise sums in k_tendency_eps
     int32_t *cell_off;              // [R][POC_MAX_CELLS+1]
     int32_t *cell_strict;           // [R][POC_MAX_CELLS] counts with age_from < age (Q8)
-    double *cdf;                    // [R][Ncap]
+    double *cdf;                    // [R][Ncap] the tick's per-cell CDFs in cell_members order; kept from tick to tick:
+    int *cdf_valid, *cdf_nz;        // [R], [R][POC_MAX_CELLS] k_draw builds them again only when a tendency, a cell's member
+                                    // list or the crime multiplier changed since (k_cells, k_tendency_pre, uploads clear the flag)
     // crimes of the tick
     int32_t *n_crimes;              // [R]
     int32_t *crime_init, *crime_k, *crime_flags;  // [R][Ccap]; flags bit0 = started by OC member

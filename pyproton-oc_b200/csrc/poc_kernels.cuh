@@ -21,7 +21,7 @@ struct StageCols {
 
 __global__ void k_pack_agents(DevCtx C, int r, int n, StageCols S, int *err) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a == 0) { C.n_agents[r] = n; C.u_par[r] = 0; }   // an upload lands in the first multiplex buffer
+    if (a == 0) { C.n_agents[r] = n; C.u_par[r] = 0; C.cdf_valid[r] = 0; }   // an upload lands in the first multiplex buffer
     if (a >= n) return;
     int age = S.age[a], job = S.job_level[a], edu = S.education_level[a], w = S.wealth_level[a];
     if (age < 0 || job < 0 || job > 15 || edu < 0 || edu > 15 || w < 0 || w > 15) atomicExch(err, 1);
@@ -303,7 +303,9 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
         for (int k = 0; k < nc; k++) { base[k] = s; s += tot[k]; }
         base[nc] = s;
         int32_t *co = RP(C.cell_off, r, POC_MAX_CELLS + 1);
-        for (int k = 0; k <= nc; k++) co[k] = base[k];
+        bool moved = false;
+        for (int k = 0; k <= nc; k++) { moved |= co[k] != base[k]; co[k] = base[k]; }
+        if (moved || yearly) C.cdf_valid[r] = 0;   // k_draw keeps its CDFs while cells, tendencies and multiplier stay as they are
         for (int k = 0; k < nc; k++) RP(C.cell_strict, r, POC_MAX_CELLS)[k] = tot[k] + adj[k];
         RP(C.counters, r, CN_COUNT)[CN_N_ALIVE] = s_alive;
         if (yearly) {  // model.py:1150-1157, left-to-right float64
@@ -314,13 +316,16 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
     }
     __syncthreads();
     int32_t *members = RP(C.cell_members, r, C.Ncap);
+    bool changed = false;
     for (int a = a_begin; a < a_end; a++) {
         uint32_t x = attr[a];
         if (!(x & F_ALIVE)) continue;
         int c = lut[((x & F_MALE) ? 256 : 0) | attr_age(x)];
         if (c == 255) continue;
-        members[base[c] + cnt_tab[c * NT + tid]++] = a;
+        const int pos = base[c] + cnt_tab[c * NT + tid]++;
+        if (members[pos] != a) { members[pos] = a; changed = true; }
     }
+    if (__syncthreads_or(changed) && tid == 0) C.cdf_valid[r] = 0;
 }
 
 // ============================================================================ A1 criminal tendency
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(1024) k_cells(DevCtx C, int mode, int begin) {
 __global__ void __launch_bounds__(256) k_tendency_pre(DevCtx C, int mode) {
     int r = C.r0 + blockIdx.y, sub = threadIdx.x & 7;
     if (mode == 2 && !is_yearly(C, C.params[r])) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) C.cdf_valid[r] = 0;   // the crime draw's CDFs are built from the tendencies
     const poc_params &P = C.params[r];
     Graph g = graph_of(C, r);
     const int32_t *ncr = RP(C.ncrimes, r, C.Ncap);
@@ -561,12 +567,18 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles, int a
     }
     __syncthreads();
     int total = off[nc], ptotal = poff[nc];
+    // The CDFs depend on the tendencies (yearly), the cells' member lists (birthdays, deaths) and, through the crimes per
+    // cell, the multiplier (yearly): on most ticks nothing of that moved and last tick's CDFs, kept in the global cdf array,
+    // are the ones this tick would build (the same inputs through the same chains): the draws read them there.
+    const bool cached = C.cdf_valid[r] != 0;
+    if (cached && tid < nc) nz[tid] = RP(C.cdf_nz, r, POC_MAX_CELLS)[tid];
     // allow_fit = 0: the launch reserved the chain windows only (populations too large for the whole-cell layout), not the
     // cell-of-eight bytes behind the weights, whatever this replica's own alive count happens to be
     const bool fit = allow_fit && ptotal <= smem_doubles;
     unsigned char *cellof8 = (unsigned char *)(wt_sm + smem_doubles);   // cell of every block of eight positions
-    const int *woff = fit ? poff : off;
-    double *wt = fit ? wt_sm : cdf;
+    const int *woff = (fit && !cached) ? poff : off;
+    double *wt = (fit && !cached) ? wt_sm : cdf;
+    if (!cached) {
     if (fit) {
         for (int k = w; k < nc; k += nw)
             for (int q = (poff[k] >> 3) + lane; q < (poff[k + 1] >> 3); q += 32) cellof8[q] = (unsigned char)k;
@@ -763,6 +775,16 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles, int a
             for (int i = off[k] + tid; i < off[k + 1]; i += blockDim.x) cdf[i] = cdf[i] / l;
         }
     }
+    __syncthreads();
+    // keep what was built for the ticks to come (cell_members order, without the padding of the shared-memory layout)
+    if (fit)
+        for (int q = tid; q < ptotal; q += blockDim.x) {
+            const int k = cellof8[q >> 3], i = q - poff[k];
+            if (i < off[k + 1] - off[k]) cdf[off[k] + i] = wt_sm[q];
+        }
+    if (tid < nc) RP(C.cdf_nz, r, POC_MAX_CELLS)[tid] = nz[tid];
+    if (tid == 0) C.cdf_valid[r] = 1;
+    }   // !cached
     __syncthreads();
     // the draws
     int ncrimes = coff[nc];
