@@ -1162,18 +1162,22 @@ __global__ void __launch_bounds__(1024) k_commit(DevCtx C) {
     const int *q_start = (nins <= 1024) ? sm_start : ins_start, *q_row = (nins <= 1024) ? sm_row : ins_rowid;
     const int *q_before = (nins <= 1024) ? sm_before : ins_before;
     // ---- new row pointers: a row moves right by the number of new links in the receiving rows before it
-    for (int a = tid; a <= n; a += blockDim.x) {
-        int lo = 0, hi = nins;   // receiving rows with id < a
-        while (lo < hi) { int m = (lo + hi) >> 1; if (q_row[m] < a) lo = m + 1; else hi = m; }
-        rp_new[a] = g.c_rowptr[a] + q_before[lo];
+    {   // (a thread's rows ascend: the number of receiving rows before them only grows, so it is carried along instead of
+        //  searched for every row -- the search was a third of this kernel, profiles/r03b_commit_*)
+        int lo = 0;   // receiving rows with id < a
+        for (int a = tid; a <= n; a += blockDim.x) {
+            while (lo < nins && q_row[lo] < a) lo++;
+            rp_new[a] = g.c_rowptr[a] + q_before[lo];
+        }
     }
     // ---- entries of rows without pairs move as they are: one thread per old entry
-#pragma unroll 4
-    for (int e = tid; e < e_old; e += blockDim.x) {
-        int lo = 0, hi = nins;   // receiving rows whose first old entry is <= e
-        while (lo < hi) { int m = (lo + hi) >> 1; if (q_start[m] <= e) lo = m + 1; else hi = m; }
-        if (lo > 0 && e < g.c_rowptr[q_row[lo - 1] + 1]) continue;     // inside a receiving row: merged below
-        ent_new[e + q_before[lo]] = g.c_ent[e];
+    {
+        int lo = 0;   // receiving rows whose first old entry is <= e (carried along like above)
+        for (int e = tid; e < e_old; e += blockDim.x) {
+            while (lo < nins && q_start[lo] <= e) lo++;
+            if (lo > 0 && e < g.c_rowptr[q_row[lo - 1] + 1]) continue;     // inside a receiving row: merged below
+            ent_new[e + q_before[lo]] = g.c_ent[e];
+        }
     }
     // ---- receiving rows: one warp per row.  An old entry moves right by the new links of this row that sort
     // before it (and takes the new count if a pair names it); a new link goes behind the old entries that sort
