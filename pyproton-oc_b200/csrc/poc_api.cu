@@ -259,6 +259,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     DA(d.cr_acc, RC * POC_MAX_GROUP); DA(d.search_list, RC); DA(d.n_search, R);
     DA(d.emb_list, 2 * RN); DA(d.n_emb, 2 * R); DA(d.emb_stamp, RN); DA(d.emb_val, RN);
     d.big_cap = std::min(N, 4096);
+    d.emb_flags = 0;
+    if (const char *e = getenv("POC_EMB_FLAGS")) d.emb_flags = atoi(e);
     DA(d.emb_big, (size_t)R * d.big_cap); DA(d.n_emb_big, R);
     DA(d.group_off, (size_t)R * (d.Ccap + 1)); DA(d.group_mem, RM);
     DA(d.pairs, (size_t)R * d.Pcap); DA(d.pair_cnt, (size_t)R * d.Pcap); DA(d.n_pairs, R);

@@ -124,6 +124,7 @@ struct DevCtx {
     int32_t *n_emb;                 // [2][R]
     int32_t *emb_big, *n_emb_big;   // [R][big_cap], [R] evaluations the small blocks hand to the large-block launch (poc_embed3.cuh)
     int big_cap;
+    int emb_flags;                  // A/B switches of poc_embed3.cuh (POC_EMB_FLAGS): 1 = criminal entries from both rows
     int32_t *emb_stamp;             // [R][Ncap]
     double *emb_val;                // [R][Ncap]
     // groups of the tick, canonical

@@ -311,13 +311,14 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                 const int e_ = (REV) ? (FROM) + (TO) - 1 - t_ : t_;                                                    \
                 const unsigned pk_ = (e_ < ecap_w) ? lds_u32(a_sedge + 4u * e_) : gedge[e_ - ecap_w];                  \
                 const unsigned ru_ = pk_ & RMASK, rv_ = (pk_ >> RB) & RMASK;                                           \
-                const unsigned wg_ = pk_ >> (2 * RB);                                                                  \
-                if (wg_ == 254u) continue;   /* second slot of the entry before it */                                  \
+                unsigned wg_ = pk_ >> (2 * RB);                                                                        \
                 double wt_;                                                                                            \
-                if (wg_ == 255u) {                                                                                     \
-                    const unsigned nx_ = (e_ + 1 < ecap_w) ? lds_u32(a_sedge + 4u * (e_ + 1)) : gedge[e_ + 1 - ecap_w]; \
-                    wt_ = 1.0 / (double)(nx_ & 0xffffffu);                                                             \
-                } else wt_ = (wg_ < 128u) ? lds_f64(a_invw + 8u * wg_) : 1.0 / (double)wg_;                            \
+                if (wg_ < 128u) wt_ = lds_f64(a_invw + 8u * wg_);   /* nearly every entry */                           \
+                else {                                                                                                 \
+                    if (wg_ == 254u) continue;   /* second slot of the entry before it */                              \
+                    if (wg_ == 255u) wg_ = ((e_ + 1 < ecap_w) ? lds_u32(a_sedge + 4u * (e_ + 1)) : gedge[e_ + 1 - ecap_w]) & 0xffffffu; \
+                    wt_ = 1.0 / (double)wg_;                                                                           \
+                }                                                                                                      \
                 const double du_ = lds_f64(a_dist + 8u * ru_), dv_ = lds_f64(a_dist + 8u * rv_);                       \
                 const double nv_ = du_ + wt_, nu_ = dv_ + wt_;                                                         \
                 if (nv_ < dv_) { smin_f64(a_dist + 8u * rv_, nv_); CHG = true; }                                       \
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
                                         const int v = ce.x, wgt = CE_CNT(ce.y) + __popc(CE_SMASK(ce.y));
                                         const uint2 bw = lds_u2(a_bp + 8u * (v >> 5));
                                         // once per pair like the multiplex entries: from the lower slot's row unless flagged
-                                        if (wgt > 0 && (v > rt.y || (ce.y & CE_ASYM)) && ((bw.x >> (v & 31)) & 1u)) {   // 0: the reference divides by zero here
+                                        if (wgt > 0 && (v > rt.y || (ce.y & CE_ASYM) || (C.emb_flags & 1)) && ((bw.x >> (v & 31)) & 1u)) {   // 0: the reference divides by zero here
                                             ok = true; tru = rt.z; wi = wgt;
                                             rv = (int)bw.y + __popc(bw.x & ((1u << (v & 31)) - 1u));
                                             if (wgt > 0xffffff) { S->over = 1; ok = false; }
