@@ -211,6 +211,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     if (const char *e = getenv("POC_EMB_GX")) ctx->emb_gx = std::max(1, atoi(e));
     int emb_slots = R * ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1);
     d.scr_slots = std::max(R * ctx->gx, emb_slots);
+    d.slot_stride = std::max(ctx->gx, ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1));
     size_t wcap = (size_t)(N + 31) / 32;
     ctx->smem_search = 2 * wcap * sizeof(unsigned);
     ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
@@ -799,17 +800,17 @@ static void launch_emb(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int parity
                 // register budget by residency: 32 at 16 blocks per SM, 36 at 14, 40 at 12 (POC_EMB_REGS picks one for A/B runs)
                 int rb = mb >= 16 ? 16 : 12;
                 if (const char *e = getenv("POC_EMB_REGS")) rb = atoi(e);
-                if (rb >= 16) k_emb3<128, 16><<<grid, 128, sm, s>>>(D, parity, sm, 0, ctx->emb_gx);
-                else if (rb >= 14) k_emb3<128, 14><<<grid, 128, sm, s>>>(D, parity, sm, 0, ctx->emb_gx);
-                else k_emb3<128, 12><<<grid, 128, sm, s>>>(D, parity, sm, 0, ctx->emb_gx);
+                if (rb >= 16) k_emb3<128, 16><<<grid, 128, sm, s>>>(D, parity, sm, 0);
+                else if (rb >= 14) k_emb3<128, 14><<<grid, 128, sm, s>>>(D, parity, sm, 0);
+                else k_emb3<128, 12><<<grid, 128, sm, s>>>(D, parity, sm, 0);
             }
-            else if (mb >= 8) k_emb3<256, 8><<<grid, 256, sm, s>>>(D, parity, sm, 0, ctx->emb_gx);
-            else k_emb3<256, 6><<<grid, 256, sm, s>>>(D, parity, sm, 0, ctx->emb_gx);
+            else if (mb >= 8) k_emb3<256, 8><<<grid, 256, sm, s>>>(D, parity, sm, 0);
+            else k_emb3<256, 6><<<grid, 256, sm, s>>>(D, parity, sm, 0);
             ctx->launches++;
-            k_emb3<1024, 2><<<dim3(std::min(4, ctx->emb_gx), D.Rg), 1024, (int)ctx->smem_emb_big, s>>>(D, parity, (int)ctx->smem_emb_big, 1, ctx->emb_gx);
+            k_emb3<1024, 2><<<dim3(std::min(4, ctx->emb_gx), D.Rg), 1024, (int)ctx->smem_emb_big, s>>>(D, parity, (int)ctx->smem_emb_big, 1);
         }
-        else if (ctx->emb_g == 512) k_emb3<512, 4><<<grid, 512, sm, s>>>(D, parity, sm, 2, ctx->emb_gx);
-        else k_emb3<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm, 2, ctx->emb_gx);
+        else if (ctx->emb_g == 512) k_emb3<512, 4><<<grid, 512, sm, s>>>(D, parity, sm, 2);
+        else k_emb3<1024, 2><<<grid, 1024, sm, s>>>(D, parity, sm, 2);
         return;
     }
     if (ctx->emb_v == 2) {

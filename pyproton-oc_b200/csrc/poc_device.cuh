@@ -156,6 +156,8 @@ struct DevCtx {
     unsigned long long *dm_defer;   // [R][1024] friendships whose reverse entry has no slot yet
     int DPcap;
     int scr_slots;
+    int slot_stride;                // scratch slot of block bx of replica r = r * slot_stride + bx in EVERY traversal kernel: the
+                                    // replica groups run concurrently on their own streams and must not meet in a slot
     double *reporters;              // [R][Tcap][POC_N_REPORTERS]
     int Tcap;
 };

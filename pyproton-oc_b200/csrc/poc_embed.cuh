@@ -142,7 +142,7 @@ __global__ void __launch_bounds__((G == 32) ? 256 : G, (G == 32) ? 4 : (G == 102
     EmbShared *S = (EmbShared *)(gbase + (size_t)DCAP * 8);
     unsigned *bitmap = (unsigned *)((unsigned char *)S + ((sizeof(EmbShared) + 7) & ~(size_t)7));
     int *wprefix = (int *)((unsigned char *)bitmap + (((size_t)wcap * 4 + 7) & ~(size_t)7));
-    int slot = (r * gridDim.x + blockIdx.x) * GPB + gid;
+    int slot = r * C.slot_stride + blockIdx.x * GPB + gid;   // (poc_device.cuh: one stride for every traversal kernel)
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     unsigned long long *gdist = C.scr_dist + (size_t)slot * (C.Ncap + 1);
     unsigned *edgebuf = C.scr_edges + (size_t)slot * C.ecap;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(G, MB) k_emb2(DevCtx C, int parity, int smem_b
     int off_dyn = L::OFF_BP + ((wcap * 8 + 15) & ~15);
     OPAQUE(off_dyn);
     const int dyn_bytes = smem_bytes - off_dyn;
-    const int slot = r * gridDim.x + blockIdx.x;
+    const int slot = r * C.slot_stride + blockIdx.x;   // (poc_device.cuh: one stride for every traversal kernel)
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     const poc_params &P = C.params[r];
     Graph g = graph_of(C, r);

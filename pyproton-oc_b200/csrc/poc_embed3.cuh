@@ -62,7 +62,7 @@ static inline size_t emb3_fixed_bytes(int G, int Ncap) {
     }
 
 template <int G, int MB>
-__global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_bytes, int mode, int slot_stride) {
+__global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_bytes, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef Emb3Layout<G> L;
     constexpr int NW = L::NW;
@@ -88,9 +88,7 @@ __global__ void __launch_bounds__(G, MB) k_emb3(DevCtx C, int parity, int smem_b
     int off_dyn = L::OFF_BP + ((wcap * 8 + 15) & ~15);
     OPAQUE(off_dyn);
     const int dyn_bytes = smem_bytes - off_dyn;
-    // scratch slot: the stride of the request launch also for the large-block launch (fewer blocks per replica), so that the
-    // launches of other replica groups, which run concurrently on their own streams, never share a slot with it
-    const int slot = r * slot_stride + blockIdx.x;
+    const int slot = r * C.slot_stride + blockIdx.x;   // (poc_device.cuh: one stride for every traversal kernel)
     int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
     const poc_params &P = C.params[r];
     Graph g = graph_of(C, r);

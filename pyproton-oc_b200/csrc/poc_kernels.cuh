@@ -986,9 +986,10 @@ __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     int r = C.r0 + blockIdx.y;
     int wcap = (C.Ncap + 31) >> 5;
     unsigned *bitmap = smem_u, *fbits = smem_u + wcap;
-    int slot = r * gridDim.x + blockIdx.x;
-    int *list = C.scr_list + (size_t)slot * (C.Ncap + 1);
-    double *keys = C.scr_key + (size_t)slot * (C.Ncap + 1);
+    // the BFS list shares its slots with the embeddedness kernels of the other replica groups (one stride for all,
+    // poc_device.cuh); the keys are this kernel's alone
+    int *list = C.scr_list + (size_t)(r * C.slot_stride + blockIdx.x) * (C.Ncap + 1);
+    double *keys = C.scr_key + (size_t)(r * gridDim.x + blockIdx.x) * (C.Ncap + 1);
     unsigned long long edges = 0, abytes = 0, ncand = 0, ncrimes = 0;
     // the next round's request list must start empty; nobody appends to it during this launch
     if (blockIdx.x == 0 && threadIdx.x == 0) { C.n_emb[(parity ^ 1) * C.R + r] = 0; C.n_emb_big[r] = 0; }
