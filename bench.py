@@ -412,7 +412,7 @@ def main():
                         host_all[w_].copy_(gathered[w_], non_blocking=True)
                     torch.cuda.synchronize()
                     rep_bytes = host_all.numel() * 8
-            cols = [E.download_agents(r, out=host_cols[r]) for r in range(Rw)]
+            cols = E.download_agents_many(0, host_cols)   # every replica's agent columns, one call (copies pipelined)
             E.sync()
             dt = time.perf_counter() - t0
             d2h = rep_bytes + sum(sum(v.nbytes for v in c.values()) for c in cols)
@@ -425,8 +425,7 @@ def main():
             t0 = time.perf_counter(); W.upload_all(); E.sync()
             t1 = time.perf_counter(); E.run_ticks(W.tick0, T, W.keys, reporters=True, out=host_rep)
             t2 = time.perf_counter()
-            for r in range(Rw):
-                E.download_agents(r, out=host_cols[r])
+            E.download_agents_many(0, host_cols)
             E.sync()
             t3 = time.perf_counter()
             breakdown = {"upload": 1e3 * (t1 - t0), "run_and_reporter_rows": 1e3 * (t2 - t1), "agent_columns": 1e3 * (t3 - t2)}

@@ -166,6 +166,10 @@ int poc_build_graph(poc_ctx *ctx, int replica);
  * buffers must stay valid until poc_sync(), which also reports invalid input found by the deferred checks. */
 int poc_build_graph_async(poc_ctx *ctx, int replica);
 int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *cols);
+/* the same for `count` consecutive replicas in one call (cols[i] receives replica replica0 + i): the unpack kernel and the
+ * device-to-host copy of the next replicas run while the columns of the one before are handed out -- what an ensemble
+ * driver calls after a run (run_modes.py:73-88 collects every run's outputs) */
+int poc_download_agents_many(poc_ctx *ctx, int replica0, int count, const poc_agent_cols *cols);
 int poc_layer_entries(poc_ctx *ctx, int replica, int layer, int64_t *out);
 int poc_download_layer(poc_ctx *ctx, int replica, int layer, int32_t *rowptr, int32_t *col, int32_t *co_off_or_null);
 

@@ -104,6 +104,7 @@ SYMBOLS = {
     "poc_build_graph": (C.c_int, [_P, C.c_int]),
     "poc_build_graph_async": (C.c_int, [_P, C.c_int]),
     "poc_download_agents": (C.c_int, [_P, C.c_int, C.POINTER(AgentCols)]),
+    "poc_download_agents_many": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "poc_layer_entries": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "poc_download_layer": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "poc_begin_tick": (C.c_int, [_P, C.c_int]),

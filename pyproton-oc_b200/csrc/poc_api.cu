@@ -42,6 +42,8 @@ struct poc_ctx {
     uint8_t *stage_dev = nullptr, *stage_host = nullptr;   // one block for all staging columns + its pinned mirror
     uint8_t *stage_host2[2] = {nullptr, nullptr};          // upload mirrors, used alternately
     cudaEvent_t stage_ev2[2] = {nullptr, nullptr}; bool stage_busy2[2] = {false, false}; int stage_next = 0;
+    uint8_t *many_dev[4] = {}, *many_host[4] = {};         // poc_download_agents_many: four staging blocks in flight
+    cudaEvent_t many_ev[4] = {};
     size_t stage_bytes = 0, stage_off[24] = {};
     int cells_threads = 1024;       // k_cells block size (its count table is n_cells x threads ints of shared memory)
     int search_threads = 256;       // k_search block size (one block per crime)
@@ -213,7 +215,11 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     d.scr_slots = std::max(R * ctx->gx, emb_slots);
     d.slot_stride = std::max(ctx->gx, ctx->emb_gx * (ctx->emb_g == 32 ? 8 : 1));
     size_t wcap = (size_t)(N + 31) / 32;
-    ctx->smem_search = 2 * wcap * sizeof(unsigned);
+    {   // bitmaps (+ the staged ring when that A/B switch is on: poc_kernels.cuh search_crime)
+        const char *e = getenv("POC_EMB_FLAGS");
+        const bool stage_ring = e && (atoi(e) & 2);
+        ctx->smem_search = ((2 * wcap + 1) & ~(size_t)1) * sizeof(unsigned) + (stage_ring ? SEARCH_SCAND * (sizeof(double) + sizeof(int)) : 0);
+    }
     ctx->smem_emb = emb_smem_bytes(ctx->emb_g, N);
     if (ctx->smem_emb + 2 * 1024 > 220 * 1024) return fail(nullptr, POC_ERR_CAPACITY, "max_agents too large for the shared-memory bitmaps");
     if (const char *e = getenv("POC_EMB_V")) { int v = atoi(e); if (v >= 1 && v <= 3) ctx->emb_v = v; }
@@ -357,6 +363,7 @@ int poc_ctx_destroy(poc_ctx *ctx) {
     for (void *p : ctx->allocs) cudaFree(p);
     for (int b = 0; b < 2; b++) if (ctx->blob_ev[b]) cudaEventDestroy(ctx->blob_ev[b]);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+    for (int b = 0; b < 4; b++) { if (ctx->many_host[b]) cudaFreeHost(ctx->many_host[b]); if (ctx->many_ev[b]) cudaEventDestroy(ctx->many_ev[b]); }
     for (int b = 0; b < 2; b++) { if (ctx->stage_host2[b]) cudaFreeHost(ctx->stage_host2[b]); if (ctx->stage_ev2[b]) cudaEventDestroy(ctx->stage_ev2[b]); }
     // (a ctx whose creation failed half-way comes through here too: every handle may still be null)
     for (auto &evx : ctx->ev) if (evx) cudaEventDestroy(evx);
@@ -650,6 +657,44 @@ int poc_download_agents(poc_ctx *ctx, int replica, poc_agent_cols *c) {
         POC_STAGE_COLS(DN)
 #undef DN
     }
+    return POC_OK;
+}
+
+int poc_download_agents_many(poc_ctx *ctx, int replica0, int count, const poc_agent_cols *cols) {
+    CHECK_CTX();
+    if (!cols || replica0 < 0 || count < 0 || replica0 + count > ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_download_agents_many: bad argument");
+    const int K = 4;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->many_dev[0])
+        for (int b = 0; b < K; b++) {
+            DA(ctx->many_dev[b], ctx->stage_bytes);
+            if (cudaHostAlloc((void **)&ctx->many_host[b], ctx->stage_bytes, cudaHostAllocDefault) != cudaSuccess) return fail(ctx, POC_ERR_CUDA, "cudaHostAlloc failed");
+            CU(cudaEventCreateWithFlags(&ctx->many_ev[b], cudaEventDisableTiming));
+        }
+    auto hand_out = [&](int i) -> int {   // replica replica0 + i has arrived in its pinned block
+        const int b = i % K, n = ctx->h_nagents[replica0 + i];
+        CU(cudaEventSynchronize(ctx->many_ev[b]));
+        const poc_agent_cols *c = &cols[i];
+        size_t k = 0;
+#define DN(f, T) { if (c->f && n) memcpy(c->f, ctx->many_host[b] + ctx->stage_off[k], sizeof(T) * (size_t)n); k++; }
+        POC_STAGE_COLS(DN)
+#undef DN
+        return POC_OK;
+    };
+    for (int i = 0; i < count; i++) {
+        const int b = i % K, n = ctx->h_nagents[replica0 + i];
+        if (i >= K) { int rc = hand_out(i - K); if (rc) return rc; }
+        StageCols s;
+        size_t k = 0;
+#define PT(f, T) s.f = (T *)(ctx->many_dev[b] + ctx->stage_off[k++]);
+        POC_STAGE_COLS(PT)
+#undef PT
+        if (n) k_unpack_agents<<<(n + 255) / 256, 256, 0, st>>>(ctx->d, replica0 + i, n, s);
+        CU(cudaMemcpyAsync(ctx->many_host[b], ctx->many_dev[b], ctx->stage_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->many_ev[b], st));
+    }
+    CU(cudaGetLastError());
+    for (int i = std::max(0, count - K); i < count; i++) { int rc = hand_out(i); if (rc) return rc; }
     return POC_OK;
 }
 

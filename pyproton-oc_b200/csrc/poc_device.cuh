@@ -124,7 +124,8 @@ struct DevCtx {
     int32_t *n_emb;                 // [2][R]
     int32_t *emb_big, *n_emb_big;   // [R][big_cap], [R] evaluations the small blocks hand to the large-block launch (poc_embed3.cuh)
     int big_cap;
-    int emb_flags;                  // A/B switches of poc_embed3.cuh (POC_EMB_FLAGS): 1 = criminal entries from both rows
+    int emb_flags;                  // A/B switches (POC_EMB_FLAGS): 1 = poc_embed3.cuh takes criminal entries from both rows,
+                                    // 2 = k_search stages the ring in shared memory
     int32_t *emb_stamp;             // [R][Ncap]
     double *emb_val;                // [R][Ncap]
     // groups of the tick, canonical

@@ -832,9 +832,10 @@ __global__ void __launch_bounds__(1024) k_draw(DevCtx C, int smem_doubles, int a
 struct ArgBest { double key; int slot; int idx; };
 __device__ __forceinline__ bool better(double k1, int s1, double k2, int s2) { return (k1 < k2) || (k1 == k2 && s1 < s2); }
 
+#define SEARCH_SCAND 512   /* ring members staged in shared memory for scoring and selection (larger rings stay in scratch) */
 __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch, int parity, unsigned *bitmap,
-                             unsigned *fbits, int *list, double *keys, unsigned long long &edges, unsigned long long &abytes,
-                             unsigned long long &ncand) {
+                             unsigned *fbits, int *list, double *keys, int *s_slot, double *s_key,
+                             unsigned long long &edges, unsigned long long &abytes, unsigned long long &ncand) {
     __shared__ int s_count, lvl_off[MAX_RADIUS + 3];
     __shared__ int s_st[6];  // nacc, target, mrem, facneeded, pickidx, stop
     __shared__ double wkey[32];
@@ -881,9 +882,20 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
             return;
         }
         awaiting = false;
+        // the ring -- the adjacency this search works on -- can be staged in shared memory (north-star (b)): slots and keys
+        // are read once per pick by the whole block; a ring over SEARCH_SCAND members stays in the block's scratch.
+        // Measured at 1,024 replicas: 178 ms per 480 ticks with the staging against 168 without (the ring is read a handful
+        // of times and was L1-resident already; the copy, its barrier and the smaller L1 cost more): off unless POC_EMB_FLAGS & 2
+        const bool staged = (C.emb_flags & 2) && m <= SEARCH_SCAND;
+        int *cl = staged ? s_slot : list + rb;
+        double *ck = staged ? s_key : keys;
+        if (staged) {
+            for (int i = tid; i < m; i += blockDim.x) s_slot[i] = list[rb + i];
+            __syncthreads();
+        }
         // candidate keys: warp per candidate
         for (int i = w; i < m; i += nw) {
-            int cand = list[rb + i];
+            int cand = cl[i];
             uint32_t ca = attr[cand];
             bool shared = warp_friend_intersect(g, cand, fbits);
             if (lane == 0) {
@@ -891,7 +903,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
                 ncand++;
                 double prox = social_proximity(self_attr, ca, shared);
                 double key = is_oc ? -1.0 * ((prox * embv[cand]) * tend[cand]) : prox * tend[cand];
-                keys[i] = key;
+                ck[i] = key;
             }
         }
         if (tid == 0) s_st[2] = m;
@@ -901,7 +913,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
             int mrem = s_st[2];
             double bk = INFINITY; int bs = 0x7fffffff, bi = -1;
             for (int i = tid; i < mrem; i += blockDim.x) {
-                double k = keys[i]; int s = list[rb + i];
+                double k = ck[i]; int s = cl[i];
                 if (bi < 0 || better(k, s, bk, bs)) { bk = k; bs = s; bi = i; }
             }
             for (int of = 16; of > 0; of >>= 1) {
@@ -918,7 +930,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
                 else {
                     acc[na] = bs; s_st[0] = na + 1;
                     if (attr[bs] & F_FAC) { s_st[1] += 1; s_st[3] = 0; }  // Q6
-                    list[rb + bi] = list[rb + mrem - 1]; keys[bi] = keys[mrem - 1]; s_st[2] = mrem - 1;
+                    cl[bi] = cl[mrem - 1]; ck[bi] = ck[mrem - 1]; s_st[2] = mrem - 1;
                 }
             }
             __syncthreads();
@@ -986,6 +998,8 @@ __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     int r = C.r0 + blockIdx.y;
     int wcap = (C.Ncap + 31) >> 5;
     unsigned *bitmap = smem_u, *fbits = smem_u + wcap;
+    double *s_key = (double *)(smem_u + ((2 * wcap + 1) & ~1));   // 8-byte aligned behind the two bitmaps
+    int *s_slot = (int *)(s_key + SEARCH_SCAND);
     // the BFS list shares its slots with the embeddedness kernels of the other replica groups (one stride for all,
     // poc_device.cuh); the keys are this kernel's alone
     int *list = C.scr_list + (size_t)(r * C.slot_stride + blockIdx.x) * (C.Ncap + 1);
@@ -997,7 +1011,7 @@ __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     for (int item = blockIdx.x; item < ns; item += gridDim.x) {
         int c = RP(C.search_list, r, C.Ccap)[item];
         if (C.cr_state[(size_t)r * C.Ccap + c] & 4) continue;
-        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, edges, abytes, ncand);
+        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, s_slot, s_key, edges, abytes, ncand);
         if (threadIdx.x == 0) { ncrimes++; abytes += 8ull + 4ull * POC_MAX_GROUP; }  // friends row pointer + group out
         __syncthreads();
     }

@@ -186,6 +186,20 @@ class CrimeEngine:
         self._ck(self.L.poc_download_agents(self.h, replica, C.byref(cols)))
         return out
 
+    def download_agents_many(self, replica0: int, outs: Sequence[Dict[str, np.ndarray]]) -> Sequence[Dict[str, np.ndarray]]:
+        """Agent columns of the replicas replica0 .. replica0 + len(outs) - 1 into the given buffers (agent_buffers()) with
+        one call: the copies of the next replicas run while the columns of the one before are handed out."""
+        arr = (AgentCols * len(outs))()
+        for i, out in enumerate(outs):
+            n = self.n_agents[replica0 + i]
+            for f, key in STATE_KEYS.items():
+                a = out[key]
+                if a.dtype != _DTYPES[f] or len(a) < n or not a.flags.c_contiguous:
+                    raise ValueError("download_agents_many: out[%r] must be a contiguous %s array of at least %d" % (key, _DTYPES[f], n))
+                setattr(arr[i], f, a.ctypes.data)
+        self._ck(self.L.poc_download_agents_many(self.h, int(replica0), len(outs), C.byref(arr)))
+        return outs
+
     @staticmethod
     def agent_buffers(n: int) -> Dict[str, np.ndarray]:
         return {key: np.zeros(n, dtype=_DTYPES[f]) for f, key in STATE_KEYS.items()}

@@ -300,7 +300,8 @@ def test_batched_replicas_equal_single_runs(P):
 
 @pytest.mark.parametrize("env", [{"POC_EMB_G": "128"}, {"POC_EMB_G": "256"}, {"POC_EMB_G": "512"}, {"POC_EMB_G": "1024"},
                                  {"POC_DRAW_T": "256"}, {"POC_DRAW_T": "1024"}, {"POC_SEARCH_T": "128"}, {"POC_SEARCH_T": "512"},
-                                 {"POC_COMMIT_T": "256"}, {"POC_GROUPS": "2"}, {"POC_GRAPH": "0"}],
+                                 {"POC_COMMIT_T": "256"}, {"POC_GROUPS": "2"}, {"POC_GRAPH": "0"}, {"POC_EMB_FLAGS": "1"},
+                                 {"POC_EMB_FLAGS": "2"}, {"POC_EMB_V": "2"}, {"POC_EMB_GX": "8", "POC_GX": "4"}],
                          ids=lambda e: "-".join("%s%s" % kv for kv in e.items()))
 def test_kernel_shapes_do_not_change_results(P, O, env, monkeypatch):
     """The launch-shape knobs the library picks by batch size (threads per embeddedness evaluation, k_draw block

@@ -121,3 +121,29 @@ def test_draw_window_mode_mixed_sizes_and_mostly_dead(P):
             assert np.array_equal(got[r][k], oc[k]), (r, k)
         rp, col, co = S.layer(6)
         assert np.array_equal(got[r]["col_6"], col) and np.array_equal(got[r]["co_off"], co), r
+
+
+def test_download_agents_many_equals_per_replica_downloads(P):
+    """poc_download_agents_many (four staging blocks in flight) returns what poc_download_agents returns replica by replica:
+    nine replicas of two different sizes after a few ticks."""
+    fa = U.load_fixture(U.GOLDEN + "/tick_n1000_s42_t12.npz")
+    fb = U.load_fixture(U.GOLDEN + "/tick_n100_s42_t1.npz")
+    sa, sb = U.pre_state(fa), U.pre_state(fb)
+    states = [sa, sb, sa, sa, sb, sa, sb, sb, sa]
+    n, stat, crim = P.CrimeEngine.capacity_for(states, 40000)
+    with P.CrimeEngine(len(states), n, stat, crim) as E:
+        E.set_params(P.make_params(U.fixture_params(fa)))
+        for r, st in enumerate(states):
+            E.upload_state(r, st)
+        E.run_ticks(12, 5, [100 + r for r in range(len(states))])
+        one = [E.download_agents(r) for r in range(len(states))]
+        outs = [E.agent_buffers(len(st["alive"])) for st in states]
+        E.download_agents_many(0, outs)
+        part = [E.agent_buffers(len(st["alive"])) for st in states[3:8]]
+        E.download_agents_many(3, part)
+    for r in range(len(states)):
+        for k in one[r]:
+            assert np.array_equal(one[r][k], outs[r][k]), (r, k)
+    for i, r in enumerate(range(3, 8)):
+        for k in one[r]:
+            assert np.array_equal(one[r][k], part[i][k]), (r, k)
