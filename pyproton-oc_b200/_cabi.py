@@ -159,6 +159,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
+        # Only a MISSING library is built here.  A stale one is rebuilt by build() (__graft_entry__.build(), which compares
+        # modification times against every CUDA source): doing that on import would let the ranks of a torchrun job, whose
+        # snapshot copies carry arbitrary mtimes, compile over each other's shared object.
         if not os.path.exists(LIB_PATH):
             build()
         L = C.CDLL(LIB_PATH)

@@ -2,6 +2,8 @@
 Bit-exact for every integer / index stage and for the fp64 stages whose operation order is defined
 (tendency, CDF, candidate keys); embeddedness is compared bit-for-bit with the oracle and within 1e-6
 relative (the north-star tolerance) with the reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -324,6 +326,39 @@ def test_kernel_shapes_do_not_change_results(P, O, env, monkeypatch):
         S = O.OracleState(st)
         S.run_ticks(O.make_params(prm), 3, ticks, keys[r], 0.0)
         assert_state_equal(got[r], S, what="replica %d under %s" % (r, env))
+
+
+def test_four_concurrent_groups_of_512_replicas_equal_single_runs(P):
+    """512 replicas take the shapes of the largest batches (four replica groups on their own streams, 128 threads per
+    evaluation plus the large-block launch, 64 / 16 blocks per replica for embeddedness / search): blocks of different
+    groups run at the same time and must never meet in a scratch slot.  Sampled replicas equal their single runs after
+    24 ticks of an OC-heavy state."""
+    fx = U.load_fixture(U.GOLDEN + "/tick_n1000_s11_oc200_t3.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    R, ticks = 512, 24
+    keys = [2000 + 3 * r for r in range(R)]
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 60000)
+    os.environ["POC_GROUPS"] = "4"
+    try:
+        with P.CrimeEngine(R, n, stat, crim) as E:
+            E.set_params(P.make_params(prm))
+            for r in range(R):
+                E.upload_state(r, st, wait=False)
+            E.run_ticks(3, ticks, keys)
+            got = {r: E.download_state(r) for r in (0, 100, 129, 257, 300, 511)}
+            cn, _ = E.counters()
+    finally:
+        del os.environ["POC_GROUPS"]
+    assert (cn[:, 9] == 0).all()
+    for r, g in got.items():
+        with P.CrimeEngine(1, n, stat, crim) as E1:
+            E1.set_params(P.make_params(prm))
+            E1.upload_state(0, st)
+            E1.run_ticks(3, ticks, [keys[r]])
+            want = E1.download_state(0)
+        for k in COLS:
+            assert np.array_equal(g[k], want[k]), (r, k)
+        assert np.array_equal(g["col_6"], want["col_6"]) and np.array_equal(g["co_off"], want["co_off"]), r
 
 
 def test_large_batch_defaults_equal_single_runs(P):
