@@ -332,7 +332,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     d.r0 = 0; d.Rg = R; d.grp = 0;
     DA(ctx->d_ti, 8); d.ti = ctx->d_ti;
     if (const char *e = getenv("POC_GRAPH")) ctx->use_graph = atoi(e) != 0;
-    cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, POC_MAX_CELLS * 1024 * (int)sizeof(int));
     cudaFuncSetAttribute(k_embeddedness<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(32, N));
     cudaFuncSetAttribute(k_embeddedness<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emb_smem_bytes(64, N));
@@ -881,7 +882,11 @@ static int launch_search_rounds(poc_ctx *ctx, const DevCtx &D, cudaStream_t s) {
     int rounds = max_radius(ctx);
     dim3 grid(ctx->gx, D.Rg);
     for (int rd = 0; rd <= rounds; rd++) {
-        { Timed t(ctx, TM_SEARCH, s); k_search<<<grid, ctx->search_threads, ctx->smem_search, s>>>(D, rd & 1); }
+        {
+            Timed t(ctx, TM_SEARCH, s);
+            if (D.emb_flags & 2) k_search<true><<<grid, ctx->search_threads, ctx->smem_search, s>>>(D, rd & 1);
+            else k_search<false><<<grid, ctx->search_threads, ctx->smem_search, s>>>(D, rd & 1);
+        }
         if (rd < rounds) { Timed t(ctx, TM_EMB, s); launch_emb(ctx, D, s, rd & 1); }
     }
     CU(cudaGetLastError());

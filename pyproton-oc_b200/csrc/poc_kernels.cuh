@@ -833,6 +833,7 @@ struct ArgBest { double key; int slot; int idx; };
 __device__ __forceinline__ bool better(double k1, int s1, double k2, int s2) { return (k1 < k2) || (k1 == k2 && s1 < s2); }
 
 #define SEARCH_SCAND 512   /* ring members staged in shared memory for scoring and selection (larger rings stay in scratch) */
+template <bool STAGE>
 __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch, int parity, unsigned *bitmap,
                              unsigned *fbits, int *list, double *keys, int *s_slot, double *s_key,
                              unsigned long long &edges, unsigned long long &abytes, unsigned long long &ncand) {
@@ -886,7 +887,8 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
         // are read once per pick by the whole block; a ring over SEARCH_SCAND members stays in the block's scratch.
         // Measured at 1,024 replicas: 178 ms per 480 ticks with the staging against 168 without (the ring is read a handful
         // of times and was L1-resident already; the copy, its barrier and the smaller L1 cost more): off unless POC_EMB_FLAGS & 2
-        const bool staged = (C.emb_flags & 2) && m <= SEARCH_SCAND;
+        // (a template switch: the unstaged kernel keeps plain global loads, k_search<true> is launched under the flag)
+        const bool staged = STAGE && m <= SEARCH_SCAND;
         int *cl = staged ? s_slot : list + rb;
         double *ck = staged ? s_key : keys;
         if (staged) {
@@ -992,6 +994,7 @@ __device__ void search_crime(const DevCtx &C, int r, int c, int tick, int epoch,
     }
 }
 
+template <bool STAGE>
 __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     int tick = C.ti[C.grp].tick, epoch = C.ti[C.grp].epoch;
     extern __shared__ unsigned smem_u[];
@@ -1011,7 +1014,7 @@ __global__ void __launch_bounds__(512, 4) k_search(DevCtx C, int parity) {
     for (int item = blockIdx.x; item < ns; item += gridDim.x) {
         int c = RP(C.search_list, r, C.Ccap)[item];
         if (C.cr_state[(size_t)r * C.Ccap + c] & 4) continue;
-        search_crime(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, s_slot, s_key, edges, abytes, ncand);
+        search_crime<STAGE>(C, r, c, tick, epoch, parity, bitmap, fbits, list, keys, s_slot, s_key, edges, abytes, ncand);
         if (threadIdx.x == 0) { ncrimes++; abytes += 8ull + 4ull * POC_MAX_GROUP; }  // friends row pointer + group out
         __syncthreads();
     }
