@@ -190,7 +190,7 @@ int poc_commit_crimes(poc_ctx *ctx, int tick, const poc_replay *const *replay_or
 /* n_ticks iterations of {begin_tick; yearly tendency + multiplier; commit_crimes; end_tick}
  * (the hot-path subset of ProtonOC.step, model.py:226-288) with no host synchronisation inside.
  * reporters_out: [n_replicas][n_ticks][POC_N_REPORTERS] doubles, copied back at the end (may be NULL). */
-#define POC_N_REPORTERS 42 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
+#define POC_N_REPORTERS 43 /* the numeric columns of calculate_fast_reporters + the path's counters, see engine.REPORTER_NAMES */
 int poc_run_ticks(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *philox_keys, double *reporters_out);
 /* the same, but the reporter rows stay on the device (for a collective over NVLink, run_modes.py:221-232 gathers the
  * outputs of the runs): *rows_dev points at [n_replicas][*ticks_per_replica][POC_N_REPORTERS] doubles owned by the ctx and
@@ -241,11 +241,12 @@ typedef struct poc_demography {
     int32_t n_prop;           /* quantiles in use (<= 1024) */
     int32_t retirement_age;   /* model.py:121 */
     int32_t _pad;
+    double weddings_mean;     /* number_weddings_mean: marriages per 1,000 persons and year (model.py:184-186) */
 } poc_demography;
-/* make_baby, make_friends, make_people_die; then retire_persons (model.py:1538-1551), remove_excess_friends (:629-643) and
- * remove_excess_professional_links (:646-659) */
+/* make_baby, make_friends, make_people_die; then retire_persons (model.py:1538-1551), remove_excess_friends (:629-643),
+ * remove_excess_professional_links (:646-659) and wedding (:368-402) */
 enum { POC_PHASE_BABY = 1, POC_PHASE_FRIENDS = 2, POC_PHASE_DIE = 4, POC_PHASE_RETIRE = 8, POC_PHASE_XFRIENDS = 16,
-       POC_PHASE_XPROF = 32, POC_PHASE_ALL = 63 };
+       POC_PHASE_XPROF = 32, POC_PHASE_WEDDING = 64, POC_PHASE_ALL = 127 };
 int poc_set_demography(poc_ctx *ctx, const poc_demography *d);
 /* which of the phases poc_run_ticks runs after commit_crimes every tick, in the order of model.py:273-284 (default 0).
  * max_agents / max_static_entries of the ctx must leave room for the newborns and their links. */

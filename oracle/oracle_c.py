@@ -105,7 +105,7 @@ class Demog(C.Structure):
     """Mirror of orc_demog (hotpath.c)."""
     _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
                 ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32),
-                ("retirement_age", C.c_int32), ("_pad", C.c_int32)]
+                ("retirement_age", C.c_int32), ("_pad", C.c_int32), ("weddings_mean", C.c_double)]
 
 
 def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None) -> Demog:
@@ -126,6 +126,7 @@ def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25
         d.prop_q[i] = v
     d.mort_max_age, d.n_prop = len(fem) - 1, 1024
     d.retirement_age = 65
+    d.weddings_mean = tables.NUMBER_WEDDINGS_MEAN
     return d
 
 
@@ -186,7 +187,7 @@ def lib():
         L.orc_get_children.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_children.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_demog_counters.argtypes = [C.c_void_p, C.c_void_p]
-        for fn in ("orc_make_baby", "orc_make_friends", "orc_make_people_die"):
+        for fn in ("orc_make_baby", "orc_make_friends", "orc_make_people_die", "orc_wedding"):
             getattr(L, fn).restype = C.c_int32
             getattr(L, fn).argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_uint64]
         L.orc_retire_persons.restype = C.c_int32
@@ -317,9 +318,9 @@ class OracleState:
         self.L.orc_set_children(self.h, a.ctypes.data)
 
     def demog_counters(self):
-        out = np.zeros(2, np.int64)
+        out = np.zeros(3, np.int64)
         self.L.orc_demog_counters(self.h, out.ctypes.data)
-        return {"number_deceased": int(out[0]), "number_born": int(out[1])}
+        return {"number_deceased": int(out[0]), "number_born": int(out[1]), "number_weddings": int(out[2])}
 
     def make_baby(self, p, dm, tick, key):
         r = int(self.L.orc_make_baby(self.h, C.byref(p), C.byref(dm), tick, key))
@@ -331,6 +332,9 @@ class OracleState:
 
     def make_people_die(self, p, dm, tick, key):
         return int(self.L.orc_make_people_die(self.h, C.byref(p), C.byref(dm), tick, key))
+
+    def wedding(self, p, dm, tick, key):
+        return int(self.L.orc_wedding(self.h, C.byref(p), C.byref(dm), tick, key))
 
     def retire_persons(self, dm):
         return int(self.L.orc_retire_persons(self.h, C.byref(dm)))

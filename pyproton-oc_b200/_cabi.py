@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libprotonoc_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "protonoc_b200.h")
 
-NUM_LAYERS, MAX_CELLS, MAX_TAB, MAX_GROUP, N_REPORTERS, CN_COUNT = 9, 32, 16, 32, 42, 24
+NUM_LAYERS, MAX_CELLS, MAX_TAB, MAX_GROUP, N_REPORTERS, CN_COUNT = 9, 32, 16, 32, 43, 24
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -26,7 +26,7 @@ class Demography(C.Structure):
     """poc_demography (include/protonoc_b200.h)."""
     _fields_ = [("mort", (C.c_double * 128) * 2), ("fert", (C.c_double * 64) * 3), ("poisson_cdf", C.c_double * 32),
                 ("prop_q", C.c_double * 1024), ("mort_max_age", C.c_int32), ("n_prop", C.c_int32),
-                ("retirement_age", C.c_int32), ("_pad", C.c_int32)]
+                ("retirement_age", C.c_int32), ("_pad", C.c_int32), ("weddings_mean", C.c_double)]
 
 
 class Params(C.Structure):

@@ -350,6 +350,7 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
 #undef EMB3_ATTR
     cudaFuncSetAttribute(k_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rings_hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
+    cudaFuncSetAttribute(k_wedding, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * wcap * sizeof(unsigned)));
     cudaFuncSetAttribute(k_emb_acc_mark, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     cudaFuncSetAttribute(k_emb_acc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_search);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -922,6 +923,11 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
 static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask, int n) {
     if (!mask || !n) return POC_OK;
     if (!ctx->demog_set) return fail(ctx, POC_ERR_STATE, "demography phases requested before poc_set_demography");
+    if (mask & POC_PHASE_WEDDING) {   // model.py:271 (before the crimes of the tick)
+        Timed t(ctx, TM_OTHER, s);
+        k_wedding<<<D.Rg, 256, 3 * (((size_t)D.Ncap + 31) / 32) * sizeof(unsigned), s>>>(D);
+        k_multiplex_insert<<<D.Rg, 1024, 0, s>>>(D);
+    }
     if (mask & POC_PHASE_RETIRE) {   // model.py:274
         Timed t(ctx, TM_OTHER, s);
         k_retire<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D);
@@ -1140,10 +1146,12 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
                 if (rc2) return rc2;
                 rc2 = launch_tendency(ctx, D, s, 2);
                 if (rc2) return rc2;
+                rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_WEDDING, n);   // model.py:271
+                if (rc2) return rc2;
                 rc2 = launch_commit(ctx, D, s, true, false, (k == 0 && g + 1 < G) ? ctx->gstag[g] : nullptr, 0);
                 if (rc2) return rc2;
                 // model.py:274-278: retire_persons, make_baby, remove_excess_friends / _professional_links, make_friends
-                rc2 = launch_phases(ctx, D, s, ctx->phases & ~POC_PHASE_DIE, n);
+                rc2 = launch_phases(ctx, D, s, ctx->phases & ~(POC_PHASE_DIE | POC_PHASE_WEDDING), n);
                 if (rc2) return rc2;
                 if (n) { Timed t(ctx, TM_OTHER, s); k_end_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, 0); }
                 rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_DIE, n);   // model.py:284

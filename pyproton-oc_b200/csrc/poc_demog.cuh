@@ -622,3 +622,205 @@ __global__ void k_removals_done(DevCtx C) {
     const int r = C.r0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (r < C.r0 + C.Rg) RP(C.dm_n, r, 4)[3] = 0;
 }
+
+// ---------------------------------------------------------------------------------------------- wedding, model.py:368-402
+// oracle/hotpath.c orc_wedding states the semantics (sequential by nature: the marriable list shrinks with every ego); one
+// block per replica walks it with three bitmaps in shared memory (marriable, visited, pool).  Links that go are cleared in
+// place; the new household / partner links are queued for k_multiplex_insert (a couple need not have been neighbours).
+__device__ __forceinline__ double det_exp_neg(double x) {   // exp(-x) by fixed arithmetic: the same bits as the oracle's
+    const double y = x * (1.0 / 1024.0);
+    double t = 1.0;
+    for (int k = 14; k >= 1; k--) t = 1.0 - y * t / (double)k;
+    for (int i = 0; i < 10; i++) t = t * t;
+    return t;
+}
+// the j-th set bit (ascending) of a bitmap; one warp, every lane returns the slot (-1: fewer bits)
+__device__ int warp_select_bit(const unsigned *bm, int nwords, int j) {
+    const int lane = lane_id();
+    int base = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int i = w0 + lane;
+        const unsigned wd = (i < nwords) ? bm[i] : 0u;
+        const int c = __popc(wd);
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+        const int tot = __shfl_sync(FULL_MASK, x, 31);
+        if (j < base + tot) {
+            const bool mine = j >= base + x - c && j < base + x;
+            const unsigned m = __ballot_sync(FULL_MASK, mine);
+            int res = -1;
+            if (mine) {
+                unsigned t = wd;
+                for (int q = j - (base + x - c); q > 0; q--) t &= t - 1;
+                res = i * 32 + (__ffs(t) - 1);
+            }
+            return __shfl_sync(FULL_MASK, res, __ffs(m) - 1);
+        }
+        base += tot;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_wedding(DevCtx C) {
+    extern __shared__ unsigned wsm[];
+    const int tick = C.ti[C.grp].tick;
+    const int r = C.r0 + blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+    const int n = C.n_agents[r], nwords = (n + 31) >> 5, wcap = (C.Ncap + 31) >> 5;
+    unsigned *marr = wsm, *seen = wsm + wcap, *pool = wsm + 2 * wcap;
+    __shared__ int s_M, s_num, s_alive, s_ego, s_partner, s_np, s_cnt, s_done, s_npairs;
+    const poc_params &P = C.params[r];
+    const DevDemog &D = *C.demog;
+    const uint32_t *attr = RP(C.attr, r, C.Ncap);
+    Graph g = graph_of(C, r);
+    uint32_t *uent = const_cast<uint32_t *>(g.u_ent);
+    int32_t *list = RP(C.dm_list, r, C.Ncap);
+    long long *ltot = RP(C.layer_tot, r, 8);
+    const unsigned long long key = C.philox_key[r];
+    int *dmn = RP(C.dm_n, r, 4);
+    unsigned long long *pairs = RP(C.dm_pairs, r, C.DPcap);
+    if (tid == 0) { s_M = 0; s_alive = 0; s_done = 0; s_npairs = 0; }
+    __syncthreads();
+    // ---- the marriable: alive, 25 < age < 55, no partner (a bit per agent, ascending slot order = the list order)
+    for (int base = 0; base < nwords * 32; base += blockDim.x) {
+        const int a = base + tid;
+        bool al = false, mr = false;
+        if (a < n) {
+            const uint32_t x = attr[a];
+            al = (x & F_ALIVE) != 0;
+            const int age = attr_age(x);
+            if (al && age > 25 && age < 55) {
+                mr = true;
+                for (int e = g.u_rowptr[a]; e < g.u_rowptr[a + 1]; e++) if (ENT_MASK(uent[e]) & MB_PARTNER) { mr = false; break; }
+            }
+        }
+        const unsigned bm = __ballot_sync(FULL_MASK, mr), ba = __ballot_sync(FULL_MASK, al);
+        if (lane == 0) {
+            if ((a >> 5) < nwords) marr[a >> 5] = bm;
+            if (bm) atomicAdd(&s_M, __popc(bm));
+            if (ba) atomicAdd(&s_alive, __popc(ba));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {   // numpy's poisson by inversion of the CDF with one uniform (oracle: the same chain)
+        const double lam = D.weddings_mean * (double)s_alive / 1000.0 / 12.0;
+        double u, u2;
+        philox_u2(key, tick, ST_WED_N, 0, u, u2);
+        int num = 0;
+        double pk = det_exp_neg(lam), cdf = pk;
+        while (u >= cdf && num < 1000) { num++; pk = pk * lam / (double)num; cdf = cdf + pk; }
+        s_num = num;
+    }
+    __syncthreads();
+    const int radius = P.max_accomplice_radius;
+    for (int it = 0; s_num > 0 && s_M > 1; it++) {
+        if (w == 0) {
+            double u, u2;
+            philox_u2(key, tick, ST_WED_EGO, it, u, u2);
+            int j = (int)floor(u * (double)s_M);
+            if (j >= s_M) j = s_M - 1;
+            const int ego = warp_select_bit(marr, nwords, j);
+            if (lane == 0) s_ego = ego;
+        }
+        for (int i = tid; i < nwords; i += blockDim.x) pool[i] = 0u;
+        __syncthreads();
+        const int ego = s_ego;
+        const uint32_t xe = attr[ego];
+        // ---- neighbors_range(friendship, radius) | neighbors_range(professional, radius): each network walked on its own
+        for (int q = 0; q < 2; q++) {
+            const unsigned lbit = q ? MB_PROF : MB_FRIEND;
+            for (int i = tid; i < nwords; i += blockDim.x) seen[i] = 0u;
+            __syncthreads();
+            if (tid == 0) { list[0] = ego; seen[ego >> 5] = 1u << (ego & 31); s_cnt = 1; }
+            __syncthreads();
+            int fb = 0, fe = 1;
+            for (int d = 0; d < radius && fb < fe; d++) {
+                for (int i = fb + w; i < fe; i += nw) {
+                    const int u = list[i];
+                    for (int e = g.u_rowptr[u] + lane; e < g.u_rowptr[u + 1]; e += 32) {
+                        const uint32_t en = uent[e];
+                        if (!(ENT_MASK(en) & lbit)) continue;
+                        const int v = ENT_COL(en);
+                        const unsigned bit = 1u << (v & 31);
+                        if (!(atomicOr(&seen[v >> 5], bit) & bit)) { list[atomicAdd(&s_cnt, 1)] = v; atomicOr(&pool[v >> 5], bit); }
+                    }
+                }
+                __syncthreads();
+                fb = fe; fe = s_cnt;
+                __syncthreads();
+            }
+        }
+        // ---- the pool: marriable, other sex, (age - ego.age) < 8, not sibling / offspring of the ego, ego not its offspring
+        if (tid == 0) s_np = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int wi = tid; wi < nwords; wi += blockDim.x) {
+            unsigned pw = pool[wi] & marr[wi], keep = 0u;
+            while (pw) {
+                const int b = __ffs(pw) - 1;
+                pw &= pw - 1;
+                const int v = wi * 32 + b;
+                const uint32_t xv = attr[v];
+                bool ok = v != ego && ((xv ^ xe) & F_MALE) && (attr_age(xv) - attr_age(xe)) < 8;
+                if (ok && (static_find_mask(g, ego, v) & (MB_SIB | MB_OFF))) ok = false;
+                if (ok && (static_find_mask(g, v, ego) & MB_OFF)) ok = false;
+                if (ok) keep |= 1u << b;
+            }
+            pool[wi] = keep;
+            cnt += __popc(keep);
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(&s_np, cnt);
+        __syncthreads();
+        if (w == 0) {
+            int partner = -1;
+            if (s_np > 0) {   // a uniform pick: extra.wedding_proximity_with always returns equal weights (see the oracle)
+                double u, u2;
+                philox_u2(key, tick, ST_WED_PICK, it, u, u2);
+                int idx = (int)floor(u * (double)s_np);
+                if (idx >= s_np) idx = s_np - 1;
+                partner = warp_select_bit(pool, nwords, idx);
+            }
+            if (lane == 0) s_partner = partner;
+        }
+        __syncthreads();
+        const int partner = s_partner;
+        if (partner >= 0) {
+            // ---- both leave their households: reciprocal links only (remove_from_household, entities.py:378-387); warp 0 / 1
+            if (w < 2) {
+                const int x = w ? partner : ego;
+                for (int e = g.u_rowptr[x] + lane; e < g.u_rowptr[x + 1]; e += 32) {
+                    const uint32_t en = uent[e];
+                    if (!(ENT_MASK(en) & MB_HH)) continue;
+                    const int m = ENT_COL(en);
+                    const int ri = static_find_idx(g, m, x);
+                    if (ri < 0) continue;
+                    // (the two warps may meet on the couple's own link: whoever clears an entry accounts for it)
+                    if (!(uent[ri] & (MB_HH << 24)) && !(m == (w ? ego : partner))) continue;
+                    const unsigned o1 = atomicAnd(&uent[e], ~(MB_HH << 24)), o2 = atomicAnd(&uent[ri], ~(MB_HH << 24));
+                    if ((o1 & (MB_HH << 24)) && (attr[x] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[4], (unsigned long long)-1ll);
+                    if ((o2 & (MB_HH << 24)) && (attr[m] & F_ALIVE)) atomicAdd((unsigned long long *)&ltot[4], (unsigned long long)-1ll);
+                    if ((o1 & (MB_HH << 24)) && (o1 & ENT_CRIM)) crim_mask_clear(g, x, m, MB_HH);
+                    if ((o2 & (MB_HH << 24)) && (o2 & ENT_CRIM)) crim_mask_clear(g, m, x, MB_HH);
+                    ent_asym_update(g, x, m);
+                }
+            }
+            if (tid == 0) {
+                const int q = s_npairs;
+                if (q + 2 <= C.DPcap) {
+                    pairs[q] = DM_KEY(ego, partner, MB_HH | MB_PARTNER); pairs[q + 1] = DM_KEY(partner, ego, MB_HH | MB_PARTNER);
+                    s_npairs = q + 2;
+                } else atomicExch(&RP(C.counters, r, CN_COUNT)[CN_ERROR], 26);
+                marr[partner >> 5] &= ~(1u << (partner & 31));
+                s_M -= 1; s_num -= 1; s_done += 1;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { marr[ego >> 5] &= ~(1u << (ego & 31)); s_M -= 1; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        dmn[0] = 0; dmn[2] = s_npairs;   // the insert pass that follows adds the couples' household + partner links
+        RP(C.counters, r, CN_COUNT)[CN_WEDDINGS] += s_done;
+    }
+}

@@ -63,7 +63,7 @@ __host__ __device__ __forceinline__ int layer_bit(int layer) { return layer < PO
 enum {
     CN_NUMBER_CRIMES = 0, CN_SIZE_FAILS, CN_FAC_CRIMES, CN_FAC_FAILS, CN_BIG_CRIME, CN_OFFSPRING_RECRUITED,
     CN_PROTECTED_RECRUITED, CN_PEOPLE_JAILED, CN_RECRUITED, CN_ERROR, CN_TICK_CRIMES, CN_TICK_MEMBERS,
-    CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_DECEASED, CN_BORN, CN_FRIENDSHIPS, CN_COUNT = 24
+    CN_TICK_ARRESTS, CN_TICK_EMB, CN_TICK_RECRUITED, CN_N_ALIVE, CN_DECEASED, CN_BORN, CN_FRIENDSHIPS, CN_WEDDINGS, CN_COUNT = 24
 };
 
 // algorithmic-work counters per replica (what an ideal implementation must move once)
@@ -170,11 +170,12 @@ struct DevDemog {
     double prop_q[1024];      // quantiles of the newborns' propensity lognormal (entities.py:71)
     int mort_max_age, n_prop;
     int retirement_age, _pad;
+    double weddings_mean;     // number_weddings_mean (model.py:184-186)
 };
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) -----------------------------------------------------------
 enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4, ST_DIE = 5, ST_FACREP = 6, ST_BABY = 7,
-       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10, ST_XFRIEND = 11, ST_XPROF = 12 };
+       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10, ST_XFRIEND = 11, ST_XPROF = 12, ST_WED_N = 13, ST_WED_EGO = 14, ST_WED_PICK = 15 };
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
 #pragma unroll

@@ -1615,7 +1615,7 @@ __global__ void __launch_bounds__(512, 3) k_report(DevCtx C, int mode) {
         for (int l = 0; l < 8; l++) row[25 + l] = (double)lt[l];
         row[33] = cn[CN_PROTECTED_RECRUITED]; row[34] = cn[CN_PEOPLE_JAILED] - pv[CN_PEOPLE_JAILED];
         row[35] = C.ti[C.grp].tick; row[36] = cn[CN_RECRUITED]; row[37] = cn[CN_TICK_CRIMES]; row[38] = cn[CN_TICK_EMB]; row[39] = cn[CN_ERROR];
-        row[40] = cn[CN_BORN]; row[41] = cn[CN_DECEASED];   // make_baby / make_people_die when those phases run on the device
+        row[40] = cn[CN_BORN]; row[41] = cn[CN_DECEASED]; row[42] = cn[CN_WEDDINGS];   // the step phases, when they run on the device
         if (mode == 2) {
             __threadfence();
             TickInfo &ti = C.ti[C.grp];

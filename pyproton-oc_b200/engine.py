@@ -38,7 +38,7 @@ REPORTER_NAMES = ["number_crimes", "crime_size_fails", "facilitator_crimes", "fa
                   "tot_friendship_link", "tot_professional_link", "tot_school_link",
                   "number_protected_recruited_this_tick", "number_law_interventions_this_tick", "tick",
                   "recruited_total", "crimes_this_tick", "embeddedness_evaluations_this_tick", "error_code",
-                  "number_born", "number_deceased"]
+                  "number_born", "number_deceased", "number_weddings"]
 TIMER_CLASSES = ["cells", "tendency", "draw", "search", "embeddedness", "commit", "arrests", "other"]
 
 
@@ -225,14 +225,14 @@ class CrimeEngine:
         return st
 
     # ------------------------------------------------------------------ demography phases
-    PHASE_BABY, PHASE_FRIENDS, PHASE_DIE, PHASE_RETIRE, PHASE_XFRIENDS, PHASE_XPROF, PHASE_ALL = 1, 2, 4, 8, 16, 32, 63
+    PHASE_BABY, PHASE_FRIENDS, PHASE_DIE, PHASE_RETIRE, PHASE_XFRIENDS, PHASE_XPROF, PHASE_WEDDING, PHASE_ALL = 1, 2, 4, 8, 16, 32, 64, 127
 
     def set_demography(self, d):
         self._ck(self.L.poc_set_demography(self.h, C.byref(d)))
 
     def set_phases(self, mask: int):
         """Which of make_baby (1) / make_friends (2) / make_people_die (4) / retire_persons (8) / remove_excess_friends (16) /
-        remove_excess_professional_links (32) run_ticks runs every tick, in the order of ProtonOC.step (default 0)."""
+        remove_excess_professional_links (32) / wedding (64) run_ticks runs every tick, in the order of ProtonOC.step (default 0)."""
         self._ck(self.L.poc_set_phases(self.h, int(mask)))
         self._phases = int(mask)
 

@@ -97,7 +97,8 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
         with CrimeEngine(len(batch), n + grow[0], 2 * max(stat, 1) + grow[1], crim, device=device) as E:
             from .params import make_demography
             m0 = models[0]   # the demography tables are per engine: one batch, one (nat_propensity, retirement_age) setting
-            E.set_demography(make_demography(m0.nat_propensity_m, m0.nat_propensity_sigma, retirement_age=m0.retirement_age))
+            E.set_demography(make_demography(m0.nat_propensity_m, m0.nat_propensity_sigma, retirement_age=m0.retirement_age,
+                                             number_weddings_mean=m0.number_weddings_mean))
             for r, (m, st) in enumerate(zip(models, states)):
                 E.set_params(m._params(), replica=r)
                 E.upload_state(r, st, wait=False)

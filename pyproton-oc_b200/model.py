@@ -281,10 +281,10 @@ class _DataCollector:
 
 class ProtonOC:
     out_of_scope_phases = ["interventions (family / social / welfare)", "graduate_and_enter_jobmarket", "find_job",
-                           "update_unemployment_status", "let_migrants_in", "return_kids", "wedding"]
-    # the phases of step() besides the crime path that run on the device (CrimeEngine.PHASE_*): retire_persons,
-    # make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, make_people_die, in the reference's
-    # order (model.py:274-284).  0 = the crime path alone.
+                           "update_unemployment_status", "let_migrants_in", "return_kids"]
+    # the phases of step() besides the crime path that run on the device (CrimeEngine.PHASE_*): wedding,
+    # retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, make_people_die, in
+    # the reference's order (model.py:271-284).  0 = the crime path alone.
     device_phases: int = CrimeEngine.PHASE_ALL
 
     def __init__(self, seed: int = int.from_bytes(os.urandom(4), sys.byteorder), collect_agents: bool = False) -> None:
@@ -310,8 +310,8 @@ class ProtonOC:
         self.number_born: int = 0
         self.number_migrants: int = 0
         self.number_weddings: int = 0
-        self.number_weddings_mean = 0
-        self.number_weddings_sd: float = 0
+        self.number_weddings_mean = tables.NUMBER_WEDDINGS_MEAN   # marriages_stats.csv (model.py:184-187)
+        self.number_weddings_sd: float = tables.NUMBER_WEDDINGS_SD
         self.number_law_interventions_this_tick: int = 0
         self.correction_for_non_facilitators: float = 0
         self.number_protected_recruited_this_tick: int = 0
@@ -485,7 +485,8 @@ class ProtonOC:
                 e._stat_cap, e._crim_cap = max(stat, 1) * 2, crim
                 self._engine = e
             e.set_params(self._params())
-            e.set_demography(make_demography(self.nat_propensity_m, self.nat_propensity_sigma, retirement_age=self.retirement_age))
+            e.set_demography(make_demography(self.nat_propensity_m, self.nat_propensity_sigma, retirement_age=self.retirement_age,
+                                             number_weddings_mean=getattr(self, "number_weddings_mean", None)))
             e.upload_state(0, st)
             if "number_of_children" in st:
                 e.upload_children(0, st["number_of_children"])
@@ -612,6 +613,9 @@ class ProtonOC:
         if (self.tick % self.ticks_per_year) == 0 or self.tick == 1:
             self.calculate_criminal_tendency()
             self.calculate_crime_multiplier()
+        if self.device_phases & CrimeEngine.PHASE_WEDDING:                                             # model.py:271
+            self._engine_ready().run_phase(CrimeEngine.PHASE_WEDDING, self.tick, [self._philox_key])
+            self._host_stale = True
         self.reset_oc_embeddedness()
         self.commit_crimes()
         e = self._engine_ready()

@@ -78,7 +78,7 @@ def make_params(attrs: Optional[Dict] = None, c_range=None, co_offenders=None, c
 
 
 def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25, mortality=None, fertility=None,
-                    retirement_age: int = 65) -> Demography:
+                    retirement_age: int = 65, number_weddings_mean: float = None) -> Demography:
     """poc_demography for the phases of SURVEY.md 8(f).  mortality: (female[ages], male[ages]) yearly probabilities
     (initial_mortality_rates.csv, entities.py:615-626), fertility: [3][64] yearly by [min(children, 2)][age]
     (initial_fertility_rates.csv, entities.py:605-613); defaults: the reference's Palermo tables."""
@@ -97,4 +97,5 @@ def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float =
         d.prop_q[i] = v
     d.mort_max_age, d.n_prop = len(fem) - 1, 1024
     d.retirement_age = int(retirement_age)   # model.py:121
+    d.weddings_mean = float(tables.NUMBER_WEDDINGS_MEAN if number_weddings_mean is None else number_weddings_mean)   # model.py:184-186
     return d

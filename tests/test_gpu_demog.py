@@ -184,8 +184,8 @@ def test_retire_and_remove_excess_match_the_oracle(P, O, name):
 
 @pytest.mark.parametrize("name,ticks", [("tick_n1000_s42_t12", 60), ("tick_n1000_s11_oc200_t3", 36), ("tick_n3000_s42_t1", 30)])
 def test_runs_with_six_phases_match_the_oracle(P, O, name, ticks):
-    """poc_run_ticks with all six phases on equals the oracle's run: the crime path's traversals (embeddedness reads every
-    undirected link once, through the one-sided flags) see the same network tick after tick."""
+    """poc_run_ticks with six phases on (all but wedding) equals the oracle's run: the crime path's traversals (embeddedness
+    reads every undirected link once, through the one-sided flags) see the same network tick after tick."""
     fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
     st, prm = U.pre_state(fx), U.fixture_params(fx)
     alive = np.flatnonzero(st["alive"] > 0)
@@ -196,7 +196,7 @@ def test_runs_with_six_phases_match_the_oracle(P, O, name, ticks):
     with engine_for(P, [st, st]) as E:
         E.set_params(P.make_params(prm))
         E.set_demography(P.make_demography())
-        E.set_phases(E.PHASE_ALL)
+        E.set_phases(63)   # every phase but wedding (the fixture / oracle call of this test)
         for r in range(2):
             E.upload_state(r, st)
             E.upload_children(r, children_of(st))
@@ -217,6 +217,102 @@ def test_runs_with_six_phases_match_the_oracle(P, O, name, ticks):
             assert rep[r, -1, 31] == int(np.diff(S.layer(7)[0])[al].sum())         # tot_professional_link
 
 
+@pytest.mark.parametrize("name", ["tick_n1000_s42_t12", "tick_n1000_s5_late_t252", "tick_n3000_s42_t24",
+                                  "tick_n1000_s7_disruptive_strong_t25", "state_n3000_s42_baseline"])
+def test_wedding_matches_the_oracle(P, O, name):
+    """wedding (model.py:368-402) on the device against the oracle's restatement, phase by phase, interleaved with the crime
+    path's state changes of the other phases: whole state equal after every call (the couples' new household / partner links
+    go through the insert pass, the households they leave are cleared in place)."""
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    tick, key = int(fx["tick"]), 616161
+    S = O.OracleState(st)
+    S.reserve(len(st["alive"]) + 600)
+    S.set_children(children_of(st))
+    OP = O.make_params(prm)
+    # a high marriage rate so that every tick has several weddings (and egos that find nobody)
+    OD, PD = O.make_demog(), P.make_demography(number_weddings_mean=60.0)
+    OD.weddings_mean = 60.0
+    total = 0
+    with engine_for(P, [st]) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(PD)
+        E.upload_state(0, st)
+        E.upload_children(0, children_of(st))
+        for rep in range(6):
+            t = tick + rep
+            S.begin_tick(t); E.begin_tick(t)
+            nw = S.wedding(OP, OD, t, key); E.run_phase(E.PHASE_WEDDING, t, [key])
+            total += nw
+            assert_equal(E, 0, S, "%s wedding round %d (%d weddings)" % (name, rep, nw))
+            S.make_baby(OP, OD, t, key); E.run_phase(E.PHASE_BABY, t, [key])
+            S.make_friends(OP, OD, t, key); E.run_phase(E.PHASE_FRIENDS, t, [key])
+            S.make_people_die(OP, OD, t, key); E.run_phase(E.PHASE_DIE, t, [key])
+            assert_equal(E, 0, S, "%s after the other phases, round %d" % (name, rep))
+        cn, _ = E.counters()
+        assert cn[0, 9] == 0 and cn[0, 19] == S.demog_counters()["number_weddings"] == total and total > 0
+        row = dict(zip(P.REPORTER_NAMES, E.report()[0]))
+        al = S.cols()["alive"] > 0
+        for l, lname in enumerate(P.LAYER_NAMES):
+            rp, _, _ = S.layer(l)
+            assert row["tot_%s_link" % lname] == int(np.diff(rp)[al].sum()), lname
+        assert row["number_weddings"] == total
+
+
+@pytest.mark.parametrize("name,ticks", [("tick_n1000_s42_t12", 60), ("tick_n3000_s42_t1", 30)])
+def test_runs_with_all_seven_phases_match_the_oracle(P, O, name, ticks):
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % name)
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    tick0, keys = int(fx["tick"]), [191, 192]
+    mult0 = float(fx["crime_multiplier"])
+    with engine_for(P, [st, st]) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_phases(E.PHASE_ALL)
+        for r in range(2):
+            E.upload_state(r, st)
+            E.upload_children(r, children_of(st))
+            E.set_crime_multiplier(mult0, r)
+        rep = E.run_ticks(tick0, ticks, keys)
+        cn, _ = E.counters()
+        assert (cn[:, 9] == 0).all()
+        for r in range(2):
+            S = O.OracleState(st)
+            S.reserve(len(st["alive"]) + 600)
+            S.set_children(children_of(st))
+            mult, tot = S.run_ticks_phases(O.make_params(prm), O.make_demog(), 127, tick0, ticks, keys[r], mult0)
+            assert_equal(E, r, S, "%s replica %d after %d ticks" % (name, r, ticks))
+            assert rep[r, -1, 0] == tot[0] and rep[r, -1, 42] == S.demog_counters()["number_weddings"]
+
+
+def test_seven_phases_in_distribution_against_the_reference(P):
+    """30 replicas against 30 continuations by the unmodified reference with wedding and the six other phases active
+    (distdemog3)."""
+    from scipy.stats import ks_2samp
+    fx = U.load_fixture(U.GOLDEN + "/distdemog3_n1000_s42.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 60000)
+    with P.CrimeEngine(runs, n + 300, stat + 20000, crim) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_phases(E.PHASE_ALL)
+        for r in range(runs):
+            E.upload_state(r, st)
+            E.upload_children(r, st["number_of_children"])
+        rep = E.run_ticks(1, ticks, [9300 + r for r in range(runs)])
+        cn, _ = E.counters()
+    assert (cn[:, 9] == 0).all()
+    names = list(P.REPORTER_NAMES)
+    for col in ["number_weddings", "tot_partner_link", "tot_household_link", "current_num_persons", "tot_friendship_link",
+                "number_crimes", "current_oc_members"]:
+        mine = rep[:, :, names.index(col)]
+        ref = fx["refdemog_" + col]
+        for t in (5, 23, ticks - 1):
+            p = ks_2samp(mine[:, t], ref[:, t]).pvalue
+            assert p > 0.005, (col, t, p, mine[:, t].mean(), ref[:, t].mean())
+
+
 def test_six_phases_in_distribution_against_the_reference(P):
     """30 replicas against 30 continuations by the unmodified reference with the six phases active (distdemog2)."""
     from scipy.stats import ks_2samp
@@ -227,7 +323,7 @@ def test_six_phases_in_distribution_against_the_reference(P):
     with P.CrimeEngine(runs, n + 300, stat + 20000, crim) as E:
         E.set_params(P.make_params(prm))
         E.set_demography(P.make_demography())
-        E.set_phases(E.PHASE_ALL)
+        E.set_phases(63)   # every phase but wedding (the fixture / oracle call of this test)
         for r in range(runs):
             E.upload_state(r, st)
             E.upload_children(r, st["number_of_children"])

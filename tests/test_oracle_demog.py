@@ -183,3 +183,61 @@ def test_retire_and_remove_excess_invariants():
         hub = hub_f if layer == 5 else hub_p
         assert all((v, u) in pairs for (u, v) in pairs if u == hub)
         assert fn(2, 99) == 0   # nobody is over the limit any more
+
+
+def test_wedding_in_distribution_against_the_reference_and_invariants():
+    """orc_wedding (model.py:368-402 restated): 30 oracle runs with all seven phases against 30 continuations by the unmodified
+    reference with exactly these phases active (distdemog3): number_weddings and the partner / household totals, KS at three
+    ticks.  Invariants of every wedding: both were marriable (25 < age < 55, no partner), of different sex, linked as partner
+    and household both ways afterwards, and no longer in the household of anybody they left."""
+    fx = U.load_fixture(U.GOLDEN + "/distdemog3_n1000_s42.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    P, D = O.make_params(prm), O.make_demog()
+    names = ["number_weddings", "tot_partner_link", "tot_household_link", "current_num_persons", "number_crimes"]
+    checks = (5, 23, ticks - 1)
+    cols = {k: np.zeros((runs, len(checks))) for k in names}
+    for j in range(runs):
+        S = O.OracleState(st)
+        S.reserve(len(st["alive"]) + 300)
+        S.set_children(st["number_of_children"])
+        mult, crimes, t_done = 0.0, 0, 0
+        for ci, t_end in enumerate(checks):
+            mult, tot = S.run_ticks_phases(P, D, 127, t_done + 1, t_end + 1 - t_done, 7300 + j, mult)
+            crimes += int(tot[0])
+            t_done = t_end + 1
+            c = S.cols()
+            al = c["alive"] > 0
+            vals = {"number_weddings": S.demog_counters()["number_weddings"], "tot_partner_link": np.diff(S.layer(3)[0])[al].sum(),
+                    "tot_household_link": np.diff(S.layer(4)[0])[al].sum(), "current_num_persons": al.sum(), "number_crimes": crimes}
+            for k in names:
+                cols[k][j, ci] = vals[k]
+    for k in names:
+        ref = fx["refdemog_" + k]
+        for ci, t in enumerate(checks):
+            p = ks_2samp(cols[k][:, ci], ref[:, t]).pvalue
+            assert p > 0.005, (k, t, p, cols[k][:, ci].mean(), ref[:, t].mean())
+    # one phase call on the 3,000-agent setup state, looked at closely
+    fx = U.load_fixture(U.GOLDEN + "/state_n3000_s42_baseline.npz")
+    st = U.pre_state(fx)
+    n = len(st["alive"])
+    S = O.OracleState(st)
+    total = 0
+    for t in range(1, 13):
+        S.begin_tick(t)
+        c0, part0, hh0 = S.cols(), S.layer(3), S.layer(4)
+        nw = S.wedding(O.make_params(U.fixture_params(fx)), D, t, 31)
+        total += nw
+        part1, hh1 = S.layer(3), S.layer(4)
+        newly = [a for a in range(n) if part1[0][a + 1] - part1[0][a] > part0[0][a + 1] - part0[0][a]]
+        assert len(newly) == 2 * nw
+        for a in newly:
+            b = int(part1[1][part1[0][a]])
+            assert part0[0][a + 1] == part0[0][a] and 25 < c0["age"][a] < 55 and c0["male"][a] != c0["male"][b]
+            assert b in part1[1][part1[0][b]:part1[0][b + 1]] or a in part1[1][part1[0][b]:part1[0][b + 1]]
+            hh_a = set(hh1[1][hh1[0][a]:hh1[0][a + 1]].tolist())
+            assert b in hh_a
+            for m in hh0[1][hh0[0][a]:hh0[0][a + 1]].tolist():   # the household it left (reciprocal links only)
+                if m != b and a in hh0[1][hh0[0][m]:hh0[0][m + 1]].tolist():
+                    assert m not in hh_a and a not in hh1[1][hh1[0][m]:hh1[0][m + 1]].tolist()
+    assert total > 0
