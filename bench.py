@@ -516,7 +516,7 @@ def main():
         SW.E.close()
         del SW
 
-    # ---- config 5 with the six step() phases that run on the device switched on (retire_persons, make_baby,
+    # ---- config 5 with the seven step() phases that run on the device switched on (wedding, retire_persons, make_baby,
     # remove_excess_friends / _professional_links, make_friends, make_people_die): births and deaths keep the age
     # structure and the criminal layer from drifting the way the crime path alone lets them over 480 ticks
     demog = None
@@ -526,13 +526,13 @@ def main():
         cn0, _ = DW.E.counters()
         dkp, _ = kernel_pass(DW)
         cn, _ = DW.E.counters()
-        cn = cn - cn0 * (cn0 > 0) * np.isin(np.arange(cn.shape[1]), [0, 16, 17])[None, :]   # cumulative counters: this pass only
-        demog = {"phases": "retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, "
-                           "make_people_die (model.py:274-284) every tick, on the device",
+        cn = cn - cn0 * (cn0 > 0) * np.isin(np.arange(cn.shape[1]), [0, 16, 17, 19])[None, :]   # cumulative counters: this pass only
+        demog = {"phases": "wedding, retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, "
+                           "make_friends, make_people_die (model.py:271-284) every tick, on the device",
                  "value": dval, "ms_per_step": dms, "gpu_launches": int(dl), "kernel_ms": dkp["kernel_ms"],
                  "roofline": dkp["roofline"], "errors": int((cn[:, 9] != 0).sum()),
                  "born_per_run": float(cn[:, 17].mean()), "deceased_per_run": float(cn[:, 16].mean()),
-                 "crimes_per_run": float(cn[:, 0].mean()), "note": "value counts the agents of the initial state x ticks, like the headline"}
+                 "crimes_per_run": float(cn[:, 0].mean()), "weddings_per_run": float(cn[:, 19].mean()), "note": "value counts the agents of the initial state x ticks, like the headline"}
         DW.E.close()
         del DW
 

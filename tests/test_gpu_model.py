@@ -185,9 +185,9 @@ def test_run_output_contract_and_fast_equals_stepwise(P):
     for col in ["employed", "facilitators", "number_students", "tot_friendship_link", "tot_household_link",
                 "tot_partner_link", "tot_offspring_link", "tot_school_link", "tot_professional_link",
                 "tot_sibling_link", "tot_parent_link", "number_law_interventions_this_tick", "current_num_persons",
-                "number_born", "number_deceased"]:
+                "number_born", "number_deceased", "number_weddings"]:
         assert fa[col].tolist()[1:] == fb[col].tolist()[1:], col
-    # the six device phases of step() were on (ProtonOC.device_phases): people died, friendships were made
+    # the device phases of step() were on (ProtonOC.device_phases): people died, friendships were made
     assert fa["number_deceased"].iloc[-1] > 0 and fa["tot_friendship_link"].iloc[-1] != fa["tot_friendship_link"].iloc[0]
     assert len(a.state_dict()["alive"]) == 400 + int(fa["number_born"].iloc[-1])
     for col in ["criminal_tendency_mean", "criminal_tencency_sd", "age_mean", "age_sd", "education_level_mean",
