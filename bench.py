@@ -112,7 +112,11 @@ def homogeneous_config(replicas):
         path = os.path.join(U.GOLDEN, name + ".npz")
         if os.path.exists(path):
             fx = U.load_fixture(path)
-            ent = [(U.pre_state(fx), U.fixture_params(fx), int(fx["tick"]), float(fx["crime_multiplier"]))]
+            st = U.pre_state(fx)
+            edu = os.path.join(U.GOLDEN, name + "_edu.npz")   # the two columns the yearly labour-status block reads
+            if "max_education_level" not in st and os.path.exists(edu):
+                st.update(U.pre_state(U.load_fixture(edu)))
+            ent = [(st, U.fixture_params(fx), int(fx["tick"]), float(fx["crime_multiplier"]))]
             return dict(name="%s (one reference state, one parameter set)" % name, entries=ent, assign=[0] * replicas)
     raise SystemExit("no workload state under tests/golden")
 
@@ -345,6 +349,8 @@ def main():
             self.E = E if E is not None else pkg.CrimeEngine(self.R, *self.cap, device=local)
             if phases:
                 self.E.set_demography(pkg.make_demography())
+                if phases & pkg.CrimeEngine.PHASE_LABOUR:
+                    self.E.set_labour(pkg.make_labour())
                 self.E.set_phases(phases)
             self.packed = [pkg.CrimeEngine.pack_state(s, pinned=True) for s in states]
             self.params = [pkg.make_params(e[1]) for e in ents]
@@ -365,6 +371,11 @@ def main():
                 E.upload_packed(r, self.packed[a])     # queued; E.sync() / the run's own synchronisation wait for them
                 if ents[a][3]:
                     E.set_crime_multiplier(ents[a][3], r)
+            if self.phases & pkg.CrimeEngine.PHASE_LABOUR:   # outside every timed region (state resident when the clock starts)
+                E.sync()
+                for r, a in enumerate(self.assign):
+                    if "max_education_level" in ents[a][0]:
+                        E.upload_education(r, ents[a][0]["max_education_level"], ents[a][0]["school_level"])
 
         def time_resident(self, warmup, steps, clk=True):
             E, times, launches = self.E, [], 0
@@ -516,26 +527,6 @@ def main():
         SW.E.close()
         del SW
 
-    # ---- config 5 with the seven step() phases that run on the device switched on (wedding, retire_persons, make_baby,
-    # remove_excess_friends / _professional_links, make_friends, make_people_die): births and deaths keep the age
-    # structure and the criminal layer from drifting the way the crime path alone lets them over 480 ticks
-    demog = None
-    if args.config == 5 and not args.no_sweep:
-        DW = Workload(homogeneous_config(R), phases=pkg.CrimeEngine.PHASE_ALL)
-        dms, dval, dl = DW.time_resident(1, max(1, min(args.steps, 2)))
-        cn0, _ = DW.E.counters()
-        dkp, _ = kernel_pass(DW)
-        cn, _ = DW.E.counters()
-        cn = cn - cn0 * (cn0 > 0) * np.isin(np.arange(cn.shape[1]), [0, 16, 17, 19])[None, :]   # cumulative counters: this pass only
-        demog = {"phases": "wedding, retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, "
-                           "make_friends, make_people_die (model.py:271-284) every tick, on the device",
-                 "value": dval, "ms_per_step": dms, "gpu_launches": int(dl), "kernel_ms": dkp["kernel_ms"],
-                 "roofline": dkp["roofline"], "errors": int((cn[:, 9] != 0).sum()),
-                 "born_per_run": float(cn[:, 17].mean()), "deceased_per_run": float(cn[:, 16].mean()),
-                 "crimes_per_run": float(cn[:, 0].mean()), "weddings_per_run": float(cn[:, 19].mean()), "note": "value counts the agents of the initial state x ticks, like the headline"}
-        DW.E.close()
-        del DW
-
     # ---- single-run latency (batch of one): the "one 10k-agent run" figure
     single = None
     if rank == 0:
@@ -553,6 +544,42 @@ def main():
         single = {"agent_ticks_per_s": a1 * T / (min(ts[1:]) / 1e3), "ms_per_run": min(ts[1:]),
                   "us_per_tick": 1e3 * min(ts[1:]) / T, "agents": a1}
         S1.E.close()
+
+    # ---- config 5 with the step() phases that run on the device switched on: the yearly labour-status block (graduate_and_
+    # enter_jobmarket, update_unemployment_status) and, every tick, wedding, retire_persons, make_baby, remove_excess_friends /
+    # _professional_links, make_friends, make_people_die: births and deaths keep the age structure and the criminal layer from
+    # drifting the way the crime path alone lets them over 480 ticks.  Measured last and contained: a failure here is reported in
+    # the line, the headline figures above are already taken.
+    demog = None
+    if args.config == 5 and not args.no_sweep:
+        try:
+            dcfg = homogeneous_config(R)
+            has_edu = "max_education_level" in dcfg["entries"][0][0]
+            DW = Workload(dcfg, phases=pkg.CrimeEngine.PHASE_EVERY if has_edu else pkg.CrimeEngine.PHASE_ALL)
+            dms, dval, dl = DW.time_resident(1, max(1, min(args.steps, 2)))
+            cn0, _ = DW.E.counters()
+            dkp, _ = kernel_pass(DW)
+            cn, _ = DW.E.counters()
+            cn = cn - cn0 * (cn0 > 0) * np.isin(np.arange(cn.shape[1]), [0, 16, 17, 19])[None, :]   # cumulative counters: this pass only
+            cols0 = DW.E.download_agents(0)
+            al0 = cols0["alive"] > 0
+            demog = {"phases": ("graduate_and_enter_jobmarket + update_unemployment_status on the yearly ticks (model.py:251-256); " if has_edu else "") +
+                               "wedding, retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, "
+                               "make_friends, make_people_die (model.py:271-284) every tick, on the device",
+                     "phase_mask": int(DW.phases),
+                     "value": dval, "ms_per_step": dms, "gpu_launches": int(dl), "kernel_ms": dkp["kernel_ms"],
+                     "roofline": dkp["roofline"], "errors": int((cn[:, 9] != 0).sum()),
+                     "born_per_run": float(cn[:, 17].mean()), "deceased_per_run": float(cn[:, 16].mean()),
+                     "crimes_per_run": float(cn[:, 0].mean()), "weddings_per_run": float(cn[:, 19].mean()),
+                     "education_level_mean_after_run": float(cols0["education_level"][al0].mean()),
+                     "students_after_run": int((cols0["has_school"][al0] > 0).sum()),
+                     "note": "value counts the agents of the initial state x ticks, like the headline"}
+            DW.E.close()
+            del DW
+        except Exception as ex:   # noqa: BLE001
+            if dist is not None:   # the other ranks wait in this block's collectives: fail the job rather than hang it
+                raise
+            demog = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     if rank == 0:
         line = {

@@ -246,9 +246,10 @@ typedef struct poc_demography {
 /* make_baby, make_friends, make_people_die; then retire_persons (model.py:1538-1551), remove_excess_friends (:629-643),
  * remove_excess_professional_links (:646-659) and wedding (:368-402) */
 enum { POC_PHASE_BABY = 1, POC_PHASE_FRIENDS = 2, POC_PHASE_DIE = 4, POC_PHASE_RETIRE = 8, POC_PHASE_XFRIENDS = 16,
-       POC_PHASE_XPROF = 32, POC_PHASE_WEDDING = 64, POC_PHASE_ALL = 127 };
+       POC_PHASE_XPROF = 32, POC_PHASE_WEDDING = 64, POC_PHASE_ALL = 127 /* the seven phases of every tick */,
+       POC_PHASE_LABOUR = 128 /* the yearly labour-status block, below */, POC_PHASE_EVERY = 255 };
 int poc_set_demography(poc_ctx *ctx, const poc_demography *d);
-/* which of the phases poc_run_ticks runs after commit_crimes every tick, in the order of model.py:273-284 (default 0).
+/* which of the phases poc_run_ticks runs every tick, in the order of model.py:248-284 (default 0).
  * max_agents / max_static_entries of the ctx must leave room for the newborns and their links. */
 int poc_set_phases(poc_ctx *ctx, int phase_mask);
 /* one phase for all replicas on the current state (stage hook for the parity tests) */
@@ -256,6 +257,33 @@ int poc_run_phase(poc_ctx *ctx, int phase, int tick, const uint64_t *philox_keys
 /* Person.number_of_children (entities.py:75): defaults to the number of offspring links at upload */
 int poc_upload_children(poc_ctx *ctx, int replica, const int32_t *n_children);
 int poc_download_children(poc_ctx *ctx, int replica, int32_t *n_children);
+/* ---- the yearly labour-status block of ProtonOC.step (model.py:248-256; SURVEY.md 8(f) "then" rows) ------------------
+ * POC_PHASE_LABOUR = graduate_and_enter_jobmarket (model.py:1351-1380 with Person.enroll_to_school / leave_school,
+ * entities.py:292-308, 389-395) and the update_unemployment_status loop written out in step() (model.py:252-256,
+ * entities.py:397-411), on the ticks where the reference runs them (tick % ticks_per_year == 0 or tick == 1), after the
+ * tendencies and the crime multiplier of that tick.  Both change the agent's own education / job / wealth level and
+ * school membership only (enroll_to_school adds no links and the identity of the school matters to nothing on this
+ * path), so a thread per agent with its own Philox draws is the reference's loop up to the random stream. */
+typedef struct poc_labour {
+    int32_t n_levels;            /* education levels = rows of schools.csv (model.py:953-965) */
+    int32_t primary_age;         /* education_levels[1][0] */
+    int32_t end_age[8];          /* [level] education_levels[level][1], level 1..n_levels */
+    int32_t work_n[8][2];        /* work_status_by_edu_lvl[education level][male] (model.py:166-167): rows, */
+    int32_t work_val[8][2][8];   /*   work status of each row, */
+    double work_cdf[8][2][8];    /*   choice CDF of the rates (extra.pick_from_pair_list, extra.py:140-149) */
+    int32_t wealth_n[8][2];      /* wealth_quintile_by_work_status[work status][male] (model.py:168-169) */
+    int32_t wealth_val[8][2][8];
+    double wealth_cdf[8][2][8];
+    double inactive[2][128];     /* labour_status_by_age_and_sex[male][age] (model.py:180-181); < 0: no row */
+    uint8_t range_age[2][128];   /* age is a key of labour_status_range[male] (model.py:182-183, 255) */
+} poc_labour;
+int poc_set_labour(poc_ctx *ctx, const poc_labour *tables);
+/* Person.max_education_level (entities.py:63) and the diploma level of Person.my_school (0 = none; read only while the
+ * agent's has_school is set) for every agent slot of a replica; both default to 0.  Newborns inherit the father's (else
+ * the mother's) max_education_level on the device (entities.py:646-649). */
+int poc_upload_education(poc_ctx *ctx, int replica, const int8_t *max_education_level, const int8_t *school_level);
+int poc_download_education(poc_ctx *ctx, int replica, int8_t *max_education_level, int8_t *school_level);
+int poc_sizeof_labour(void);
 /* agent slots of a replica (grows with births) */
 int poc_n_agents(poc_ctx *ctx, int replica, int32_t *out);
 

@@ -37,6 +37,26 @@ def export_setup(name, n_agents, seed, overrides=None, steps=0):
         path, os.path.getsize(path) / 1024, time.time() - t, int(st["oc_member"].sum()), int(st["facilitator"].sum())))
 
 
+def export_education_sidecar(name, n_agents, seed, steps):
+    """The two columns the yearly labour-status block reads (max_education_level, school_level) for a state fixture exported
+    before they were part of export_state: the reference run is repeated (it is bit-reproducible), every other column is
+    checked against the fixture, and the two columns go to <name>_edu.npz."""
+    ref_model, _, _ = H.load_reference()
+    model = ref_model.ProtonOC(seed=seed)
+    model.setup(n_agents)
+    for _ in range(steps):
+        model.step()
+    st = H.export_state(model)
+    old = np.load(os.path.join(OUT, name + ".npz"))
+    for k, v in st.items():
+        if "pre_" + k not in old.files:   # columns added to export_state after the fixture was written
+            continue
+        assert np.array_equal(old["pre_" + k], v), k
+    path = os.path.join(OUT, name + "_edu.npz")
+    np.savez_compressed(path, pre_max_education_level=st["max_education_level"], pre_school_level=st["school_level"])
+    print("wrote", path, os.path.getsize(path))
+
+
 def export_sweep_pool(variant: str, seeds):
     """Config 5 (override-mode ensemble): the reference's own setup states at 10,000 agents for the three
     samples/sample_json.json variants x a pool of seeds -- what bench.py --sweep draws its 1,024 replicas from."""
@@ -60,6 +80,13 @@ def main(argv):
         return
     if len(argv) > 2 and argv[1] == "pool":   # python -m oracle.make_states pool <variant> <seed> [<seed> ...]
         export_sweep_pool(argv[2], [int(x) for x in argv[3:]])
+        return
+    if len(argv) > 1 and argv[1] == "edu":   # python -m oracle.make_states edu state_n10000_s42_t13 10000 42 12
+        export_education_sidecar(argv[2], int(argv[3]), int(argv[4]), int(argv[5]))
+        return
+    if len(argv) > 1 and argv[1] == "distdemog4":   # + graduate_and_enter_jobmarket (update_unemployment_status always ran)
+        export_distribution_demog("distdemog4_n1000_s42", ticks=60, keep=DEMOG_KEEP2 + ["wedding", "graduate_and_enter_jobmarket"],
+                                  cols=DEMOG_COLS + LABOUR_COLS, hists=True)
         return
     only = argv[1] if len(argv) > 1 else None
     cases = [("state_n3000_s42_baseline", 3000, 42, None), ("state_n10000_s42_baseline", 10000, 42, None)]
@@ -97,7 +124,23 @@ DEMOG_COLS = ["number_crimes", "current_oc_members", "people_jailed", "tot_crimi
               "tot_professional_link", "tot_partner_link", "tot_school_link", "employed", "number_weddings"]
 
 
-def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42, n_runs=30, ticks=48, keep=None):
+LABOUR_COLS = ["education_level_mean", "education_level_sd", "number_students"]
+
+
+def _hists(model):
+    """job / education / wealth / school level counts over the living (0..7 each), and the living students"""
+    ag = model.schedule.agents
+    h = np.zeros((4, 8), dtype=np.float64)
+    for a in ag:
+        h[0, int(a.job_level)] += 1
+        h[1, int(a.education_level)] += 1
+        h[2, int(a.wealth_level)] += 1
+        h[3, int(a.my_school.diploma_level) if a.my_school is not None else 0] += 1
+    return h
+
+
+def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42, n_runs=30, ticks=48, keep=None, cols=None,
+                              hists=False):
     """Whole-run distribution fixture for the SURVEY.md 8(f) rows built on the device: the reference continued from ONE
     setup state with `n_runs` RNG streams, with its own make_baby / make_friends / make_people_die and the crime path
     active and every other phase of step() replaced by a no-op (`refdemog_*`).  Per tick: DEMOG_COLS."""
@@ -106,8 +149,9 @@ def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42
         # the yearly hiring loop is written out inside step() (model.py:257-269), not a phase that can be switched off: its
         # find_job would refill the jobs the retired leave and add professional links; with find_job a no-op the loop does nothing
         ref_entities.Person.find_job = lambda self: None
+    cols = cols or DEMOG_COLS
     d = {}
-    rows_all = []
+    rows_all, hist_all = [], []
     for j in range(n_runs):
         model = ref_model.ProtonOC(seed=seed)
         model.setup(n_agents)
@@ -125,12 +169,16 @@ def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42
         rows = []
         for _ in range(ticks):
             model.step()
-            rows.append([float(getattr(model, c)) for c in DEMOG_COLS])
+            rows.append([float(getattr(model, c)) for c in cols])
         rows_all.append(np.array(rows, dtype=np.float64))
-        print("refdemog run", j, rows_all[-1][-1][:12])
+        if hists:
+            hist_all.append(_hists(model))
+        print("refdemog run", j, rows_all[-1][-1][:12], flush=True)
     arr = np.array(rows_all)
-    for i, col in enumerate(DEMOG_COLS):
+    for i, col in enumerate(cols):
         d["refdemog_" + col] = arr[:, :, i]
+    if hists:   # [run][job, education, wealth, school level][value] after the last tick
+        d["refdemog_final_hists"] = np.array(hist_all)
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **d)
     print("wrote", path)

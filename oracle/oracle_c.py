@@ -130,6 +130,21 @@ def make_demog(nat_propensity_m: float = 1.0, nat_propensity_sigma: float = 0.25
     return d
 
 
+class Labour(C.Structure):
+    """Mirror of orc_labour (hotpath.c); same layout as poc_labour."""
+    _fields_ = [("n_levels", C.c_int32), ("primary_age", C.c_int32), ("end_age", C.c_int32 * 8),
+                ("work_n", (C.c_int32 * 2) * 8), ("work_val", ((C.c_int32 * 8) * 2) * 8), ("work_cdf", ((C.c_double * 8) * 2) * 8),
+                ("wealth_n", (C.c_int32 * 2) * 8), ("wealth_val", ((C.c_int32 * 8) * 2) * 8),
+                ("wealth_cdf", ((C.c_double * 8) * 2) * 8),
+                ("inactive", (C.c_double * 128) * 2), ("range_age", (C.c_uint8 * 128) * 2)]
+
+
+def make_labour(**tables_) -> Labour:
+    """The tables of the yearly labour-status block; defaults = the Palermo tables (pyproton_oc_b200.tables)."""
+    from pyproton_oc_b200.params import fill_labour
+    return fill_labour(Labour(), **tables_)
+
+
 _lib = None
 
 
@@ -195,6 +210,13 @@ def lib():
         for fn in (L.orc_remove_excess_friends, L.orc_remove_excess_professional):
             fn.restype = C.c_int32
             fn.argtypes = [C.c_void_p, C.c_int32, C.c_uint64]
+        L.orc_sizeof_labour.restype = C.c_int32
+        L.orc_set_labour.argtypes = [C.c_void_p, C.POINTER(Labour)]
+        L.orc_get_education.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_education.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_labour_yearly.restype = C.c_int32
+        L.orc_labour_yearly.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_uint64]
+        assert L.orc_sizeof_labour() == C.sizeof(Labour)
         L.orc_run_ticks_phases.restype = C.c_int32
         L.orc_run_ticks_phases.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_uint64, C.POINTER(C.c_double), C.c_void_p]
@@ -287,6 +309,8 @@ class OracleState:
             rp[l], cp[l] = r.ctypes.data, c.ctypes.data
         co = np.ascontiguousarray(st["co_off"], dtype=np.int32)
         self.h = self.L.orc_create(self.n, C.byref(cols), rp, cp, co.ctypes.data)
+        if "max_education_level" in st:
+            self.set_education(st["max_education_level"], st["school_level"])
 
     def close(self):
         if self.h:
@@ -345,15 +369,39 @@ class OracleState:
     def remove_excess_professional(self, tick, key):
         return int(self.L.orc_remove_excess_professional(self.h, tick, key))
 
+    # ---- the yearly labour-status block (model.py:251-256)
+    def set_labour(self, lb):
+        self.L.orc_set_labour(self.h, C.byref(lb))
+
+    def set_education(self, max_edu, school_level):
+        self._refresh_n()
+        a = np.ascontiguousarray(max_edu, dtype=np.int8)
+        b = np.ascontiguousarray(school_level, dtype=np.int8)
+        assert len(a) == self.n and len(b) == self.n
+        self.L.orc_set_education(self.h, a.ctypes.data, b.ctypes.data)
+
+    def education(self):
+        self._refresh_n()
+        a, b = np.empty(self.n, np.int8), np.empty(self.n, np.int8)
+        self.L.orc_get_education(self.h, a.ctypes.data, b.ctypes.data)
+        return a, b
+
+    def labour_yearly(self, p, dm, tick, key):
+        """graduate_and_enter_jobmarket + update_unemployment_status: (graduations, status draws)"""
+        r = int(self.L.orc_labour_yearly(self.h, C.byref(p), C.byref(dm), tick, key))
+        if r < 0:
+            raise RuntimeError("oracle: set_labour first")
+        return r % 65536, r // 65536
+
     def run_ticks_phases(self, p, dm, phases: int, tick0: int, n_ticks: int, philox_key: int, crime_multiplier: float = 0.0):
         """Hot path + the demography phases in `phases` (1 make_baby, 2 make_friends, 4 make_people_die, 8 retire_persons,
-        16 remove_excess_friends, 32 remove_excess_professional_links)."""
+        16 remove_excess_friends, 32 remove_excess_professional_links, 64 wedding, 128 the yearly labour-status block)."""
         mult = C.c_double(crime_multiplier)
         totals = np.zeros(6, dtype=np.int64)
         rc = self.L.orc_run_ticks_phases(self.h, C.byref(p), C.byref(dm), phases, tick0, n_ticks, philox_key, C.byref(mult),
                                          totals.ctypes.data)
         if rc:
-            raise RuntimeError("oracle: slot capacity exhausted (reserve more)")
+            raise RuntimeError("oracle: set_labour first" if rc == -2 else "oracle: slot capacity exhausted (reserve more)")
         self._refresh_n()
         return float(mult.value), totals
 

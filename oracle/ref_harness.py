@@ -139,6 +139,10 @@ def export_state(model, extra_agents=()) -> Dict[str, np.ndarray]:
     st["retired"] = np.array([bool(a.retired) for a in agents], dtype=np.uint8)
     st["has_job"] = np.array([a.my_job is not None for a in agents], dtype=np.uint8)
     st["has_school"] = np.array([a.my_school is not None for a in agents], dtype=np.uint8)
+    # graduate_and_enter_jobmarket (model.py:1351-1380) reads these two; a school's identity never matters to it
+    st["max_education_level"] = np.array([int(a.max_education_level) for a in agents], dtype=np.int8)
+    st["school_level"] = np.array([int(a.my_school.diploma_level) if a.my_school is not None else 0 for a in agents],
+                                  dtype=np.int8)
     st["target_of_intervention"] = np.array([bool(a.target_of_intervention) for a in agents], dtype=np.uint8)
     st["num_crimes_committed"] = np.array([int(a.num_crimes_committed) for a in agents], dtype=np.int32)
     st["num_crimes_committed_this_tick"] = np.array(

@@ -29,6 +29,15 @@ class Demography(C.Structure):
                 ("retirement_age", C.c_int32), ("_pad", C.c_int32), ("weddings_mean", C.c_double)]
 
 
+class Labour(C.Structure):
+    """poc_labour (include/protonoc_b200.h): the tables of the yearly labour-status block (model.py:251-256, 1351-1380)."""
+    _fields_ = [("n_levels", C.c_int32), ("primary_age", C.c_int32), ("end_age", C.c_int32 * 8),
+                ("work_n", (C.c_int32 * 2) * 8), ("work_val", ((C.c_int32 * 8) * 2) * 8), ("work_cdf", ((C.c_double * 8) * 2) * 8),
+                ("wealth_n", (C.c_int32 * 2) * 8), ("wealth_val", ((C.c_int32 * 8) * 2) * 8),
+                ("wealth_cdf", ((C.c_double * 8) * 2) * 8),
+                ("inactive", (C.c_double * 128) * 2), ("range_age", (C.c_uint8 * 128) * 2)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("n_cells", C.c_int32), ("cell_male", C.c_int32 * MAX_CELLS), ("cell_age_from", C.c_int32 * MAX_CELLS),
@@ -124,6 +133,10 @@ SYMBOLS = {
     "poc_run_phase": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "poc_upload_children": (C.c_int, [_P, C.c_int, _P]),
     "poc_download_children": (C.c_int, [_P, C.c_int, _P]),
+    "poc_set_labour": (C.c_int, [_P, _P]),
+    "poc_upload_education": (C.c_int, [_P, C.c_int, _P, _P]),
+    "poc_download_education": (C.c_int, [_P, C.c_int, _P, _P]),
+    "poc_sizeof_labour": (C.c_int, []),
     "poc_n_agents": (C.c_int, [_P, C.c_int, _P]),
     "poc_packed_size": (C.c_int64, [C.c_int, _P]),
     "poc_pack_state": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int64]),
@@ -168,7 +181,8 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError here means the library does not match the header
             fn.restype, fn.argtypes = res, args
-        if L.poc_sizeof_params() != C.sizeof(Params) or L.poc_sizeof_tick_out() != C.sizeof(TickOut):
+        if L.poc_sizeof_params() != C.sizeof(Params) or L.poc_sizeof_tick_out() != C.sizeof(TickOut) or \
+                L.poc_sizeof_labour() != C.sizeof(Labour):
             raise PocError("ctypes structs out of sync with libprotonoc_b200.so")
         _lib = L
     return _lib

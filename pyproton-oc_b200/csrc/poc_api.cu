@@ -87,6 +87,8 @@ struct poc_ctx {
     int phases = 0;                 // demography phases poc_run_ticks runs per tick (poc_set_phases)
     DevDemog *d_demog = nullptr;
     bool demog_set = false;
+    DevLabour *d_labour = nullptr;
+    bool labour_set = false;
 };
 
 static thread_local std::string g_err;
@@ -255,6 +257,8 @@ static int ctx_init(poc_ctx *ctx, int n_replicas, int max_agents, int64_t max_st
     d.DPcap = std::max(4 * N, 16384);
     DA(d.dm_pairs, (size_t)R * d.DPcap); DA(d.dm_defer, (size_t)R * 1024);
     DA(ctx->d_demog, 1); d.demog = ctx->d_demog;
+    DA(ctx->d_labour, 1); d.labour = ctx->d_labour;
+    DA(d.edu2, RN);
     DA(d.params, R); DA(d.crime_mult, R); DA(d.counters, (size_t)R * CN_COUNT); DA(d.edges, R); DA(d.stats, (size_t)R * ST_COUNT); DA(d.layer_tot, (size_t)R * 8);
     DA(d.cell_members, RN); DA(d.cell_off, (size_t)R * (POC_MAX_CELLS + 1)); DA(d.cell_strict, (size_t)R * POC_MAX_CELLS);
     DA(d.cdf, RN); DA(d.cdf_valid, R); DA(d.cdf_nz, (size_t)R * POC_MAX_CELLS);
@@ -920,9 +924,14 @@ static int launch_commit(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, bool cel
 }
 
 // the demography phases of one tick for one replica range (kernels in poc_demog.cuh); n = agent slots the grids cover
-static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask, int n) {
+static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask, int n, int force_labour = 0) {
     if (!mask || !n) return POC_OK;
     if (!ctx->demog_set) return fail(ctx, POC_ERR_STATE, "demography phases requested before poc_set_demography");
+    if (mask & POC_PHASE_LABOUR) {   // model.py:251-256 (after the tendencies and the multiplier of a yearly tick)
+        if (!ctx->labour_set) return fail(ctx, POC_ERR_STATE, "POC_PHASE_LABOUR requested before poc_set_labour");
+        Timed t(ctx, TM_OTHER, s);
+        k_labour<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, force_labour);
+    }
     if (mask & POC_PHASE_WEDDING) {   // model.py:271 (before the crimes of the tick)
         Timed t(ctx, TM_OTHER, s);
         k_wedding<<<D.Rg, 256, 3 * (((size_t)D.Ncap + 31) / 32) * sizeof(unsigned), s>>>(D);
@@ -983,21 +992,68 @@ int poc_set_demography(poc_ctx *ctx, const poc_demography *dm) {
 
 int poc_set_phases(poc_ctx *ctx, int mask) {
     CHECK_CTX();
-    if (mask & ~POC_PHASE_ALL) return fail(ctx, POC_ERR_ARG, "poc_set_phases: unknown phase");
+    if (mask & ~POC_PHASE_EVERY) return fail(ctx, POC_ERR_ARG, "poc_set_phases: unknown phase");
     if (mask && !ctx->demog_set) return fail(ctx, POC_ERR_STATE, "poc_set_phases: poc_set_demography first");
+    if ((mask & POC_PHASE_LABOUR) && !ctx->labour_set) return fail(ctx, POC_ERR_STATE, "poc_set_phases: poc_set_labour first");
     ctx->phases = mask;
     return POC_OK;
 }
 
 int poc_run_phase(poc_ctx *ctx, int phase, int tick, const uint64_t *keys) {
     CHECK_CTX();
-    if (phase <= 0 || (phase & ~POC_PHASE_ALL) || (phase & (phase - 1))) return fail(ctx, POC_ERR_ARG, "poc_run_phase: one phase at a time");
+    if (phase <= 0 || (phase & ~POC_PHASE_EVERY) || (phase & (phase - 1))) return fail(ctx, POC_ERR_ARG, "poc_run_phase: one phase at a time");
     if (keys) CU(cudaMemcpyAsync(ctx->d.philox_key, keys, sizeof(uint64_t) * ctx->d.R, cudaMemcpyHostToDevice, ctx->stream));
     TickInfo t{tick, ctx->epoch, 0, 0};
     CU(cudaMemcpyAsync(ctx->d_ti, &t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = launch_phases(ctx, ctx->d, ctx->stream, phase, ctx->d.Ncap);
+    int rc = launch_phases(ctx, ctx->d, ctx->stream, phase, ctx->d.Ncap, 1);   // the hook runs the labour block whatever the tick
     if (rc) return rc;
     return refresh_counts(ctx);
+}
+
+int poc_sizeof_labour(void) { return (int)sizeof(poc_labour); }
+
+int poc_set_labour(poc_ctx *ctx, const poc_labour *lb) {
+    CHECK_CTX();
+    static_assert(sizeof(poc_labour) == sizeof(DevLabour), "poc_labour / DevLabour out of sync");
+    if (!lb || lb->n_levels < 1 || lb->n_levels > 7) return fail(ctx, POC_ERR_ARG, "poc_set_labour: bad argument");
+    for (int k = 0; k < 8; k++)
+        for (int m = 0; m < 2; m++) {
+            if (lb->work_n[k][m] < 0 || lb->work_n[k][m] > 8 || lb->wealth_n[k][m] < 0 || lb->wealth_n[k][m] > 8)
+                return fail(ctx, POC_ERR_ARG, "poc_set_labour: table too long");
+            for (int i = 0; i < lb->work_n[k][m]; i++)      // a work status indexes the wealth table, both go into 4-bit fields
+                if (lb->work_val[k][m][i] < 0 || lb->work_val[k][m][i] > 7) return fail(ctx, POC_ERR_ARG, "poc_set_labour: work status out of range");
+            for (int i = 0; i < lb->wealth_n[k][m]; i++)
+                if (lb->wealth_val[k][m][i] < 0 || lb->wealth_val[k][m][i] > 15) return fail(ctx, POC_ERR_ARG, "poc_set_labour: wealth level out of range");
+        }
+    CU(cudaMemcpyAsync(ctx->d_labour, lb, sizeof(DevLabour), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->labour_set = true;
+    return POC_OK;
+}
+
+int poc_upload_education(poc_ctx *ctx, int replica, const int8_t *max_edu, const int8_t *school_level) {
+    CHECK_CTX();
+    if (!max_edu || !school_level || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_upload_education: bad argument");
+    const int n = ctx->h_nagents[replica];
+    std::vector<uint8_t> h((size_t)n);
+    for (int a = 0; a < n; a++) {
+        if (max_edu[a] < 0 || max_edu[a] > 15 || school_level[a] < 0 || school_level[a] > 15) return fail(ctx, POC_ERR_ARG, "poc_upload_education: level out of range");
+        h[a] = (uint8_t)(max_edu[a] | (school_level[a] << 4));
+    }
+    CU(cudaMemcpyAsync(ctx->d.edu2 + (size_t)replica * ctx->d.Ncap, h.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return POC_OK;
+}
+
+int poc_download_education(poc_ctx *ctx, int replica, int8_t *max_edu, int8_t *school_level) {
+    CHECK_CTX();
+    if (!max_edu || !school_level || replica < 0 || replica >= ctx->d.R) return fail(ctx, POC_ERR_ARG, "poc_download_education: bad argument");
+    const int n = ctx->h_nagents[replica];
+    std::vector<uint8_t> h((size_t)n);
+    CU(cudaMemcpyAsync(h.data(), ctx->d.edu2 + (size_t)replica * ctx->d.Ncap, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int a = 0; a < n; a++) { max_edu[a] = (int8_t)(h[a] & 15); school_level[a] = (int8_t)(h[a] >> 4); }
+    return POC_OK;
 }
 
 int poc_upload_children(poc_ctx *ctx, int replica, const int32_t *nc) {
@@ -1146,12 +1202,14 @@ static int run_ticks_impl(poc_ctx *ctx, int tick0, int n_ticks, const uint64_t *
                 if (rc2) return rc2;
                 rc2 = launch_tendency(ctx, D, s, 2);
                 if (rc2) return rc2;
+                rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_LABOUR, n);    // model.py:251-256
+                if (rc2) return rc2;
                 rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_WEDDING, n);   // model.py:271
                 if (rc2) return rc2;
                 rc2 = launch_commit(ctx, D, s, true, false, (k == 0 && g + 1 < G) ? ctx->gstag[g] : nullptr, 0);
                 if (rc2) return rc2;
                 // model.py:274-278: retire_persons, make_baby, remove_excess_friends / _professional_links, make_friends
-                rc2 = launch_phases(ctx, D, s, ctx->phases & ~(POC_PHASE_DIE | POC_PHASE_WEDDING), n);
+                rc2 = launch_phases(ctx, D, s, ctx->phases & ~(POC_PHASE_DIE | POC_PHASE_WEDDING | POC_PHASE_LABOUR), n);
                 if (rc2) return rc2;
                 if (n) { Timed t(ctx, TM_OTHER, s); k_end_tick<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, 0); }
                 rc2 = launch_phases(ctx, D, s, ctx->phases & POC_PHASE_DIE, n);   // model.py:284

@@ -156,6 +156,10 @@ struct DevCtx {
     unsigned long long *dm_pairs;   // [R][DPcap] directed entries to add: u << 40 | v << 8 | layer mask
     unsigned long long *dm_defer;   // [R][1024] friendships whose reverse entry has no slot yet
     int DPcap;
+    // the yearly labour-status block (model.py:251-256): tables, one set for the ctx; per agent max_education_level (low nibble)
+    // and the diploma level of my_school (high nibble, read only while F_HASSCHOOL is set)
+    const struct DevLabour *labour;
+    uint8_t *edu2;                  // [R][Ncap]
     int scr_slots;
     int slot_stride;                // scratch slot of block bx of replica r = r * slot_stride + bx in EVERY traversal kernel: the
                                     // replica groups run concurrently on their own streams and must not meet in a slot
@@ -173,9 +177,19 @@ struct DevDemog {
     double weddings_mean;     // number_weddings_mean (model.py:184-186)
 };
 
+struct DevLabour {            // = poc_labour (include/protonoc_b200.h)
+    int n_levels, primary_age;
+    int end_age[8];
+    int work_n[8][2]; int work_val[8][2][8]; double work_cdf[8][2][8];
+    int wealth_n[8][2]; int wealth_val[8][2][8]; double wealth_cdf[8][2][8];
+    double inactive[2][128];
+    uint8_t range_age[2][128];
+};
+
 // ---- Philox4x32-10 (Salmon et al. SC'11) -----------------------------------------------------------
 enum { ST_CRIME = 0, ST_FAC = 1, ST_ARREST_N = 2, ST_ARREST = 3, ST_SENT = 4, ST_DIE = 5, ST_FACREP = 6, ST_BABY = 7,
-       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10, ST_XFRIEND = 11, ST_XPROF = 12, ST_WED_N = 13, ST_WED_EGO = 14, ST_WED_PICK = 15 };
+       ST_BABYATTR = 8, ST_FRIEND_N = 9, ST_FRIEND = 10, ST_XFRIEND = 11, ST_XPROF = 12, ST_WED_N = 13, ST_WED_EGO = 14, ST_WED_PICK = 15,
+       ST_GRAD = 16, ST_UNEMP = 17 };
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
 #pragma unroll

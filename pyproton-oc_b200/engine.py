@@ -226,15 +226,35 @@ class CrimeEngine:
 
     # ------------------------------------------------------------------ demography phases
     PHASE_BABY, PHASE_FRIENDS, PHASE_DIE, PHASE_RETIRE, PHASE_XFRIENDS, PHASE_XPROF, PHASE_WEDDING, PHASE_ALL = 1, 2, 4, 8, 16, 32, 64, 127
+    # the yearly labour-status block (graduate_and_enter_jobmarket + update_unemployment_status, model.py:251-256): needs set_labour
+    PHASE_LABOUR, PHASE_EVERY = 128, 255
 
     def set_demography(self, d):
         self._ck(self.L.poc_set_demography(self.h, C.byref(d)))
 
     def set_phases(self, mask: int):
         """Which of make_baby (1) / make_friends (2) / make_people_die (4) / retire_persons (8) / remove_excess_friends (16) /
-        remove_excess_professional_links (32) / wedding (64) run_ticks runs every tick, in the order of ProtonOC.step (default 0)."""
+        remove_excess_professional_links (32) / wedding (64) run_ticks runs every tick and whether it runs the labour-status block
+        (128) on the yearly ticks, in the order of ProtonOC.step (default 0)."""
         self._ck(self.L.poc_set_phases(self.h, int(mask)))
         self._phases = int(mask)
+
+    def set_labour(self, lb):
+        """Tables of PHASE_LABOUR (params.make_labour)."""
+        self._ck(self.L.poc_set_labour(self.h, C.byref(lb)))
+
+    def upload_education(self, replica: int, max_education_level, school_level):
+        """Person.max_education_level and the diploma level of Person.my_school (0 = none) per agent slot; without this call
+        both are 0 (nobody continues past the school he is in)."""
+        a = np.ascontiguousarray(max_education_level, dtype=np.int8)
+        b = np.ascontiguousarray(school_level, dtype=np.int8)
+        assert len(a) == self.n_agents[replica] and len(b) == self.n_agents[replica]
+        self._ck(self.L.poc_upload_education(self.h, replica, a.ctypes.data, b.ctypes.data))
+
+    def download_education(self, replica: int = 0):
+        a, b = np.zeros(self.n_agents[replica], np.int8), np.zeros(self.n_agents[replica], np.int8)
+        self._ck(self.L.poc_download_education(self.h, replica, a.ctypes.data, b.ctypes.data))
+        return a, b
 
     def _refresh_counts(self):
         v = C.c_int32(0)

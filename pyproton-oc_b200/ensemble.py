@@ -103,8 +103,10 @@ def gpu_batch_runner(device: int = 0, template: Optional[Dict[str, np.ndarray]] 
                 E.set_params(m._params(), replica=r)
                 E.upload_state(r, st, wait=False)
             E.sync()   # input errors of the queued uploads surface here
+            E.set_labour(m0._labour())   # likewise one set of labour-status tables per engine
             for r, st in enumerate(states):
                 E.upload_children(r, st["number_of_children"])
+                E.upload_education(r, st["max_education_level"], st["school_level"])
             E.set_phases(phases)
             E.crime_multiplier()   # ProtonOC.setup: model.py:1029-1030
             E.tendency()

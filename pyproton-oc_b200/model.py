@@ -28,7 +28,7 @@ import pandas as pd
 
 from . import synth, tables
 from .engine import LAYER_NAMES, REPORTER_NAMES, CrimeEngine
-from .params import make_demography, make_params
+from .params import make_demography, make_labour, make_params
 
 free_parameters = ["migration_on", "initial_agents", "num_ticks", "intervention",
                    "max_accomplice_radius", "number_arrests_per_year",
@@ -94,7 +94,9 @@ _COLS = {"alive": np.uint8, "age": np.int32, "birth_tick": np.int32, "male": np.
          "has_school": np.uint8, "target_of_intervention": np.uint8, "num_crimes_committed": np.int32,
          "num_crimes_committed_this_tick": np.int32, "criminal_tendency": np.float64,
          "sentence_countdown": np.float64, "new_recruit": np.int32, "arrest_weight": np.float64, "father": np.int32,
-         "number_of_children": np.int32}
+         "number_of_children": np.int32,
+         # graduate_and_enter_jobmarket (model.py:1351-1380): Person.max_education_level, diploma level of Person.my_school
+         "max_education_level": np.int8, "school_level": np.int8}
 _COL_DEFAULTS = {"alive": 1, "wealth_level": 1, "new_recruit": -2, "father": -1}
 # Person attribute -> state column
 _ATTR = {"gender_is_male": "male", "num_crimes_committed": "num_crimes_committed",
@@ -280,12 +282,12 @@ class _DataCollector:
 
 
 class ProtonOC:
-    out_of_scope_phases = ["interventions (family / social / welfare)", "graduate_and_enter_jobmarket", "find_job",
-                           "update_unemployment_status", "let_migrants_in", "return_kids"]
-    # the phases of step() besides the crime path that run on the device (CrimeEngine.PHASE_*): wedding,
-    # retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, make_friends, make_people_die, in
-    # the reference's order (model.py:271-284).  0 = the crime path alone.
-    device_phases: int = CrimeEngine.PHASE_ALL
+    out_of_scope_phases = ["interventions (family / social / welfare)", "find_job", "let_migrants_in", "return_kids"]
+    # the phases of step() besides the crime path that run on the device (CrimeEngine.PHASE_*): on the yearly
+    # ticks graduate_and_enter_jobmarket and the update_unemployment_status loop (PHASE_LABOUR, model.py:251-256); every tick
+    # wedding, retire_persons, make_baby, remove_excess_friends, remove_excess_professional_links, make_friends,
+    # make_people_die, in the reference's order (model.py:271-284).  0 = the crime path alone.
+    device_phases: int = CrimeEngine.PHASE_EVERY
 
     def __init__(self, seed: int = int.from_bytes(os.urandom(4), sys.byteorder), collect_agents: bool = False) -> None:
         self.seed: int = seed
@@ -356,6 +358,15 @@ class ProtonOC:
         self.num_co_offenders_dist = [list(r) for r in tables.NUM_CO_OFFENDERS_DIST]
         self.male_punishment_length = [[r[0], r[2]] for r in tables.CONVICTION_LENGTH]
         self.female_punishment_length = [[r[0], r[1]] for r in tables.CONVICTION_LENGTH]
+        # tables of the yearly labour-status block (model.py:166-169, 180-183; education_levels: enter and escape age per level,
+        # model.py:953-965 without the school counts)
+        self.education_levels: Dict = {k: [v[0], v[1]] for k, v in tables.EDUCATION_LEVELS.items()}
+        self.work_status_by_edu_lvl = {k: {m: [list(r) for r in rows] for m, rows in d.items()}
+                                       for k, d in tables.WORK_STATUS_BY_EDU_LVL.items()}
+        self.wealth_quintile_by_work_status = {k: {m: [list(r) for r in rows] for m, rows in d.items()}
+                                               for k, d in tables.WEALTH_QUINTILE_BY_WORK_STATUS.items()}
+        self.labour_status_by_age_and_sex = {m: dict(d) for m, d in tables.LABOUR_STATUS_BY_AGE_AND_SEX.items()}
+        self.labour_status_range = {m: dict(d) for m, d in tables.LABOUR_STATUS_RANGE.items()}
         # ---- everything below is implementation state (not model attributes)
         self._st: Dict[str, np.ndarray] = {k: np.zeros(0, dt) for k, dt in _COLS.items()}
         self._adj: List[List[set]] = [[] for _ in LAYER_NAMES]
@@ -470,6 +481,13 @@ class ProtonOC:
                            co_offenders=self.num_co_offenders_dist,
                            conviction=[(m[0], f[1], m[1]) for m, f in zip(self.male_punishment_length, self.female_punishment_length)])
 
+    def _labour(self):
+        """Tables of the yearly labour-status block from the model's own attributes (model.py:166-169, 180-183, 953-965)."""
+        return make_labour(education_levels={int(k): (int(v[0]), int(v[1])) for k, v in self.education_levels.items()},
+                           work_status=self.work_status_by_edu_lvl, wealth_quintile=self.wealth_quintile_by_work_status,
+                           labour_status=self.labour_status_by_age_and_sex,
+                           range_ages={k: sorted(v) for k, v in self.labour_status_range.items()})
+
     def _engine_ready(self) -> CrimeEngine:
         """Upload the host state if it changed; (re)create the engine when capacities are exceeded."""
         if self._dirty or self._engine is None:
@@ -487,9 +505,11 @@ class ProtonOC:
             e.set_params(self._params())
             e.set_demography(make_demography(self.nat_propensity_m, self.nat_propensity_sigma, retirement_age=self.retirement_age,
                                              number_weddings_mean=getattr(self, "number_weddings_mean", None)))
+            e.set_labour(self._labour())
             e.upload_state(0, st)
             if "number_of_children" in st:
                 e.upload_children(0, st["number_of_children"])
+            e.upload_education(0, st["max_education_level"], st["school_level"])
             e.set_crime_multiplier(float(self.crime_multiplier))
             self._dirty = False
         else:
@@ -507,6 +527,7 @@ class ProtonOC:
         retired[:len(self._st["retired"])] = self._st["retired"][:n]
         st["retired"] = retired | ((st["age"] >= self.retirement_age) & (st["alive"] > 0)).astype(retired.dtype)
         st["number_of_children"] = self._engine.download_children(0)
+        st["max_education_level"], st["school_level"] = self._engine.download_education(0)
         self.load_state(st)
         self._dirty = False
 
@@ -613,6 +634,9 @@ class ProtonOC:
         if (self.tick % self.ticks_per_year) == 0 or self.tick == 1:
             self.calculate_criminal_tendency()
             self.calculate_crime_multiplier()
+            if self.device_phases & CrimeEngine.PHASE_LABOUR:                                          # model.py:251-256
+                self._engine_ready().run_phase(CrimeEngine.PHASE_LABOUR, self.tick, [self._philox_key])
+                self._host_stale = True
         if self.device_phases & CrimeEngine.PHASE_WEDDING:                                             # model.py:271
             self._engine_ready().run_phase(CrimeEngine.PHASE_WEDDING, self.tick, [self._philox_key])
             self._host_stale = True

@@ -10,7 +10,7 @@ from typing import Dict, Iterable, Optional
 import numpy as np
 
 from . import tables
-from ._cabi import MAX_CELLS, MAX_TAB, Demography, Params
+from ._cabi import MAX_CELLS, MAX_TAB, Demography, Labour, Params
 
 # the model attributes the hot path reads (model.py:108-134, 82-83) with the reference defaults
 HOT_PATH_DEFAULTS = dict(
@@ -99,3 +99,42 @@ def make_demography(nat_propensity_m: float = 1.0, nat_propensity_sigma: float =
     d.retirement_age = int(retirement_age)   # model.py:121
     d.weddings_mean = float(tables.NUMBER_WEDDINGS_MEAN if number_weddings_mean is None else number_weddings_mean)   # model.py:184-186
     return d
+
+
+def fill_labour(lb, education_levels=None, work_status=None, wealth_quintile=None, labour_status=None, range_ages=None):
+    """Fill a poc_labour-shaped ctypes struct (the oracle's mirror has the same layout).  Tables as the reference holds them:
+    education_levels {level: (enter age, escape age)} (model.py:953-965), work_status {education level: {male: [[status,
+    rate], ...]}} (model.py:166-167), wealth_quintile {work status: {male: [[wealth, rate], ...]}} (:168-169), labour_status
+    {male: {age: share}} (:180-181), range_ages {male: [ages]} (:182-183); defaults: the reference's Palermo tables."""
+    education_levels = education_levels if education_levels is not None else tables.EDUCATION_LEVELS
+    work_status = work_status if work_status is not None else tables.WORK_STATUS_BY_EDU_LVL
+    wealth_quintile = wealth_quintile if wealth_quintile is not None else tables.WEALTH_QUINTILE_BY_WORK_STATUS
+    labour_status = labour_status if labour_status is not None else tables.LABOUR_STATUS_BY_AGE_AND_SEX
+    range_ages = range_ages if range_ages is not None else tables.LABOUR_STATUS_RANGE_AGES
+    if not education_levels or sorted(education_levels) != list(range(1, len(education_levels) + 1)) or len(education_levels) > 7:
+        raise ValueError("education levels must be numbered 1..n, n <= 7")
+    lb.n_levels = len(education_levels)
+    lb.primary_age = int(education_levels[1][0])
+    for lv, row in education_levels.items():
+        lb.end_age[lv] = int(row[1])
+    for tab, n_, val_, cdf_ in ((work_status, lb.work_n, lb.work_val, lb.work_cdf),
+                                (wealth_quintile, lb.wealth_n, lb.wealth_val, lb.wealth_cdf)):
+        for key, by_sex in tab.items():
+            for male, rows in by_sex.items():
+                if not 0 <= int(key) < 8 or len(rows) > 8:
+                    raise ValueError("table too large for poc_labour")
+                cdf = choice_cdf([r[-1] for r in rows])          # extra.pick_from_pair_list: weighted_one_of over the rates
+                n_[int(key)][int(bool(male))] = len(rows)
+                for i, r in enumerate(rows):
+                    val_[int(key)][int(bool(male))][i] = int(r[0])
+                    cdf_[int(key)][int(bool(male))][i] = float(cdf[i])
+    for male in (0, 1):
+        for a in range(128):
+            lb.inactive[male][a] = float(labour_status[bool(male)].get(a, -1.0))   # no row: the reference raises KeyError
+            lb.range_age[male][a] = 1 if a in range_ages[bool(male)] else 0
+    return lb
+
+
+def make_labour(**tables_) -> Labour:
+    """poc_labour for CrimeEngine.set_labour (graduate_and_enter_jobmarket + update_unemployment_status on the device)."""
+    return fill_labour(Labour(), **tables_)

@@ -86,6 +86,8 @@ def export_state(model):
         "retired": col(lambda a: bool(a.retired), np.uint8),
         "has_job": col(lambda a: a.my_job is not None, np.uint8),
         "has_school": col(lambda a: a.my_school is not None, np.uint8),
+        "max_education_level": col(lambda a: int(a.max_education_level), np.int8),
+        "school_level": col(lambda a: int(a.my_school.diploma_level) if a.my_school is not None else 0, np.int8),
         "target_of_intervention": col(lambda a: bool(a.target_of_intervention), np.uint8),
         "num_crimes_committed": col(lambda a: int(a.num_crimes_committed), np.int32),
         "num_crimes_committed_this_tick": col(lambda a: int(a.num_crimes_committed_this_tick), np.int32),

@@ -98,6 +98,17 @@ def synthetic_state(n_agents: int, seed: int = 42, template: Optional[Dict[str, 
         edu = np.where(age < 6, 0, np.minimum(rng.integers(0, 5, n), (age // 6))).astype(np.int8)
         wealth = rng.integers(1, 6, n).astype(np.int8)
         retired = (age >= 65).astype(np.uint8)
+    # what graduate_and_enter_jobmarket reads (model.py:1351-1380): the level of the school an agent attends and how far it may go
+    if template is not None and "max_education_level" in template:
+        school_level = np.where(has_school > 0, template["school_level"][pick], 0).astype(np.int8)
+        max_edu = template["max_education_level"][pick].astype(np.int8)
+    else:
+        from . import tables
+        school_level = np.zeros(n, np.int8)
+        for lv, (a0, a1) in tables.EDUCATION_LEVELS.items():
+            school_level[(has_school > 0) & (age >= a0) & (age <= a1 + 1)] = lv
+        has_school = (school_level > 0).astype(np.uint8)   # a student attends a school of some level
+        max_edu = np.maximum(np.maximum(edu, school_level), rng.integers(1, len(tables.EDUCATION_LEVELS) + 1, n)).astype(np.int8)
     order = np.argsort(rng.random(n))  # slots carry no meaning beyond tie-breaks
     propensity = np.exp(nat_propensity_m + nat_propensity_sigma * rng.standard_normal(n))  # model.py:1216
     birth_tick = (0 - age * 12).astype(np.int32)                                            # entities.py:271
@@ -166,7 +177,8 @@ def synthetic_state(n_agents: int, seed: int = 42, template: Optional[Dict[str, 
         "has_job": has_job, "has_school": has_school, "target_of_intervention": np.zeros(n, np.uint8),
         "num_crimes_committed": np.zeros(n, np.int32), "num_crimes_committed_this_tick": np.zeros(n, np.int32),
         "criminal_tendency": np.zeros(n, np.float64), "sentence_countdown": np.zeros(n, np.float64),
-        "new_recruit": np.full(n, -2, np.int32), "arrest_weight": np.zeros(n, np.float64)}
+        "new_recruit": np.full(n, -2, np.int32), "arrest_weight": np.zeros(n, np.float64),
+        "max_education_level": max_edu, "school_level": school_level}
     father = np.full(n, -1, np.int32)
     fm = male[off_s] > 0
     father[off_d[fm]] = off_s[fm]
