@@ -81,6 +81,9 @@ def main(argv):
     if len(argv) > 2 and argv[1] == "pool":   # python -m oracle.make_states pool <variant> <seed> [<seed> ...]
         export_sweep_pool(argv[2], [int(x) for x in argv[3:]])
         return
+    if len(argv) > 1 and argv[1] == "disthot":   # python -m oracle.make_states disthot <agents> <runs> <ticks> <workers>
+        export_distribution_hot(int(argv[2]), int(argv[3]), int(argv[4]), int(argv[5]))
+        return
     if len(argv) > 1 and argv[1] == "edu":   # python -m oracle.make_states edu state_n10000_s42_t13 10000 42 12
         export_education_sidecar(argv[2], int(argv[3]), int(argv[4]), int(argv[5]))
         return
@@ -222,6 +225,52 @@ def export_distribution(name="dist_n1000_s42", n_agents=1000, seed=42, n_runs=40
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **d)
     print("wrote", path)
+
+
+HOT_COLS = ["number_crimes", "current_oc_members", "people_jailed", "current_prisoners", "tot_criminal_link",
+            "number_crimes_committed_of_persons", "crimes_committed_by_oc_this_tick", "big_crime_from_small_fish",
+            "criminal_tendency_mean", "num_crime_committed_sd"]
+
+
+def _hot_run(job):
+    """One continuation of the setup state by the reference with the out-of-scope phases as no-ops (worker process)."""
+    n_agents, seed, j, ticks, want_state = job
+    ref_model, _, _ = H.load_reference()
+    model = ref_model.ProtonOC(seed=seed)
+    model.setup(n_agents)
+    head = None
+    if want_state:
+        head = {"pre_" + k: v for k, v in H.export_state(model).items()}
+        for k in PARAM_KEYS:
+            head["param_" + k] = np.float64(getattr(model, k))
+        head["tick"] = np.int32(model.tick)
+        head["crime_multiplier"] = np.float64(model.crime_multiplier)
+    model.random = np.random.default_rng(1000 + j)
+    for ph in OUT_OF_SCOPE_PHASES:
+        setattr(model, ph, lambda *a, **k: None)
+    rows = []
+    for _ in range(ticks):
+        model.step()
+        rows.append([float(getattr(model, c)) for c in HOT_COLS])
+    print("refhot run", j, rows[-1][:5], flush=True)
+    return j, np.array(rows, dtype=np.float64), head
+
+
+def export_distribution_hot(n_agents, n_runs, ticks, workers, seed=42):
+    """Whole-run distribution fixture at the sizes the path is benchmarked at (north-star check 2): `n_runs` continuations of
+    ONE reference setup state by the reference's own code for exactly the crime path (`refhot_*`, like export_distribution),
+    one process per run because a 10,000-agent tick of the reference takes seconds."""
+    import multiprocessing as mp
+    jobs = [(n_agents, seed, j, ticks, j == 0) for j in range(n_runs)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = sorted(pool.map(_hot_run, jobs, chunksize=1), key=lambda r: r[0])
+    d = dict(res[0][2])
+    arr = np.array([r[1] for r in res])
+    for i, col in enumerate(HOT_COLS):
+        d["refhot_" + col] = arr[:, :, i]
+    path = os.path.join(OUT, "dist_n%d_s%d.npz" % (n_agents, seed))
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path))
 
 
 if __name__ == "__main__":

@@ -930,7 +930,7 @@ static int launch_phases(poc_ctx *ctx, const DevCtx &D, cudaStream_t s, int mask
     if (mask & POC_PHASE_LABOUR) {   // model.py:251-256 (after the tendencies and the multiplier of a yearly tick)
         if (!ctx->labour_set) return fail(ctx, POC_ERR_STATE, "POC_PHASE_LABOUR requested before poc_set_labour");
         Timed t(ctx, TM_OTHER, s);
-        k_labour<<<dim3((n + 255) / 256, D.Rg), 256, 0, s>>>(D, force_labour);
+        k_labour<<<dim3(std::min((n + 255) / 256, 4), D.Rg), 256, 0, s>>>(D, force_labour);
     }
     if (mask & POC_PHASE_WEDDING) {   // model.py:271 (before the crimes of the tick)
         Timed t(ctx, TM_OTHER, s);

@@ -570,50 +570,55 @@ __device__ __forceinline__ int pick_pair(const int *val, const double *cdf, int 
     return val[i < n ? i : n - 1];
 }
 __global__ void __launch_bounds__(256) k_labour(DevCtx C, int force) {
-    const int r = C.r0 + blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = C.r0 + blockIdx.y;
     const int tick = C.ti[C.grp].tick;
     const poc_params &P = C.params[r];
     if (!force && !((tick % P.ticks_per_year) == 0 || tick == 1)) return;   // model.py:248
-    if (a >= C.n_agents[r]) return;
+    const int n = C.n_agents[r];
     uint32_t *attr = RP(C.attr, r, C.Ncap);
-    const uint32_t x = attr[a];
-    if (!(x & F_ALIVE)) return;
+    uint8_t *e2 = RP(C.edu2, r, C.Ncap);
+    const int32_t *birth = RP(C.birth, r, C.Ncap);
     const DevLabour &L = *C.labour;
     const unsigned long long key = C.philox_key[r];
-    uint8_t *e2 = RP(C.edu2, r, C.Ncap);
-    const unsigned ed = e2[a];
-    const int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, maxedu = (int)(ed & 15u);
-    int edu = attr_edu(x), job = attr_job(x), wl = attr_wealth(x), slv = (int)(ed >> 4);
-    bool school = (x & F_HASSCHOOL) != 0;
-    // model.py:1356-1360: children of primary age who never went to school enrol at level 1
-    if (edu == 0 && age == L.primary_age && !school) { school = true; slv = 1; }
-    // :1361-1380: who is one year past the last age of the own school graduates
-    const int lv = school ? slv : 0;
-    if (lv >= 1 && lv <= L.n_levels && age == L.end_age[lv] + 1) {
-        school = false; slv = 0;   // leave_school
-        edu = lv;
-        if (lv + 1 <= L.n_levels && lv + 1 <= maxedu) { school = true; slv = lv + 1; }
-        else {
-            double u0, u1;
-            philox_u2(key, tick, ST_GRAD, a, u0, u1);
-            const double u2 = philox_u1s(key, tick, ST_GRAD, a, 1);
-            if (L.work_n[lv][male] > 0) job = pick_pair(L.work_val[lv][male], L.work_cdf[lv][male], L.work_n[lv][male], u0);
-            if (job >= 0 && job < 8 && L.wealth_n[job][male] > 0)
-                wl = pick_pair(L.wealth_val[job][male], L.wealth_cdf[job][male], L.wealth_n[job][male], u1);
-            if (age > 14 && age < C.demog->retirement_age && job == 1 && age < 128 && u2 < L.inactive[male][age]) job = 0;
+    const int retirement_age = C.demog->retirement_age;
+    // a few blocks per replica stride over the agents: eleven launches of twelve find nothing to do and should cost nothing
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const uint32_t x = attr[a];
+        if (!(x & F_ALIVE)) continue;
+        const unsigned ed = e2[a];
+        const int age = attr_age(x), male = (x & F_MALE) ? 1 : 0, maxedu = (int)(ed & 15u);
+        int edu = attr_edu(x), job = attr_job(x), wl = attr_wealth(x), slv = (int)(ed >> 4);
+        bool school = (x & F_HASSCHOOL) != 0;
+        // model.py:1356-1360: children of primary age who never went to school enrol at level 1
+        if (edu == 0 && age == L.primary_age && !school) { school = true; slv = 1; }
+        // :1361-1380: who is one year past the last age of the own school graduates
+        const int lv = school ? slv : 0;
+        if (lv >= 1 && lv <= L.n_levels && age == L.end_age[lv] + 1) {
+            school = false; slv = 0;   // leave_school
+            edu = lv;
+            if (lv + 1 <= L.n_levels && lv + 1 <= maxedu) { school = true; slv = lv + 1; }
+            else {
+                double u0, u1;
+                philox_u2(key, tick, ST_GRAD, a, u0, u1);
+                const double u2 = philox_u1s(key, tick, ST_GRAD, a, 1);
+                if (L.work_n[lv][male] > 0) job = pick_pair(L.work_val[lv][male], L.work_cdf[lv][male], L.work_n[lv][male], u0);
+                if (job >= 0 && job < 8 && L.wealth_n[job][male] > 0)
+                    wl = pick_pair(L.wealth_val[job][male], L.wealth_cdf[job][male], L.wealth_n[job][male], u1);
+                if (age > 14 && age < retirement_age && job == 1 && age < 128 && u2 < L.inactive[male][age]) job = 0;
+            }
         }
+        // model.py:252-256: the not employed draw their status again when they enter an age range of labour_status_range
+        if (job < 2 && ((tick - birth[a]) % P.ticks_per_year) == 0 && age < 128 && L.range_age[male][age]) {
+            double u, u_;
+            philox_u2(key, tick, ST_UNEMP, a, u, u_);
+            job = (u < L.inactive[male][age]) ? 0 : 1;   // entities.py:410-411
+        }
+        const uint32_t y = (x & ~(F_HASSCHOOL | 0x0fff0000u)) | (school ? F_HASSCHOOL : 0u) | ((uint32_t)(job & 15) << 16) |
+                           ((uint32_t)(edu & 15) << 20) | ((uint32_t)(wl & 15) << 24);
+        if (y != x) attr[a] = y;
+        const unsigned ed2 = (unsigned)maxedu | ((unsigned)slv << 4);
+        if (ed2 != ed) e2[a] = (uint8_t)ed2;
     }
-    // model.py:252-256: the not employed draw their status again when they enter an age range of labour_status_range
-    if (job < 2 && ((tick - RP(C.birth, r, C.Ncap)[a]) % P.ticks_per_year) == 0 && age < 128 && L.range_age[male][age]) {
-        double u, u_;
-        philox_u2(key, tick, ST_UNEMP, a, u, u_);
-        job = (u < L.inactive[male][age]) ? 0 : 1;   // entities.py:410-411
-    }
-    const uint32_t y = (x & ~(F_HASSCHOOL | 0x0fff0000u)) | (school ? F_HASSCHOOL : 0u) | ((uint32_t)(job & 15) << 16) |
-                       ((uint32_t)(edu & 15) << 20) | ((uint32_t)(wl & 15) << 24);
-    if (y != x) attr[a] = y;
-    const unsigned ed2 = (unsigned)maxedu | ((unsigned)slv << 4);
-    if (ed2 != ed) e2[a] = (uint8_t)ed2;
 }
 
 // remove_excess_friends / remove_excess_professional_links, pass 1 (thread per agent, decisions on the state the phase

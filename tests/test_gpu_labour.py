@@ -179,7 +179,7 @@ def test_eight_phases_in_distribution_against_the_reference(P):
         for t in (11, 35, ticks - 1):
             p = ks_2samp(mine[:, t], ref[:, t]).pvalue
             assert p > 0.005, (col, t, p, mine[:, t].mean(), ref[:, t].mean())
-    # the reference counts dead students too (Person.die never leaves the school): a handful over 60 ticks
+    # (make_people_die takes the dead out of their school, model.py:1597-1598: number_students counts the living on both sides)
     stu = rep[:, -1, names.index("number_students")]
     assert abs(stu.mean() - fx["refdemog_number_students"][:, -1].mean()) <= 4.0
     mine_h, ref_h = np.array(hists, dtype=np.float64), fx["refdemog_final_hists"]

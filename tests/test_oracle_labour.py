@@ -68,7 +68,7 @@ def test_labour_block_in_distribution_against_the_reference(fx):
         born.append(S.demog_counters()["number_born"])
     mine_h, ref_h = np.array(mine_h), fx["refdemog_final_hists"]
     assert ks_2samp(edu_mean, fx["refdemog_education_level_mean"][:, -1]).pvalue > 0.005
-    # the reference counts the dead who were students too (Person.die never leaves the school, entities.py:652-661): a handful
+    # (make_people_die takes the dead out of their school, model.py:1597-1598: number_students counts the living on both sides)
     assert abs(np.mean(students) - fx["refdemog_number_students"][:, -1].mean()) <= 4.0
     assert ks_2samp(born, fx["refdemog_number_born"][:, -1]).pvalue > 0.005
     names = ["job_level", "education_level", "wealth_level", "school_level"]
