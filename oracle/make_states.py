@@ -81,8 +81,14 @@ def main(argv):
     if len(argv) > 2 and argv[1] == "pool":   # python -m oracle.make_states pool <variant> <seed> [<seed> ...]
         export_sweep_pool(argv[2], [int(x) for x in argv[3:]])
         return
-    if len(argv) > 1 and argv[1] == "disthot":   # python -m oracle.make_states disthot <agents> <runs> <ticks> <workers>
-        export_distribution_hot(int(argv[2]), int(argv[3]), int(argv[4]), int(argv[5]))
+    if len(argv) > 1 and argv[1] == "disthot":   # python -m oracle.make_states disthot <agents> <runs> <ticks> <workers> [oc | sample0]
+        kind = argv[6] if len(argv) > 6 else ""
+        ov = {"": None,
+              # many OC members: OC-initiated group crimes, embeddedness-weighted candidates and recruitment every tick
+              "oc": {"num_oc_persons": 300, "num_oc_families": 24},
+              # samples/sample_json.json variant "0": facilitator repression, 80 OC members
+              "sample0": {"intervention": "facilitators", "num_oc_persons": 80, "number_arrests_per_year": 20, "num_oc_families": 16}}[kind]
+        export_distribution_hot(int(argv[2]), int(argv[3]), int(argv[4]), int(argv[5]), overrides=ov, tag="_" + kind if kind else "")
         return
     if len(argv) > 1 and argv[1] == "edu":   # python -m oracle.make_states edu state_n10000_s42_t13 10000 42 12
         export_education_sidecar(argv[2], int(argv[3]), int(argv[4]), int(argv[5]))
@@ -234,9 +240,11 @@ HOT_COLS = ["number_crimes", "current_oc_members", "people_jailed", "current_pri
 
 def _hot_run(job):
     """One continuation of the setup state by the reference with the out-of-scope phases as no-ops (worker process)."""
-    n_agents, seed, j, ticks, want_state = job
+    n_agents, seed, j, ticks, want_state, overrides = job
     ref_model, _, _ = H.load_reference()
     model = ref_model.ProtonOC(seed=seed)
+    if overrides:
+        model.override_dict(overrides)
     model.setup(n_agents)
     head = None
     if want_state:
@@ -256,19 +264,20 @@ def _hot_run(job):
     return j, np.array(rows, dtype=np.float64), head
 
 
-def export_distribution_hot(n_agents, n_runs, ticks, workers, seed=42):
+def export_distribution_hot(n_agents, n_runs, ticks, workers, seed=42, overrides=None, tag=""):
     """Whole-run distribution fixture at the sizes the path is benchmarked at (north-star check 2): `n_runs` continuations of
     ONE reference setup state by the reference's own code for exactly the crime path (`refhot_*`, like export_distribution),
     one process per run because a 10,000-agent tick of the reference takes seconds."""
     import multiprocessing as mp
-    jobs = [(n_agents, seed, j, ticks, j == 0) for j in range(n_runs)]
+    jobs = [(n_agents, seed, j, ticks, j == 0, overrides) for j in range(n_runs)]
     with mp.get_context("fork").Pool(workers) as pool:
         res = sorted(pool.map(_hot_run, jobs, chunksize=1), key=lambda r: r[0])
     d = dict(res[0][2])
     arr = np.array([r[1] for r in res])
     for i, col in enumerate(HOT_COLS):
         d["refhot_" + col] = arr[:, :, i]
-    path = os.path.join(OUT, "dist_n%d_s%d.npz" % (n_agents, seed))
+    d["overrides_json"] = np.array(json.dumps(overrides or {}))
+    path = os.path.join(OUT, "dist_n%d_s%d%s.npz" % (n_agents, seed, tag))
     np.savez_compressed(path, **d)
     print("wrote", path, os.path.getsize(path))
 

@@ -47,6 +47,17 @@ def test_labour_tables_match_the_reference_layout():
     assert a.work_cdf[1][0][0] == 1.0
 
 
+def test_labour_tables_are_validated():
+    import pyproton_oc_b200 as P
+    with pytest.raises(ValueError):
+        P.make_labour(education_levels={1: (6, 10), 3: (14, 18)})           # levels must be numbered 1..n
+    with pytest.raises(ValueError):
+        P.make_labour(work_status={9: {True: [[1, 1.0]], False: [[1, 1.0]]}})   # education level past the table
+    lb = P.make_labour(education_levels={1: (5, 9), 2: (10, 14)}, range_ages={True: [20], False: [30]})
+    assert lb.n_levels == 2 and lb.primary_age == 5 and list(lb.end_age)[:3] == [0, 9, 14]
+    assert lb.range_age[1][20] == 1 and lb.range_age[0][30] == 1 and lb.range_age[0][20] == 0
+
+
 def test_labour_block_in_distribution_against_the_reference(fx):
     st, prm = U.pre_state(fx), U.fixture_params(fx)
     runs, ticks = fx["refdemog_number_crimes"].shape

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--warm-ticks", type=int, default=0, help="ticks run before the measured ones (state ages)")
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--repeat", type=int, default=1, help="repeat upload+run and report the fastest")
-    ap.add_argument("--phases", type=int, default=0, help="device phases of step() to run every tick (CrimeEngine.PHASE_*, 63 = all six)")
+    ap.add_argument("--phases", type=int, default=0, help="device phases of step() to run (CrimeEngine.PHASE_*: 127 = the seven of every tick, 255 = + the yearly labour-status block)")
     ap.add_argument("--synthetic", type=int, default=0, help="use a synthetic population of this many agents (config 4) instead of the bench workload")
     args = ap.parse_args()
     import bench
@@ -41,13 +41,21 @@ def main():
     E.set_params(pkg.make_params(prm))
     if args.phases:
         E.set_demography(pkg.make_demography())
+        if args.phases & E.PHASE_LABOUR:
+            E.set_labour(pkg.make_labour())
         E.set_phases(args.phases)
     keys = [r * 7919 + 17 for r in range(args.replicas)]
+
+    def upload(r):
+        E.upload_state(r, st)
+        E.set_crime_multiplier(mult, r)
+        if (args.phases & E.PHASE_LABOUR) and "max_education_level" in st:
+            E.upload_education(r, st["max_education_level"], st["school_level"])
+
     best = None
     for rep_i in range(args.repeat - 1):
         for r in range(args.replicas):
-            E.upload_state(r, st)
-            E.set_crime_multiplier(mult, r)
+            upload(r)
         E.sync(); E.marker(0)
         E.run_ticks(tick0, args.ticks, keys, reporters=False)
         E.marker(1); E.sync()
@@ -57,8 +65,7 @@ def main():
         print("device time, best of %d: %.2f ms (%.1f us/tick, %.1f M agent-ticks/s)" % (
             args.repeat - 1, best, 1e3 * best / args.ticks, 1e-6 * int(st["alive"].sum()) * args.ticks * args.replicas / (best / 1e3)))
     for r in range(args.replicas):
-        E.upload_state(r, st)
-        E.set_crime_multiplier(mult, r)
+        upload(r)
     if args.warm_ticks:
         E.run_ticks(tick0, args.warm_ticks, keys, reporters=False)
         tick0 += args.warm_ticks
