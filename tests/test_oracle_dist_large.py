@@ -1,7 +1,9 @@
 """North-star check 2 at the sizes the path is benchmarked at: whole-run outputs of the crime path against the UNMODIFIED
 reference, in distribution over seeds.  tests/golden/dist_n3000_s42.npz (24 runs x 96 ticks) and dist_n10000_s42.npz (14 runs x
 36 ticks) hold continuations of ONE reference setup state by the reference's own code for exactly this path (every other phase
-of step() a no-op; oracle/make_states.py disthot).  Here the CPU restatement runs the same number of continuations with its own
+of step() a no-op; oracle/make_states.py disthot); dist_n1000_s42_oc (28 x 60 ticks, 30 OC members among 1,000 agents: the
+OC-initiated branch with its embeddedness-weighted candidates every few ticks) and dist_n3000_s42_sample0 (14 x 36 ticks, the
+samples/sample_json.json variant with facilitator repression and 24 OC members) do the same for two other parameter sets.  Here the CPU restatement runs the same number of continuations with its own
 Philox keys; tests/test_gpu_dist_large.py runs the same keys on the device, where every run equals the restatement's bit for bit
 (tests/test_gpu_parity.py), so the two files pass or fail together."""
 import numpy as np
@@ -11,7 +13,7 @@ from scipy.stats import ks_2samp
 import util as U
 from oracle import oracle_c as O
 
-CASES = [("dist_n3000_s42", 7000), ("dist_n10000_s42", 7100)]
+CASES = [("dist_n3000_s42", 7000), ("dist_n10000_s42", 7100), ("dist_n1000_s42_oc", 7200), ("dist_n3000_s42_sample0", 7300)]
 CHECK_COLS = ["current_oc_members", "people_jailed", "current_prisoners", "tot_criminal_link", "number_crimes_committed_of_persons",
               "big_crime_from_small_fish", "criminal_tendency_mean", "num_crime_committed_sd"]
 
