@@ -90,6 +90,9 @@ def main(argv):
               "sample0": {"intervention": "facilitators", "num_oc_persons": 80, "number_arrests_per_year": 20, "num_oc_families": 16}}[kind]
         export_distribution_hot(int(argv[2]), int(argv[3]), int(argv[4]), int(argv[5]), overrides=ov, tag="_" + kind if kind else "")
         return
+    if len(argv) > 1 and argv[1] == "distdemogpar":   # python -m oracle.make_states distdemogpar <agents> <runs> <ticks> <workers>  (1000 30 60 / 10000 14 36)
+        export_distribution_demog_parallel("distdemog4_n%d_s42" % int(argv[2]), int(argv[2]), int(argv[3]), int(argv[4]), int(argv[5]))
+        return
     if len(argv) > 1 and argv[1] == "edu":   # python -m oracle.make_states edu state_n10000_s42_t13 10000 42 12
         export_education_sidecar(argv[2], int(argv[3]), int(argv[4]), int(argv[5]))
         return
@@ -154,16 +157,20 @@ def export_distribution_demog(name="distdemog_n1000_s42", n_agents=1000, seed=42
     setup state with `n_runs` RNG streams, with its own make_baby / make_friends / make_people_die and the crime path
     active and every other phase of step() replaced by a no-op (`refdemog_*`).  Per tick: DEMOG_COLS."""
     ref_model, ref_entities, _ = H.load_reference()
-    if keep and "retire_persons" in keep:
-        # the yearly hiring loop is written out inside step() (model.py:257-269), not a phase that can be switched off: its
-        # find_job would refill the jobs the retired leave and add professional links; with find_job a no-op the loop does nothing
-        ref_entities.Person.find_job = lambda self: None
+    find_job = ref_entities.Person.find_job
     cols = cols or DEMOG_COLS
     d = {}
     rows_all, hist_all = [], []
     for j in range(n_runs):
+        ref_entities.Person.find_job = find_job   # setup hands out the jobs through it (model.py:1045-1047)
         model = ref_model.ProtonOC(seed=seed)
         model.setup(n_agents)
+        if keep and "retire_persons" in keep:
+            # the yearly hiring loop is written out inside step() (model.py:257-269), not a phase that can be switched off: its
+            # find_job would refill the jobs the retired leave and add professional links; with find_job a no-op AFTER setup the
+            # loop does nothing.  (distdemog2 / distdemog3 were recorded with the no-op in place during setup as well: nobody has
+            # a job in those two fixtures, so they say nothing about the professional layer; distdemog4 does.)
+            ref_entities.Person.find_job = lambda self: None
         if not d:
             st = H.export_state(model)
             d.update({"pre_" + k: v for k, v in st.items()})
@@ -262,6 +269,55 @@ def _hot_run(job):
         rows.append([float(getattr(model, c)) for c in HOT_COLS])
     print("refhot run", j, rows[-1][:5], flush=True)
     return j, np.array(rows, dtype=np.float64), head
+
+
+def _demog_run(job):
+    """One continuation with the phases in `keep` (and the crime path) active, every other phase a no-op (worker process)."""
+    n_agents, seed, j, ticks, want_state, keep, cols = job
+    ref_model, ref_entities, _ = H.load_reference()
+    # a pool worker serves several runs: put the reference's own find_job back for the setup (which hands out the jobs through
+    # it), switch it off AFTERWARDS (see export_distribution_demog)
+    if not hasattr(ref_entities.Person, "_find_job_of_the_reference"):
+        ref_entities.Person._find_job_of_the_reference = ref_entities.Person.find_job
+    ref_entities.Person.find_job = ref_entities.Person._find_job_of_the_reference
+    model = ref_model.ProtonOC(seed=seed)
+    model.setup(n_agents)
+    ref_entities.Person.find_job = lambda self: None
+    head = None
+    if want_state:
+        head = {"pre_" + k: v for k, v in H.export_state(model).items()}
+        for k in PARAM_KEYS:
+            head["param_" + k] = np.float64(getattr(model, k))
+        head["tick"] = np.int32(model.tick)
+        head["crime_multiplier"] = np.float64(model.crime_multiplier)
+    model.random = np.random.default_rng(1000 + j)
+    for ph in OUT_OF_SCOPE_PHASES:
+        if ph not in keep:
+            setattr(model, ph, lambda *a, **k: None)
+    rows = []
+    for _ in range(ticks):
+        model.step()
+        rows.append([float(getattr(model, c)) for c in cols])
+    print("refdemog run", j, rows[-1][:12], flush=True)
+    return j, np.array(rows, dtype=np.float64), _hists(model), head
+
+
+def export_distribution_demog_parallel(name, n_agents, n_runs, ticks, workers, seed=42):
+    """export_distribution_demog with all eight device phases kept, one process per run (10,000-agent reference ticks take seconds)."""
+    import multiprocessing as mp
+    keep = DEMOG_KEEP2 + ["wedding", "graduate_and_enter_jobmarket"]
+    cols = DEMOG_COLS + LABOUR_COLS
+    jobs = [(n_agents, seed, j, ticks, j == 0, keep, cols) for j in range(n_runs)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = sorted(pool.map(_demog_run, jobs, chunksize=1), key=lambda r: r[0])
+    d = dict(res[0][3])
+    arr = np.array([r[1] for r in res])
+    for i, col in enumerate(cols):
+        d["refdemog_" + col] = arr[:, :, i]
+    d["refdemog_final_hists"] = np.array([r[2] for r in res])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path))
 
 
 def export_distribution_hot(n_agents, n_runs, ticks, workers, seed=42, overrides=None, tag=""):

@@ -314,7 +314,9 @@ def test_seven_phases_in_distribution_against_the_reference(P):
 
 
 def test_six_phases_in_distribution_against_the_reference(P):
-    """30 replicas against 30 continuations by the unmodified reference with the six phases active (distdemog2)."""
+    """30 replicas against 30 continuations by the unmodified reference with the six phases active (distdemog2).  Nobody holds
+    a job in this fixture (tests/golden/README.md): `employed` and `tot_professional_link` are 0 on both sides here; the runs
+    with jobs are distdemog4 (tests/test_gpu_labour.py, tests/test_gpu_demog_large.py)."""
     from scipy.stats import ks_2samp
     fx = U.load_fixture(U.GOLDEN + "/distdemog2_n1000_s42.npz")
     st, prm = U.pre_state(fx), U.fixture_params(fx)

@@ -173,7 +173,7 @@ def test_eight_phases_in_distribution_against_the_reference(P):
     assert (cn[:, 9] == 0).all()
     names = list(P.REPORTER_NAMES)
     for col in ["education_level_mean", "current_num_persons", "tot_friendship_link", "number_crimes", "current_oc_members",
-                "number_weddings"]:
+                "number_weddings", "employed", "tot_professional_link"]:   # the last two: retire_persons, remove_excess_professional_links
         mine = rep[:, :, names.index(col)]
         ref = fx["refdemog_" + col]
         for t in (11, 35, ticks - 1):

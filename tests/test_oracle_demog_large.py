@@ -1,0 +1,98 @@
+"""The eight step() phases that exist on the device, at 10,000 agents, against the UNMODIFIED reference in distribution:
+tests/golden/distdemog4_n10000_s42.npz holds 14 continuations (36 ticks) of the reference's own 10,000-agent setup state by the
+reference with graduate_and_enter_jobmarket, update_unemployment_status, wedding, retire_persons, make_baby, remove_excess_*,
+make_friends, make_people_die and the crime path active and every other phase a no-op (oracle/make_states.py distdemogpar).
+The CPU restatement runs as many continuations with its own keys; tests/test_gpu_demog_large.py runs the same keys on the device,
+where every run equals the restatement's bit for bit (tests/test_gpu_labour.py), so the two files pass or fail together."""
+import numpy as np
+from scipy.stats import ks_2samp
+
+import util as U
+from oracle import oracle_c as O
+
+NAME, KEY0 = "distdemog4_n10000_s42", 9600
+CHECKS = (11, 23, 35)
+COLS = ["current_num_persons", "tot_friendship_link", "tot_household_link", "tot_partner_link", "tot_professional_link",
+        "tot_offspring_link", "employed", "number_crimes", "current_oc_members", "number_weddings", "number_born",
+        "number_deceased", "education_level_mean", "number_students"]
+LAYER_OF = {"tot_friendship_link": 5, "tot_household_link": 4, "tot_partner_link": 3, "tot_professional_link": 7,
+            "tot_offspring_link": 1}
+
+
+def hists_of(c, school_level):
+    al = c["alive"] > 0
+    return np.array([np.bincount(c["job_level"][al], minlength=8)[:8], np.bincount(c["education_level"][al], minlength=8)[:8],
+                     np.bincount(c["wealth_level"][al], minlength=8)[:8],
+                     np.bincount(np.where(c["has_school"][al] > 0, school_level[al], 0), minlength=8)[:8]], dtype=np.float64)
+
+
+# Two columns are NOT matched in distribution at this size, and the tests say by how much.  At 10,000 agents the reference's setup
+# leaves 282 agents over the cap of 30 professional links (employers of up to 248 people; at 1,000 agents the largest employer
+# has 12 and nobody is over the cap).  The reference walks them one after the other, so an agent whose colleague has just dropped
+# their link finds itself with less to drop (model.py:646-659); in the batch form (oracle/hotpath.c remove_excess) every agent
+# sheds its whole surplus as counted before the phase, both ends of a pair can each drop other links, and the first tick removes
+# about 900 directed entries (6 %) more.  The gap does not accumulate (933, 837, 769 entries at ticks 12, 24, 36).  Colleagues
+# are candidates of make_friends, so the friendship layer follows at 1 %.  Everything else is KS-matched.
+BOUNDED = {"tot_professional_link": (-0.08, 0.01), "tot_friendship_link": (-0.02, 0.005)}
+
+
+def check_against_reference(fx, mine, hists):
+    """mine[col]: [runs][len(CHECKS)] at the ticks CHECKS; hists: [runs][4][8] after the last tick."""
+    for col, (lo, hi) in BOUNDED.items():
+        ref = fx["refdemog_" + col][:, list(CHECKS)].mean(0)
+        gap = (mine[col].mean(0) - ref) / ref
+        assert (gap >= lo).all() and (gap <= hi).all(), (col, gap)
+        assert abs(gap[-1]) <= abs(gap[0]) + 0.002, (col, gap)   # a one-off of the first tick, not a drift
+    for col in COLS:
+        if col in BOUNDED:
+            continue
+        ref = fx["refdemog_" + col]
+        for ci, t in enumerate(CHECKS):
+            a, b = mine[col][:, ci], ref[:, t]
+            p = ks_2samp(a, b).pvalue
+            assert p > 0.005, (col, t, p, a.mean(), b.mean())
+        if ref[:, -1].mean() > 20:   # means at the end of the run: within four standard errors of the difference plus 2 %
+            a, b = mine[col][:, -1], ref[:, -1]
+            se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+            assert abs(a.mean() - b.mean()) <= 4 * se + 0.02 * b.mean(), (col, a.mean(), b.mean(), se)
+    ref_h = fx["refdemog_final_hists"]
+    for i, nm in enumerate(["job_level", "education_level", "wealth_level", "school_level"]):
+        for v in range(8):
+            a, b = hists[:, i, v], ref_h[:, i, v]
+            if a.mean() < 3 and b.mean() < 3:
+                continue
+            se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+            assert abs(a.mean() - b.mean()) <= 4 * se + 0.02 * b.mean() + 1.0, (nm, v, a.mean(), b.mean(), se)
+
+
+def test_oracle_eight_phases_at_10k_in_distribution_against_the_reference():
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % NAME)
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    runs, ticks = fx["refdemog_number_crimes"].shape
+    assert ticks == CHECKS[-1] + 1
+    P, D, L = O.make_params(prm), O.make_demog(), O.make_labour()
+    mine = {c: np.zeros((runs, len(CHECKS))) for c in COLS}
+    hists = []
+    for r in range(runs):
+        S = O.OracleState(st)
+        S.reserve(len(st["alive"]) + 3000)
+        S.set_children(st["number_of_children"])
+        S.set_labour(L)
+        mult, crimes, done = 0.0, 0, 0
+        for ci, te in enumerate(CHECKS):
+            mult, tot = S.run_ticks_phases(P, D, 255, done + 1, te + 1 - done, KEY0 + r, mult)
+            crimes += int(tot[0])
+            done = te + 1
+            c = S.cols()
+            al = c["alive"] > 0
+            dc = S.demog_counters()
+            vals = {"current_num_persons": al.sum(), "employed": (c["has_job"][al] > 0).sum(), "number_crimes": crimes,
+                    "current_oc_members": c["oc_member"][al].sum(), "number_weddings": dc["number_weddings"],
+                    "number_born": dc["number_born"], "number_deceased": dc["number_deceased"],
+                    "education_level_mean": c["education_level"][al].mean(), "number_students": (c["has_school"][al] > 0).sum()}
+            for k, l in LAYER_OF.items():
+                vals[k] = np.diff(S.layer(l)[0])[al].sum()
+            for k in COLS:
+                mine[k][r, ci] = vals[k]
+        hists.append(hists_of(c, S.education()[1]))
+    check_against_reference(fx, mine, np.array(hists))

@@ -63,7 +63,7 @@ def test_labour_block_in_distribution_against_the_reference(fx):
     runs, ticks = fx["refdemog_number_crimes"].shape
     assert ticks == 60 and "max_education_level" in st
     P, D, L = O.make_params(prm), O.make_demog(), O.make_labour()
-    mine_h, edu_mean, students, born = [], [], [], []
+    mine_h, edu_mean, students, born, employed, prof = [], [], [], [], [], []
     n_runs = 16
     for j in range(n_runs):
         S = O.OracleState(st)
@@ -77,7 +77,14 @@ def test_labour_block_in_distribution_against_the_reference(fx):
         edu_mean.append(c["education_level"][al].mean())
         students.append(int((c["has_school"][al] > 0).sum()))
         born.append(S.demog_counters()["number_born"])
+        employed.append(int((c["has_job"][al] > 0).sum()))
+        prof.append(int(np.diff(S.layer(7)[0])[al].sum()))
     mine_h, ref_h = np.array(mine_h), fx["refdemog_final_hists"]
+    # people hold jobs in this fixture (find_job is neutralised after setup, not before): retire_persons and
+    # remove_excess_professional_links move these two columns
+    assert fx["refdemog_employed"][:, 0].mean() > 100 and fx["refdemog_tot_professional_link"][:, 0].mean() > 300
+    assert ks_2samp(employed, fx["refdemog_employed"][:, -1]).pvalue > 0.005
+    assert ks_2samp(prof, fx["refdemog_tot_professional_link"][:, -1]).pvalue > 0.005
     assert ks_2samp(edu_mean, fx["refdemog_education_level_mean"][:, -1]).pvalue > 0.005
     # (make_people_die takes the dead out of their school, model.py:1597-1598: number_students counts the living on both sides)
     assert abs(np.mean(students) - fx["refdemog_number_students"][:, -1].mean()) <= 4.0
