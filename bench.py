@@ -22,6 +22,9 @@ reporter rows.
             pinned host memory, the run, download of the reporter rows and of the agent columns
   roofline  dominant kernel class (and `roofline_search` for the accomplice search): algorithmic bytes /
             CUDA-event launch time vs the measured HBM peak
+  with_step_phases  the headline batch again with the eight phases of step() that exist on the device switched on (the yearly
+            labour-status block; wedding, retire_persons, make_baby, remove_excess_*, make_friends, make_people_die every tick);
+            measured last, a failure there is reported in the line instead of losing the figures above
   cpu_baseline  the UNMODIFIED reference (baseline/_ref through oracle/refshim) on one host core, a bounded sample,
             with the C restatement (oracle/hotpath.c) beside it (`port`)
 
