@@ -190,3 +190,33 @@ def test_eight_phases_in_distribution_against_the_reference(P):
                 continue
             se = np.sqrt(a.var() / len(a) + b.var() / len(b))
             assert abs(a.mean() - b.mean()) <= 4 * se + 0.03 * b.mean() + 1.0, (nm, v, a.mean(), b.mean(), se)
+
+
+def test_full_length_eight_phase_run_of_the_bench_state_matches_the_oracle(P, O):
+    """The run bench.py times as `with_step_phases`, one replica of it: the reference's 10,000-agent state at tick 13 (education
+    columns from the _edu sidecar), 480 ticks with all eight device phases, against the CPU restatement -- whole state."""
+    fx = U.load_fixture(U.GOLDEN + "/state_n10000_s42_t13.npz")
+    st, prm = U.pre_state(fx), U.fixture_params(fx)
+    st.update(U.pre_state(U.load_fixture(U.GOLDEN + "/state_n10000_s42_t13_edu.npz")))
+    tick0, mult0, key, ticks = int(fx["tick"]), float(fx["crime_multiplier"]), 17, 480
+    n, stat, crim = P.CrimeEngine.capacity_for([st], 160000)
+    with P.CrimeEngine(1, n + 3000, stat + 100000, crim) as E:
+        E.set_params(P.make_params(prm))
+        E.set_demography(P.make_demography())
+        E.set_labour(P.make_labour())
+        E.set_phases(E.PHASE_EVERY)
+        E.upload_state(0, st)
+        E.upload_education(0, st["max_education_level"], st["school_level"])
+        E.set_crime_multiplier(mult0)
+        rep = E.run_ticks(tick0, ticks, [key])
+        cn, _ = E.counters()
+        assert cn[0, 9] == 0
+        S = O.OracleState(st)
+        S.reserve(len(st["alive"]) + 3000)
+        S.set_labour(O.make_labour())
+        mult, tot = S.run_ticks_phases(O.make_params(prm), O.make_demog(), 255, tick0, ticks, key, mult0)
+        assert_equal(E, 0, S, "10,000 agents, 480 ticks, eight phases")
+        assert_education_equal(E, 0, S, "10,000 agents, 480 ticks")
+        dc = S.demog_counters()
+        assert rep[0, -1, 0] == tot[0] and cn[0, 16] == dc["number_deceased"] and cn[0, 17] == dc["number_born"]
+        assert dc["number_deceased"] > 5000 and dc["number_born"] > 500   # four decades: most of the initial population is gone
