@@ -217,6 +217,8 @@ def lib():
         L.orc_labour_yearly.restype = C.c_int32
         L.orc_labour_yearly.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_uint64]
         assert L.orc_sizeof_labour() == C.sizeof(Labour)
+        L.orc_remove_excess_diagnostic.restype = C.c_int32
+        L.orc_remove_excess_diagnostic.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
         L.orc_run_ticks_phases.restype = C.c_int32
         L.orc_run_ticks_phases.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Demog), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_uint64, C.POINTER(C.c_double), C.c_void_p]
@@ -392,6 +394,11 @@ class OracleState:
         if r < 0:
             raise RuntimeError("oracle: set_labour first")
         return r % 65536, r // 65536
+
+    def remove_excess_diagnostic(self, mode: int, tick: int, key: int) -> int:
+        """Both remove_excess phases in the reference's sequential order (mode 0) or as the rounds of its parallel form (mode 1;
+        returns the number of rounds).  Diagnostic: no kernel follows either."""
+        return int(self.L.orc_remove_excess_diagnostic(self.h, mode, tick, key))
 
     def run_ticks_phases(self, p, dm, phases: int, tick0: int, n_ticks: int, philox_key: int, crime_multiplier: float = 0.0):
         """Hot path + the demography phases in `phases` (1 make_baby, 2 make_friends, 4 make_people_die, 8 retire_persons,

@@ -125,3 +125,24 @@ def test_the_deviation_is_the_batch_order_of_remove_excess():
             p = ks_2samp(mine[c][:, ci], ref[:, t]).pvalue
             assert p > 0.01, (c, t, p, mine[c][:, ci].mean(), ref[:, t].mean())
         assert abs(mine[c][:, -1].mean() - ref[:, -1].mean()) <= 0.012 * ref[:, -1].mean(), c
+
+
+def test_rounds_of_non_adjacent_agents_reproduce_the_sequential_order():
+    """The parallel form of the reference's order proposed in DESIGN.md section 9 (an over-cap agent acts in the round in which no
+    lower-slot neighbour of the layer is still over its cap and waiting), against the agent-by-agent walk, in the restatement:
+    the same state, layer for layer.  51 rounds on the first tick after the 10,000-agent setup (the longest chain inside the big
+    employers), none on the ticks after it."""
+    fx = U.load_fixture(U.GOLDEN + "/%s.npz" % NAME)
+    st = U.pre_state(fx)
+    A, B = O.OracleState(st), O.OracleState(st)
+    rounds = []
+    for t in (1, 2, 3):
+        A.begin_tick(t); B.begin_tick(t)
+        A.remove_excess_diagnostic(0, t, 5)
+        rounds.append(B.remove_excess_diagnostic(1, t, 5))
+        for l in (5, 7):
+            for x, y in zip(A.layer(l)[:2], B.layer(l)[:2]):
+                assert np.array_equal(x, y), (t, l)
+    assert 10 < rounds[0] < 250 and rounds[1] == 0 and rounds[2] == 0
+    deg = np.diff(A.layer(7)[0])
+    assert deg.max() <= 30 and len(A.layer(7)[1]) < len(st["col_7"])
